@@ -1,0 +1,145 @@
+/*
+ * subg_b200.h -- C ABI of the B200-native SubGAcc hot path.
+ *
+ * One shared library (surel_plus_b200/_lib/libsubg_b200.so), plain pointers and
+ * sizes, no Python.h and no torch types.  This is the drop-in boundary: the
+ * reference binds this path through a CPython extension module (`subg_acc`,
+ * method table at subg_acc/subg_acc.c:1036-1043) and through SciPy calls in
+ * train.py; each entry point below cites the reference interface it replaces.
+ * INTEGRATION.md shows the ctypes stubs a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; subg_last_error()
+ *     returns the message of the last failure on the calling thread.
+ *         SUBG_ERR_ARG    -> reference raises TypeError      (subg_acc.c:658)
+ *         SUBG_ERR_MEM    -> reference raises MemoryError    (subg_acc.c:688-721)
+ *         SUBG_ERR_ASSERT -> reference raises AssertionError (subg_acc.c:913,1003)
+ *   - "hd" pointers may point to host or device memory; the library inspects
+ *     the pointer (cudaPointerGetAttributes) and copies when needed.  "dev"
+ *     pointers must be device memory on the object's device.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *     Calls are asynchronous with respect to the host except where a size has
+ *     to be returned (documented per function).
+ *   - handles are not thread-safe; distinct handles may be used concurrently.
+ *   - there is NO CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef SUBG_B200_H
+#define SUBG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SUBG_ABI_VERSION 1
+
+#define SUBG_OK          0
+#define SUBG_ERR_ARG    -1
+#define SUBG_ERR_MEM    -2
+#define SUBG_ERR_ASSERT -3
+#define SUBG_ERR_CUDA   -4
+#define SUBG_ERR_UNSUPPORTED -5
+
+/* RNG modes of the walk sampler */
+#define SUBG_RNG_PHILOX 0 /* counter-based Philox4x32-10 keyed by (seed, seed index, walk): fast path, statistical parity */
+#define SUBG_RNG_RAND_R 1 /* replays glibc rand_r exactly as the reference with nthread=1 (bit-exact end to end) */
+#define SUBG_RNG_TRACE  2 /* walks supplied by the caller: int32 [n, num_walks, num_steps] */
+
+/* status bits reported by subg_spg_info */
+#define SUBG_STATUS_BUCKET_OVERFLOW 1u /* a set hit `bucket`; reference prints a warning (subg_acc.c:835-836) */
+#define SUBG_STATUS_DEAD_END        2u /* RAND_R replay met a node without out-neighbours: stream no longer matches */
+
+typedef struct subg_graph subg_graph; /* CSR graph resident in HBM (int64 or int32 rowptr, int32 col) */
+typedef struct subg_spg subg_spg;     /* SpG: CSR-of-sets resident in HBM */
+
+int subg_abi_version(void);
+const char *subg_last_error(void);
+
+/* ---- graph ------------------------------------------------------------------
+ * Replaces the (indptr, indices) numpy arguments of gset_sampler
+ * (subg_acc/subg_acc.c:655-671).  rowptr_is64: 1 -> const int64_t*, 0 -> const
+ * int32_t* (what the reference accepts).  Graphs with E < 2^31 are stored with a
+ * 32-bit rowptr in HBM (8-byte rowptr pair per walk step), larger ones with 64-bit. */
+int subg_graph_create(const void *rowptr_hd, int rowptr_is64, const int32_t *col_hd,
+                      int64_t N, int64_t E, int device, void *stream, subg_graph **out);
+int subg_graph_info(const subg_graph *g, int64_t *N, int64_t *E, int *device);
+void subg_graph_free(subg_graph *g);
+
+/* ---- set sampler + LP encoder + SpG build -----------------------------------
+ * Replaces gset_sampler / C function set_sampler (subg_acc/subg_acc.c:649-1034)
+ * and the CSR construction of subg_matrix (sampler/random_walks.py:79-80).
+ *   seeds_hd   int32[n]  (the reference's `query`; must be distinct for SpJoin use)
+ *   num_walks  M (1..32767), num_steps m >= 1 (walk length; CLI --num_steps - 1)
+ *   bucket     < 0 -> M*m+1 slots per set, else the reference's `bucket` cap
+ *   rng_mode   SUBG_RNG_*; walks_hd only for SUBG_RNG_TRACE
+ * Synchronises the stream (set sizes decide allocations). */
+int subg_gset_sample(const subg_graph *g, const int32_t *seeds_hd, int64_t n,
+                     int num_walks, int num_steps, int bucket, uint64_t seed,
+                     int rng_mode, const int32_t *walks_hd, void *stream, subg_spg **out);
+
+/* n = sets, T = total entries, c = unique LP rows, ncol = num_steps+1 */
+int subg_spg_info(const subg_spg *s, int64_t *n, int64_t *T, int32_t *c, int32_t *ncol,
+                  int32_t *max_set, uint32_t *status, int32_t *value_kind);
+
+/* The reference's return list [nsize, remap, enc(, raw_enc)] (subg_acc.c:1017-1024),
+ * bit-compatible: remap[0] node ids in first-visit order, remap[1] LP-row ids in
+ * first-occurrence order, enc int16[c, ncol].  raw_enc_hd (int16[T, ncol]) may be NULL.
+ * Destinations may be host or device. */
+int subg_spg_export(const subg_spg *s, int32_t *nsize_hd, int32_t *remap_hd,
+                    int16_t *enc_hd, int16_t *raw_enc_hd, void *stream);
+
+/* Device views of the sorted CSR-of-sets (what subg_matrix returns as scipy CSR,
+ * sampler/random_walks.py:79): indptr int64[n+1], indices int32[T] ascending per
+ * row, data int32[T] = LP-row id + 1 (0 = absent) or float64[T] for value SpGs,
+ * slot uint16[T] first-visit rank, enc int16[c, ncol], nsize int32[n].  Any out
+ * pointer may be NULL.  Views stay valid until subg_spg_free. */
+int subg_spg_views(const subg_spg *s, const int64_t **indptr, const int32_t **indices,
+                   const void **data, const uint16_t **slot, const int16_t **enc,
+                   const int32_t **nsize);
+
+/* Wrap an existing CSR (e.g. the scipy matrix produced by the reference's
+ * subg_matrix / topk_ppr_matrix+encoding) as an SpG for the join.
+ * value_kind 0: int32 data (LP pointers), 1: float64 data (PPR / SPD values). */
+int subg_spg_from_csr(const int64_t *indptr_hd, const int32_t *indices_hd, const void *data_hd,
+                      int value_kind, int64_t n_rows, int64_t nnz, int device, void *stream,
+                      subg_spg **out);
+void subg_spg_free(subg_spg *s);
+
+/* ---- SpJoin -------------------------------------------------------------------
+ * Replaces gather / bgather / pgather / hgather (train.py:13-111).
+ * arity 2: edge int64[2,B]  -> segments [all left sets | all right sets]
+ * arity 3: hedge int64[3,B] -> segments [u|w, w|u, v|w, w|v] (train.py:57-68)
+ * plan:  edge_hd is copied to edge_dev (int64[arity*B], may equal edge_hd when it
+ *        is already device memory), indptr_dev int64[nseg+1] receives the segment
+ *        offsets (nseg = 2B or 4B) and *N_out the total number of rows.
+ *        Synchronises the stream (N sizes the caller's output tensor).
+ * run:   out_dev is  int32[N,2]      (enc_table_dev == NULL, int SpG)   -> train.py:82-83
+ *                    float32[N,2,k]  (enc_table_dev float32[c+1,k])     -> train.py:37 encode[xz]
+ *                    float32[N,2]    (float64 SpG, PPR/SPD mode)        -> train.py:39-43
+ *        segid_dev (nullable) int64[N] receives the segment id of every row
+ *        (train.py:27-30 ptr=False, and hgather's `ind`). */
+int subg_spjoin_plan(const subg_spg *s, const int64_t *edge_hd, int64_t B, int arity,
+                     int64_t *edge_dev, int64_t *indptr_dev, int64_t *N_out, void *stream);
+int subg_spjoin_run(const subg_spg *s, const int64_t *edge_dev, int64_t B, int arity,
+                    const int64_t *indptr_dev, const float *enc_table_dev, int k,
+                    void *out_dev, int64_t *segid_dev, void *stream);
+
+/* ---- PPR set sampler -----------------------------------------------------------
+ * Replaces topk_ppr_matrix (sampler/pprgo.py:83-111): ACL forward push per seed
+ * (pprgo.py:9-38), top-k by score, optional normalisation (0 row, 1 sym, 2 col),
+ * result as a float64 value SpG with rows in seed order and ascending node ids.
+ * encoder: 0 none, 1 'PPR' rescale (utils.py:35-36), 2 'SPD' (utils.py:29-34). */
+int subg_ppr_topk(const subg_graph *g, const int32_t *seeds_hd, int64_t n, float alpha,
+                  float eps, int topk, int normalization, int encoder, void *stream,
+                  subg_spg **out);
+
+/* pinned host memory helpers (so numpy arrays handed back by the Python shim can be
+ * filled with asynchronous copies) */
+int subg_host_alloc(void **ptr, int64_t bytes);
+void subg_host_free(void *ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUBG_B200_H */

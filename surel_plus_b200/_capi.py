@@ -1,0 +1,88 @@
+"""ctypes binding of include/subg_b200.h (libsubg_b200.so).
+
+The product path has no CPU fallback: if the CUDA library is missing or no GPU is
+visible, every entry point raises.  Error codes map to the exception classes the
+reference raises (subg_acc/subg_acc.c:658, 688-721, 913, 1003).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libsubg_b200.so")
+
+SUBG_RNG_PHILOX, SUBG_RNG_RAND_R, SUBG_RNG_TRACE = 0, 1, 2
+STATUS_BUCKET_OVERFLOW, STATUS_DEAD_END = 1, 2
+
+#: every symbol include/subg_b200.h declares (checked by tests/test_capi_symbols.py)
+SYMBOLS = [
+    "subg_abi_version", "subg_last_error",
+    "subg_graph_create", "subg_graph_info", "subg_graph_free",
+    "subg_gset_sample", "subg_spg_info", "subg_spg_export", "subg_spg_views",
+    "subg_spg_from_csr", "subg_spg_free",
+    "subg_spjoin_plan", "subg_spjoin_run",
+    "subg_ppr_topk",
+    "subg_host_alloc", "subg_host_free",
+]
+
+_lib = None
+
+
+class SubgUnsupported(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library; raise loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -m surel_plus_b200.build` "
+            "(nvcc, sm_100a).  There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i64, i32, u64 = C.c_void_p, C.c_int64, C.c_int, C.c_uint64
+    L.subg_abi_version.restype = i32
+    L.subg_last_error.restype = C.c_char_p
+    L.subg_graph_create.argtypes = [vp, i32, vp, i64, i64, i32, vp, C.POINTER(vp)]
+    L.subg_graph_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
+    L.subg_graph_free.argtypes = [vp]
+    L.subg_graph_free.restype = None
+    L.subg_gset_sample.argtypes = [vp, vp, i64, i32, i32, i32, u64, i32, vp, vp, C.POINTER(vp)]
+    L.subg_spg_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]
+    L.subg_spg_export.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.subg_spg_views.argtypes = [vp] + [C.POINTER(vp)] * 6
+    L.subg_spg_from_csr.argtypes = [vp, vp, vp, i32, i64, i64, i32, vp, C.POINTER(vp)]
+    L.subg_spg_free.argtypes = [vp]
+    L.subg_spg_free.restype = None
+    L.subg_spjoin_plan.argtypes = [vp, vp, i64, i32, vp, vp, C.POINTER(i64), vp]
+    L.subg_spjoin_run.argtypes = [vp, vp, i64, i32, vp, vp, i32, vp, vp, vp]
+    L.subg_ppr_topk.argtypes = [vp, vp, i64, C.c_float, C.c_float, i32, i32, i32, vp, C.POINTER(vp)]
+    L.subg_host_alloc.argtypes = [C.POINTER(vp), i64]
+    L.subg_host_free.argtypes = [vp]
+    L.subg_host_free.restype = None
+    for name in SYMBOLS:
+        fn = getattr(L, name)
+        if fn.restype is C.c_int and name not in ("subg_abi_version",):
+            fn.restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    """Translate a SUBG_ERR_* code into the reference's exception class."""
+    if rc == 0:
+        return
+    msg = load().subg_last_error().decode("utf-8", "replace")
+    if rc == -1:
+        raise TypeError(msg)
+    if rc == -2:
+        raise MemoryError(msg)
+    if rc == -3:
+        raise AssertionError(msg)
+    if rc == -5:
+        raise SubgUnsupported(msg)
+    raise RuntimeError(f"libsubg_b200: {msg} (rc={rc})")

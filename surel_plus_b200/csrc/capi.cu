@@ -1,0 +1,212 @@
+// extern "C" surface of libsubg_b200.so (declared in include/subg_b200.h).
+#include <algorithm>
+#include <string>
+
+#include "common.cuh"
+
+namespace subg {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string &msg) { g_last_error = msg; }
+int fail(int code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+
+bool is_device_ptr(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, int M, int m, int bucket, uint64_t seed,
+                     int rng_mode, const int32_t *walks_hd, cudaStream_t st, SpG **out);
+int spg_export_impl(const SpG *s, int32_t *nsize_hd, int32_t *remap_hd, int16_t *enc_hd, int16_t *raw_hd,
+                    cudaStream_t st);
+int spg_from_csr_impl(const int64_t *indptr_hd, const int32_t *indices_hd, const void *data_hd, int value_kind,
+                      int64_t n_rows, int64_t nnz, int device, cudaStream_t st, SpG **out);
+void spg_free_impl(SpG *s);
+int spjoin_plan_impl(const SpG *s, const int64_t *edge_hd, int64_t B, int arity, int64_t *edge_dev,
+                     int64_t *indptr_dev, int64_t *N_out, cudaStream_t st);
+int spjoin_run_impl(const SpG *s, const int64_t *edge_dev, int64_t B, int arity, const int64_t *indptr_dev,
+                    const float *enc_table_dev, int k, void *out_dev, int64_t *segid_dev, cudaStream_t st);
+int ppr_topk_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, float alpha, float eps, int topk,
+                  int normalization, int encoder, cudaStream_t st, SpG **out);
+
+__global__ void widen_rowptr_kernel(const int32_t *in, long long *out, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = in[i];
+}
+__global__ void narrow_rowptr_kernel(const long long *in, int32_t *out, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (int32_t)in[i];
+}
+
+static int init_device(int device) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(SUBG_ERR_CUDA, "no CUDA device: libsubg_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= count) return fail(SUBG_ERR_ARG, "bad device index");
+    // keep freed scratch in the stream-ordered pool instead of returning it to the driver
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    return SUBG_OK;
+}
+
+}  // namespace subg
+
+using namespace subg;
+
+extern "C" {
+
+int subg_abi_version(void) { return SUBG_ABI_VERSION; }
+const char *subg_last_error(void) { return g_last_error.c_str(); }
+
+int subg_graph_create(const void *rowptr_hd, int rowptr_is64, const int32_t *col_hd, int64_t N, int64_t E,
+                      int device, void *stream, subg_graph **out) {
+    if (!rowptr_hd || !out || N < 0 || E < 0 || (E > 0 && !col_hd)) return fail(SUBG_ERR_ARG, "Input parsing error.");
+    if (N >= (1ll << 31)) return fail(SUBG_ERR_ARG, "node ids must fit int32");
+    if (int rc = init_device(device)) return rc;
+    DeviceGuard guard(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    Graph *g = new Graph();
+    g->device = device; g->N = N; g->E = E;
+    g->rowptr64 = E >= (1ll << 31);
+    cudaDeviceGetAttribute(&g->num_sms, cudaDevAttrMultiProcessorCount, device);
+    const size_t in_b = rowptr_is64 ? 8 : 4, keep_b = g->rowptr64 ? 8 : 4;
+    void *tmp = nullptr;
+    cudaError_t e = cudaMallocAsync(&g->rowptr, ((size_t)N + 2) * keep_b, st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&g->col, ((size_t)E + 16) * 4, st);
+    if (e == cudaSuccess && E > 0) e = cudaMemcpyAsync(g->col, col_hd, (size_t)E * 4, cudaMemcpyDefault, st);
+    if (e == cudaSuccess) {
+        if (in_b == keep_b) {
+            e = cudaMemcpyAsync(g->rowptr, rowptr_hd, ((size_t)N + 1) * keep_b, cudaMemcpyDefault, st);
+        } else {
+            const void *src = rowptr_hd;
+            if (!is_device_ptr(rowptr_hd)) {
+                e = cudaMallocAsync(&tmp, ((size_t)N + 1) * in_b, st);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(tmp, rowptr_hd, ((size_t)N + 1) * in_b, cudaMemcpyHostToDevice, st);
+                src = tmp;
+            }
+            if (e == cudaSuccess) {
+                const unsigned blocks = (unsigned)std::min<int64_t>((N + 256) / 256, 4 * (int64_t)g->num_sms);
+                if (rowptr_is64) narrow_rowptr_kernel<<<blocks, 256, 0, st>>>((const long long *)src, (int32_t *)g->rowptr, N + 1);
+                else widen_rowptr_kernel<<<blocks, 256, 0, st>>>((const int32_t *)src, (long long *)g->rowptr, N + 1);
+                e = cudaGetLastError();
+            }
+        }
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (tmp) cudaFreeAsync(tmp, st);
+    if (e != cudaSuccess) {
+        if (g->rowptr) cudaFreeAsync(g->rowptr, st);
+        if (g->col) cudaFreeAsync(g->col, st);
+        delete g;
+        return fail(e == cudaErrorMemoryAllocation ? SUBG_ERR_MEM : SUBG_ERR_CUDA, cudaGetErrorString(e));
+    }
+    *out = reinterpret_cast<subg_graph *>(g);
+    return SUBG_OK;
+}
+
+int subg_graph_info(const subg_graph *g_, int64_t *N, int64_t *E, int *device) {
+    const Graph *g = reinterpret_cast<const Graph *>(g_);
+    if (!g) return fail(SUBG_ERR_ARG, "null graph");
+    if (N) *N = g->N;
+    if (E) *E = g->E;
+    if (device) *device = g->device;
+    return SUBG_OK;
+}
+
+void subg_graph_free(subg_graph *g_) {
+    Graph *g = reinterpret_cast<Graph *>(g_);
+    if (!g) return;
+    DeviceGuard guard(g->device);
+    if (g->rowptr) cudaFreeAsync(g->rowptr, 0);
+    if (g->col) cudaFreeAsync(g->col, 0);
+    delete g;
+}
+
+int subg_gset_sample(const subg_graph *g, const int32_t *seeds_hd, int64_t n, int num_walks, int num_steps,
+                     int bucket, uint64_t seed, int rng_mode, const int32_t *walks_hd, void *stream,
+                     subg_spg **out) {
+    return gset_sample_impl(reinterpret_cast<const Graph *>(g), seeds_hd, n, num_walks, num_steps, bucket, seed,
+                            rng_mode, walks_hd, (cudaStream_t)stream, reinterpret_cast<SpG **>(out));
+}
+
+int subg_spg_info(const subg_spg *s_, int64_t *n, int64_t *T, int32_t *c, int32_t *ncol, int32_t *max_set,
+                  uint32_t *status, int32_t *value_kind) {
+    const SpG *s = reinterpret_cast<const SpG *>(s_);
+    if (!s) return fail(SUBG_ERR_ARG, "null SpG");
+    if (n) *n = s->n;
+    if (T) *T = s->T;
+    if (c) *c = s->c;
+    if (ncol) *ncol = s->ncol;
+    if (max_set) *max_set = s->max_set;
+    if (status) *status = s->status;
+    if (value_kind) *value_kind = s->value_kind;
+    return SUBG_OK;
+}
+
+int subg_spg_export(const subg_spg *s, int32_t *nsize_hd, int32_t *remap_hd, int16_t *enc_hd, int16_t *raw_enc_hd,
+                    void *stream) {
+    return spg_export_impl(reinterpret_cast<const SpG *>(s), nsize_hd, remap_hd, enc_hd, raw_enc_hd, (cudaStream_t)stream);
+}
+
+int subg_spg_views(const subg_spg *s_, const int64_t **indptr, const int32_t **indices, const void **data,
+                   const uint16_t **slot, const int16_t **enc, const int32_t **nsize) {
+    const SpG *s = reinterpret_cast<const SpG *>(s_);
+    if (!s) return fail(SUBG_ERR_ARG, "null SpG");
+    if (indptr) *indptr = s->indptr;
+    if (indices) *indices = s->indices;
+    if (data) *data = s->data;
+    if (slot) *slot = s->slot;
+    if (enc) *enc = s->enc;
+    if (nsize) *nsize = s->nsize;
+    return SUBG_OK;
+}
+
+int subg_spg_from_csr(const int64_t *indptr_hd, const int32_t *indices_hd, const void *data_hd, int value_kind,
+                      int64_t n_rows, int64_t nnz, int device, void *stream, subg_spg **out) {
+    if (int rc = init_device(device)) return rc;
+    return spg_from_csr_impl(indptr_hd, indices_hd, data_hd, value_kind, n_rows, nnz, device, (cudaStream_t)stream,
+                             reinterpret_cast<SpG **>(out));
+}
+
+void subg_spg_free(subg_spg *s) { spg_free_impl(reinterpret_cast<SpG *>(s)); }
+
+int subg_spjoin_plan(const subg_spg *s, const int64_t *edge_hd, int64_t B, int arity, int64_t *edge_dev,
+                     int64_t *indptr_dev, int64_t *N_out, void *stream) {
+    return spjoin_plan_impl(reinterpret_cast<const SpG *>(s), edge_hd, B, arity, edge_dev, indptr_dev, N_out,
+                            (cudaStream_t)stream);
+}
+
+int subg_spjoin_run(const subg_spg *s, const int64_t *edge_dev, int64_t B, int arity, const int64_t *indptr_dev,
+                    const float *enc_table_dev, int k, void *out_dev, int64_t *segid_dev, void *stream) {
+    return spjoin_run_impl(reinterpret_cast<const SpG *>(s), edge_dev, B, arity, indptr_dev, enc_table_dev, k, out_dev,
+                           segid_dev, (cudaStream_t)stream);
+}
+
+int subg_ppr_topk(const subg_graph *g, const int32_t *seeds_hd, int64_t n, float alpha, float eps, int topk,
+                  int normalization, int encoder, void *stream, subg_spg **out) {
+    return ppr_topk_impl(reinterpret_cast<const Graph *>(g), seeds_hd, n, alpha, eps, topk, normalization, encoder,
+                         (cudaStream_t)stream, reinterpret_cast<SpG **>(out));
+}
+
+int subg_host_alloc(void **ptr, int64_t bytes) {
+    if (!ptr || bytes < 0) return fail(SUBG_ERR_ARG, "bad host allocation request");
+    cudaError_t e = cudaHostAlloc(ptr, (size_t)(bytes ? bytes : 1), cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail(SUBG_ERR_MEM, cudaGetErrorString(e));
+    return SUBG_OK;
+}
+void subg_host_free(void *ptr) {
+    if (ptr) cudaFreeHost(ptr);
+}
+
+}  // extern "C"

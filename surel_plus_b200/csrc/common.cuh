@@ -1,0 +1,150 @@
+// Shared device/host helpers of the SubGAcc CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/subg_b200.h"
+
+#ifndef __CUDA_ARCH__
+#define SUBG_HOST_ONLY
+#endif
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "surel_plus_b200 targets sm_100a (B200) only"
+#endif
+
+namespace subg {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// ------------------------------------------------------------------ error plumbing
+void set_error(const std::string &msg);
+int fail(int code, const std::string &msg);
+
+#define SUBG_CUDA(call)                                                                      \
+    do {                                                                                     \
+        cudaError_t _e = (call);                                                             \
+        if (_e != cudaSuccess)                                                               \
+            return ::subg::fail(_e == cudaErrorMemoryAllocation ? SUBG_ERR_MEM : SUBG_ERR_CUDA, \
+                                std::string(#call) + ": " + cudaGetErrorString(_e));         \
+    } while (0)
+
+// RAII device guard
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+bool is_device_ptr(const void *p);
+
+// stream-ordered scratch allocation
+template <typename T>
+inline cudaError_t dmalloc(T **p, size_t count, cudaStream_t st) {
+    return cudaMallocAsync((void **)p, (count ? count : 1) * sizeof(T), st);
+}
+inline void dfree(void *p, cudaStream_t st) {
+    if (p) cudaFreeAsync(p, st);
+}
+
+// ------------------------------------------------------------------ object layouts
+struct Graph {
+    int device = 0;
+    int64_t N = 0, E = 0;
+    bool rowptr64 = false;
+    void *rowptr = nullptr;  // int32[N+1] or int64[N+1]
+    int32_t *col = nullptr;  // int32[E]
+    int num_sms = 148;
+};
+
+struct SpG {
+    int device = 0;
+    int64_t n = 0;         // rows (sets), in seed order
+    int64_t T = 0;         // total entries
+    int32_t c = 0;         // unique LP rows (0 for value SpGs)
+    int32_t ncol = 0;      // num_steps + 1
+    int32_t M = 0;
+    int32_t max_set = 0;
+    uint32_t status = 0;
+    int value_kind = 0;    // 0 int32 pointers, 1 float64 values
+    int64_t *indptr = nullptr;   // [n+1]
+    int32_t *indices = nullptr;  // [T] ascending per row
+    void *data = nullptr;        // int32[T] (id+1) or float64[T]
+    uint16_t *slot = nullptr;    // [T] first-visit rank (sampler-built SpGs only)
+    int16_t *enc = nullptr;      // [c, ncol]
+    int32_t *nsize = nullptr;    // [n]
+    int32_t *seeds = nullptr;    // [n] node id of each row
+    int num_sms = 148;
+};
+
+// ------------------------------------------------------------------ device helpers
+#ifdef __CUDACC__
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(FULL, v, d);
+        if (lane_id() >= d) v += t;
+    }
+    return v;
+}
+
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+
+// Philox4x32-10 (Salmon et al., SC'11): counter (c0..c3), key (k0,k1) -> 4 x 32 random bits.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+        uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += W0;
+        k.y += W1;
+    }
+    return c;
+}
+
+// glibc rand_r: one call = three LCG steps producing 11+10+10 bits.
+__device__ __forceinline__ uint32_t lcg(uint32_t s) { return s * 1103515245u + 12345u; }
+__device__ __forceinline__ uint32_t rand_r_dev(uint32_t &state) {
+    uint32_t s = lcg(state);
+    uint32_t out = (s >> 16) & 2047u;
+    s = lcg(s);
+    out = (out << 10) ^ ((s >> 16) & 1023u);
+    s = lcg(s);
+    out = (out << 10) ^ ((s >> 16) & 1023u);
+    state = s;
+    return out;
+}
+// advance an LCG state by `steps` single steps (mod 2^32) in O(log steps)
+__device__ __forceinline__ uint32_t lcg_jump(uint32_t state, uint32_t steps) {
+    uint32_t a = 1103515245u, c = 12345u;  // current power-of-two map  x -> a x + c
+    uint32_t A = 1u, Cc = 0u;              // accumulated map
+    while (steps) {
+        if (steps & 1u) { A = a * A; Cc = a * Cc + c; }
+        c = (a + 1u) * c;
+        a = a * a;
+        steps >>= 1;
+    }
+    return A * state + Cc;
+}
+#endif  // __CUDACC__
+
+}  // namespace subg

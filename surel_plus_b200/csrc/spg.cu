@@ -1,0 +1,440 @@
+// SpG construction on the device: sampler launch, set-size scan, row compaction,
+// first-occurrence ranking of the unique LP rows, export in the reference's layout.
+//
+//   dense compaction            subg_acc/subg_acc.c:848-872  -> compact_rows_kernel
+//   unique ids / enc table      subg_acc/subg_acc.c:957-1000 -> collect/finalize kernels + remap
+//   CSR-of-sets (sorted cols)   sampler/random_walks.py:79-80 -> rows leave the sampler sorted
+//   return list                 subg_acc/subg_acc.c:1017-1024 -> export kernels
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
+
+#include "sampler.cuh"
+#include "scan.cuh"
+
+namespace subg {
+
+// implemented in sampler_k32.cu / sampler_k64.cu
+cudaError_t launch_gset_sample_k32(const SamplerArgs &a, int WT, int MS, int num_sms, cudaStream_t st);
+cudaError_t launch_gset_sample_k64(const SamplerArgs &a, int WT, int MS, int num_sms, cudaStream_t st);
+
+static int ceil_log2(uint64_t x) {
+    int b = 0;
+    while ((1ull << b) < x) b++;
+    return b;
+}
+static int64_t env_i64(const char *name, int64_t dflt) {
+    const char *v = getenv(name);
+    return v ? atoll(v) : dflt;
+}
+
+__global__ void check_seeds_kernel(const int32_t *seeds, int64_t n, int64_t N, uint32_t *bad) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (seeds[i] < 0 || seeds[i] >= N) atomicOr(bad, 1u);
+}
+
+__global__ void fill_u64_kernel(unsigned long long *p, int64_t n, unsigned long long v) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// staging rows (pitch S_pad) -> dense rows at indptr[i]; one warp per row
+__global__ void compact_rows_kernel(const int32_t *st_node, const int32_t *st_prov, const uint16_t *st_rank,
+                                    int S_pad, const int32_t *nsize, const long long *indptr, int64_t n_chunk,
+                                    int32_t *indices, int32_t *data, uint16_t *slot, int32_t *max_set) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    int mx = 0;
+    for (int64_t i = warp; i < n_chunk; i += nwarps) {
+        const int s = nsize[i];
+        const int64_t src = i * (int64_t)S_pad, dst = indptr[i];
+        for (int j = lane; j < s; j += 32) {
+            indices[dst + j] = st_node[src + j];
+            data[dst + j] = st_prov[src + j];
+            slot[dst + j] = st_rank[src + j];
+        }
+        mx = max(mx, s);
+    }
+    if (lane == 0 && mx > 0) atomicMax(max_set, mx);
+}
+
+__global__ void collect_unique_kernel(const unsigned long long *tab_key, const unsigned long long *tab_pos,
+                                      uint32_t cap, unsigned long long *u_pos, uint32_t *u_slot, uint32_t *cnt) {
+    for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < cap; h += gridDim.x * blockDim.x)
+        if (tab_key[h] != kEmptyKey) {
+            const uint32_t j = atomicAdd(cnt, 1u);
+            u_pos[j] = tab_pos[h];
+            u_slot[j] = h;
+        }
+}
+
+// sorted by first occurrence: id j <- table slot; decode the key back into an int16 LP row
+__global__ void finalize_unique_kernel(const uint32_t *sorted_slot, uint32_t c, const unsigned long long *tab_key,
+                                       int M, int m, int SHIFT, int32_t *rank_of_slot, int16_t *enc) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= c) return;
+    const uint32_t h = sorted_slot[j];
+    rank_of_slot[h] = (int32_t)j;
+    const unsigned long long key = tab_key[h];
+    const int ncol = m + 1;
+    const unsigned long long fm = (1ull << SHIFT) - 1ull;
+    enc[(int64_t)j * ncol] = ((key >> (m * SHIFT)) & 1ull) ? (int16_t)M : (int16_t)0;
+    for (int q = 1; q <= m; q++) enc[(int64_t)j * ncol + q] = (int16_t)((key >> (SHIFT * (m - q))) & fm);
+}
+
+__global__ void remap_ids_kernel(int32_t *data, int64_t T, const int32_t *rank_of_slot) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < T; i += (int64_t)gridDim.x * blockDim.x)
+        data[i] = rank_of_slot[data[i]] + 1;
+}
+
+// reference layout: entries of a set in first-visit order, ids without the +1
+__global__ void export_remap_kernel(const long long *indptr, const int32_t *indices, const int32_t *data,
+                                    const uint16_t *slot, int64_t n, int64_t T, int32_t *remap,
+                                    const int16_t *enc, int ncol, int16_t *raw) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < n; i += nwarps) {
+        const int64_t b = indptr[i], e = indptr[i + 1];
+        for (int64_t j = b + lane; j < e; j += 32) {
+            const int64_t d = b + slot[j];
+            const int32_t id = data[j] - 1;
+            remap[d] = indices[j];
+            remap[T + d] = id;
+            if (raw)
+                for (int q = 0; q < ncol; q++) raw[d * ncol + q] = enc[(int64_t)id * ncol + q];
+        }
+    }
+}
+
+static void free_spg_arrays(SpG *s, cudaStream_t st) {
+    dfree(s->indptr, st); dfree(s->indices, st); dfree(s->data, st); dfree(s->slot, st);
+    dfree(s->enc, st); dfree(s->nsize, st); dfree(s->seeds, st);
+    s->indptr = nullptr; s->indices = nullptr; s->data = nullptr; s->slot = nullptr;
+    s->enc = nullptr; s->nsize = nullptr; s->seeds = nullptr;
+}
+
+struct SamplePlan {
+    int WT, MS, OB, SHIFT, stride, S_pad, rec_cap, nbw, fy_cap, smem_per_warp;
+    bool key64;
+};
+
+static int make_plan(const Graph *g, int M, int m, int bucket, SamplePlan *p) {
+    if (M < 1 || M > 32767) return fail(SUBG_ERR_ARG, "num_walks must be in [1, 32767] (int16 landing counts)");
+    if (m < 1) return fail(SUBG_ERR_ARG, "num_steps must be >= 1");
+    if (bucket == 0) return fail(SUBG_ERR_ARG, "bucket must be >= 1 or negative");
+    int shift = 0;
+    while ((M >> shift) != 0) shift++;
+    if ((int64_t)m * shift + 1 > 64)  // subg_acc.c:905-915
+        return fail(SUBG_ERR_ASSERT, "Longer width of type for hasing key needed > INT64.");
+    if (m > 4 || M > 512)
+        return fail(SUBG_ERR_UNSUPPORTED, "this build supports num_steps <= 4 and num_walks <= 512");
+    p->SHIFT = shift;
+    p->MS = m <= 2 ? 2 : 4;
+    const int LS = p->MS == 2 ? 1 : 2;
+    int W = (M + 31) / 32, WT = 1;
+    while (WT < W) WT <<= 1;
+    if (m == p->MS && 32 * WT == M) WT <<= 1;  // keep lane 31's last register free for the root
+    if (WT > 16) return fail(SUBG_ERR_UNSUPPORTED, "num_walks too large for the register-resident sampler");
+    p->WT = WT;
+    const uint32_t max_ord = 1u + ((uint32_t)(M - 1) << LS) + (uint32_t)(m - 1);
+    p->OB = ceil_log2((uint64_t)max_ord + 1);
+    p->key64 = !((uint64_t)g->N <= (1ull << (32 - p->OB)) - 1ull);
+    const int full = M * m + 1;
+    p->stride = bucket < 0 ? full : bucket;
+    const int eff = std::min(p->stride, full);
+    p->S_pad = (eff + 7) & ~7;
+    p->rec_cap = (full + 7) & ~7;
+    p->nbw = (int)((max_ord + 1 + 31) / 32);
+    int fc = 16;
+    while (fc < 2 * M) fc <<= 1;
+    p->fy_cap = fc;
+    const int rec_bytes = p->rec_cap * 14 + p->nbw * 8;
+    const int fy_bytes = 8 * M + 8 * fc;
+    p->smem_per_warp = (std::max(rec_bytes, fy_bytes) + 15) & ~15;
+    return SUBG_OK;
+}
+
+int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, int M, int m, int bucket,
+                     uint64_t seed, int rng_mode, const int32_t *walks_hd, cudaStream_t st, SpG **out) {
+    if (!g || !out || n < 0 || (n > 0 && !seeds_hd)) return fail(SUBG_ERR_ARG, "Input parsing error.");
+    if (rng_mode < 0 || rng_mode > 2) return fail(SUBG_ERR_ARG, "unknown rng_mode");
+    if (rng_mode == SUBG_RNG_TRACE && !walks_hd && n > 0) return fail(SUBG_ERR_ARG, "trace mode needs walks");
+    SamplePlan pl;
+    if (int rc = make_plan(g, M, m, bucket, &pl)) return rc;
+    DeviceGuard guard(g->device);
+
+    SpG *s = new SpG();
+    s->device = g->device; s->n = n; s->ncol = m + 1; s->M = M; s->num_sms = g->num_sms; s->value_kind = 0;
+
+    // everything below that is not part of the SpG is scratch
+    int32_t *d_walks = nullptr, *d_calls = nullptr, *st_node = nullptr, *st_prov = nullptr, *rank_of_slot = nullptr;
+    uint16_t *st_rank = nullptr;
+    long long *call_base = nullptr, *scan_scratch = nullptr;
+    unsigned long long *tab_key = nullptr, *tab_pos = nullptr, *u_pos = nullptr, *u_pos2 = nullptr;
+    uint32_t *u_slot = nullptr, *u_slot2 = nullptr, *d_flags = nullptr;  // [0]=status [1]=tab_count [2]=bad seeds [3]=unique cnt
+    int32_t *d_maxset = nullptr;
+    void *cub_tmp = nullptr;
+    bool walks_owned = false;
+    int rc = SUBG_OK;
+    int64_t cap = 0;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            rc = fail(_e == cudaErrorMemoryAllocation ? SUBG_ERR_MEM : SUBG_ERR_CUDA,              \
+                      std::string(#call) + ": " + cudaGetErrorString(_e));                         \
+            goto done;                                                                             \
+        }                                                                                          \
+    } while (0)
+
+    {
+        CK(dmalloc(&s->seeds, (size_t)n, st));
+        CK(dmalloc(&s->nsize, (size_t)n, st));
+        CK(dmalloc(&s->indptr, (size_t)n + 1, st));
+        CK(dmalloc(&d_flags, 4, st));
+        CK(dmalloc(&d_maxset, 1, st));
+        CK(cudaMemsetAsync(d_flags, 0, 4 * sizeof(uint32_t), st));
+        CK(cudaMemsetAsync(d_maxset, 0, sizeof(int32_t), st));
+        if (n > 0) {
+            CK(cudaMemcpyAsync(s->seeds, seeds_hd, (size_t)n * sizeof(int32_t), cudaMemcpyDefault, st));
+            check_seeds_kernel<<<std::min<int64_t>((n + 255) / 256, 4 * g->num_sms), 256, 0, st>>>(s->seeds, n, g->N, d_flags + 2);
+        }
+        const int nscan = std::max(1, scan_num_blocks(n));
+        CK(dmalloc(&scan_scratch, (size_t)nscan, st));
+
+        if (rng_mode == SUBG_RNG_RAND_R && n > 0) {
+            CK(dmalloc(&d_calls, (size_t)n, st));
+            CK(dmalloc(&call_base, (size_t)n + 1, st));
+            rand_r_calls_kernel<<<std::min<int64_t>((n + 255) / 256, 4 * g->num_sms), 256, 0, st>>>(
+                g->rowptr, g->rowptr64 ? 1 : 0, s->seeds, n, M, m, d_calls);
+            CK(exclusive_scan_i32_i64(d_calls, call_base, n, 0, scan_scratch, st));
+        }
+        if (rng_mode == SUBG_RNG_TRACE && n > 0) {
+            if (is_device_ptr(walks_hd)) d_walks = const_cast<int32_t *>(walks_hd);
+            else {
+                const size_t cnt = (size_t)n * M * m;
+                CK(dmalloc(&d_walks, cnt, st));
+                walks_owned = true;
+                CK(cudaMemcpyAsync(d_walks, walks_hd, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+            }
+        }
+
+        // staging: chunk of seeds x S_pad entries x (node 4B + provisional id 4B + rank 2B)
+        const int64_t budget = env_i64("SUBG_STAGING_BYTES", 6ll << 30);
+        int64_t chunk = std::max<int64_t>(1, budget / ((int64_t)pl.S_pad * 10));
+        chunk = std::min<int64_t>(chunk, std::max<int64_t>(n, 1));
+        CK(dmalloc(&st_node, (size_t)chunk * pl.S_pad, st));
+        CK(dmalloc(&st_prov, (size_t)chunk * pl.S_pad, st));
+        CK(dmalloc(&st_rank, (size_t)chunk * pl.S_pad, st));
+
+        int tab_log2 = (int)env_i64("SUBG_LP_TABLE_LOG2", 20);
+        for (int attempt = 0;; attempt++) {
+            const uint32_t tab_cap = 1u << tab_log2;
+            CK(dmalloc(&tab_key, (size_t)tab_cap, st));
+            CK(dmalloc(&tab_pos, (size_t)tab_cap, st));
+            fill_u64_kernel<<<4 * g->num_sms, 256, 0, st>>>(tab_key, tab_cap, kEmptyKey);
+            fill_u64_kernel<<<4 * g->num_sms, 256, 0, st>>>(tab_pos, tab_cap, ~0ull);
+            CK(cudaMemsetAsync(d_flags, 0, 2 * sizeof(uint32_t), st));
+            CK(cudaMemsetAsync(d_maxset, 0, sizeof(int32_t), st));
+
+            int64_t T = 0;
+            bool table_full = false;
+            for (int64_t base = 0; base < n; base += chunk) {
+                const int64_t nc = std::min(chunk, n - base);
+                SamplerArgs a{};
+                a.rowptr = g->rowptr; a.rowptr64 = g->rowptr64 ? 1 : 0; a.col = g->col;
+                a.seeds = s->seeds + base; a.n_chunk = nc; a.seed_base = base;
+                a.M = M; a.m = m; a.stride = pl.stride; a.OB = pl.OB; a.SHIFT = pl.SHIFT;
+                a.rng_mode = rng_mode; a.rng_lo = (uint32_t)seed; a.rng_hi = (uint32_t)(seed >> 32);
+                a.call_base = (const int64_t *)call_base;
+                a.walks = d_walks ? d_walks + base * (int64_t)M * m : nullptr;
+                a.st_node = st_node; a.st_prov = st_prov; a.st_rank = st_rank; a.S_pad = pl.S_pad;
+                a.nsize = s->nsize + base;
+                a.tab_key = tab_key; a.tab_pos = tab_pos; a.tab_mask = tab_cap - 1;
+                a.tab_count = d_flags + 1; a.status = d_flags;
+                a.rec_cap = pl.rec_cap; a.nbw = pl.nbw; a.fy_cap = pl.fy_cap; a.smem_per_warp = pl.smem_per_warp;
+                CK(pl.key64 ? launch_gset_sample_k64(a, pl.WT, pl.MS, g->num_sms, st)
+                            : launch_gset_sample_k32(a, pl.WT, pl.MS, g->num_sms, st));
+                CK(exclusive_scan_i32_i64(s->nsize + base, (long long *)s->indptr + base, nc, T, scan_scratch, st));
+                long long T_new = 0;
+                uint32_t flags[3];
+                CK(cudaMemcpyAsync(&T_new, s->indptr + base + nc, sizeof(long long), cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                if (flags[2]) { rc = fail(SUBG_ERR_ARG, "query contains node ids outside [0, N)"); goto done; }
+                if (flags[1] > tab_cap / 2 || (flags[0] & kStatusTableFull)) { table_full = true; break; }
+                if (T_new > cap) {  // grow the dense arrays (exact when one chunk covers all seeds)
+                    int64_t want = T_new;
+                    if (base + nc < n) want = std::max<int64_t>(T_new, (int64_t)((double)T_new * n / (base + nc) * 1.05) + 1024);
+                    int32_t *ni = nullptr, *nd = nullptr; uint16_t *ns = nullptr;
+                    CK(dmalloc(&ni, (size_t)want + 16, st));
+                    CK(dmalloc(&nd, (size_t)want + 16, st));
+                    CK(dmalloc(&ns, (size_t)want + 16, st));
+                    if (T > 0) {
+                        CK(cudaMemcpyAsync(ni, s->indices, (size_t)T * 4, cudaMemcpyDeviceToDevice, st));
+                        CK(cudaMemcpyAsync(nd, s->data, (size_t)T * 4, cudaMemcpyDeviceToDevice, st));
+                        CK(cudaMemcpyAsync(ns, s->slot, (size_t)T * 2, cudaMemcpyDeviceToDevice, st));
+                    }
+                    dfree(s->indices, st); dfree(s->data, st); dfree(s->slot, st);
+                    s->indices = ni; s->data = nd; s->slot = ns;
+                    cap = want;
+                }
+                const int64_t cblocks = std::min<int64_t>((nc * 32 + 255) / 256, 8 * (int64_t)g->num_sms);
+                compact_rows_kernel<<<(unsigned)std::max<int64_t>(cblocks, 1), 256, 0, st>>>(
+                    st_node, st_prov, st_rank, pl.S_pad, s->nsize + base, (const long long *)s->indptr + base, nc,
+                    s->indices, (int32_t *)s->data, s->slot, d_maxset);
+                T = T_new;
+            }
+            if (table_full) {
+                dfree(tab_key, st); dfree(tab_pos, st); tab_key = nullptr; tab_pos = nullptr;
+                tab_log2 += 3;
+                if (tab_log2 > 30) { rc = fail(SUBG_ERR_MEM, "LP-row table exceeds 2^30 entries"); goto done; }
+                continue;
+            }
+            if (n == 0) CK(cudaMemsetAsync(s->indptr, 0, sizeof(int64_t), st));
+            s->T = T;
+
+            // ---- unique LP rows in first-occurrence order
+            uint32_t hflags[2];
+            CK(cudaMemcpyAsync(hflags, d_flags, sizeof(hflags), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            s->status = hflags[0] & ~kStatusTableFull;
+            const uint32_t c = hflags[1];
+            s->c = (int32_t)c;
+            CK(dmalloc(&s->enc, (size_t)c * (m + 1), st));
+            if (c > 0) {
+                CK(dmalloc(&u_pos, (size_t)c, st)); CK(dmalloc(&u_pos2, (size_t)c, st));
+                CK(dmalloc(&u_slot, (size_t)c, st)); CK(dmalloc(&u_slot2, (size_t)c, st));
+                CK(dmalloc(&rank_of_slot, (size_t)tab_cap, st));
+                collect_unique_kernel<<<4 * g->num_sms, 256, 0, st>>>(tab_key, tab_pos, tab_cap, u_pos, u_slot, d_flags + 3);
+                size_t tmp_bytes = 0;
+                CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, u_pos, u_pos2, u_slot, u_slot2, (int)c, 0, 64, st));
+                CK(cudaMallocAsync(&cub_tmp, tmp_bytes ? tmp_bytes : 1, st));
+                CK(cub::DeviceRadixSort::SortPairs(cub_tmp, tmp_bytes, u_pos, u_pos2, u_slot, u_slot2, (int)c, 0, 64, st));
+                finalize_unique_kernel<<<(c + 255) / 256, 256, 0, st>>>(u_slot2, c, tab_key, M, m, pl.SHIFT, rank_of_slot, s->enc);
+                if (T > 0) {
+                    const int64_t rb = std::min<int64_t>((T + 255) / 256, 16 * (int64_t)g->num_sms);
+                    remap_ids_kernel<<<(unsigned)rb, 256, 0, st>>>((int32_t *)s->data, T, rank_of_slot);
+                }
+            }
+            int32_t mx = 0;
+            CK(cudaMemcpyAsync(&mx, d_maxset, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            s->max_set = mx;
+            break;
+        }
+        if (!s->indices) {  // n == 0 or all empty: keep valid (padded) arrays
+            CK(dmalloc(&s->indices, 16, st)); CK(dmalloc((int32_t **)&s->data, 16, st)); CK(dmalloc(&s->slot, 16, st));
+        }
+    }
+done:
+#undef CK
+    if (walks_owned) dfree(d_walks, st);
+    dfree(d_calls, st); dfree(call_base, st); dfree(scan_scratch, st);
+    dfree(st_node, st); dfree(st_prov, st); dfree(st_rank, st);
+    dfree(tab_key, st); dfree(tab_pos, st); dfree(u_pos, st); dfree(u_pos2, st);
+    dfree(u_slot, st); dfree(u_slot2, st); dfree(rank_of_slot, st);
+    dfree(d_flags, st); dfree(d_maxset, st); dfree(cub_tmp, st);
+    if (rc != SUBG_OK) {
+        free_spg_arrays(s, st);
+        delete s;
+        return rc;
+    }
+    *out = s;
+    return SUBG_OK;
+}
+
+int spg_export_impl(const SpG *s, int32_t *nsize_hd, int32_t *remap_hd, int16_t *enc_hd, int16_t *raw_hd,
+                    cudaStream_t st) {
+    if (!s) return fail(SUBG_ERR_ARG, "null SpG");
+    if (s->value_kind != 0 || !s->slot) return fail(SUBG_ERR_ARG, "export needs a sampler-built LP SpG");
+    DeviceGuard guard(s->device);
+    const int64_t T = s->T, n = s->n;
+    const int ncol = s->ncol;
+    if (nsize_hd && n > 0)
+        SUBG_CUDA(cudaMemcpyAsync(nsize_hd, s->nsize, (size_t)n * sizeof(int32_t), cudaMemcpyDefault, st));
+    if (enc_hd && s->c > 0)
+        SUBG_CUDA(cudaMemcpyAsync(enc_hd, s->enc, (size_t)s->c * ncol * sizeof(int16_t), cudaMemcpyDefault, st));
+    if ((remap_hd || raw_hd) && T > 0) {
+        int32_t *d_remap = nullptr;
+        int16_t *d_raw = nullptr;
+        const bool remap_dev = remap_hd && is_device_ptr(remap_hd);
+        const bool raw_dev = raw_hd && is_device_ptr(raw_hd);
+        if (remap_dev) d_remap = remap_hd;
+        else SUBG_CUDA(dmalloc(&d_remap, (size_t)2 * T, st));
+        if (raw_hd) {
+            if (raw_dev) d_raw = raw_hd;
+            else SUBG_CUDA(dmalloc(&d_raw, (size_t)T * ncol, st));
+        }
+        const int64_t blocks = std::min<int64_t>((n * 32 + 255) / 256, 8 * (int64_t)s->num_sms);
+        export_remap_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), 256, 0, st>>>(
+            (const long long *)s->indptr, s->indices, (const int32_t *)s->data, s->slot, n, T, d_remap, s->enc, ncol, d_raw);
+        SUBG_CUDA(cudaGetLastError());
+        if (remap_hd && !remap_dev)
+            SUBG_CUDA(cudaMemcpyAsync(remap_hd, d_remap, (size_t)2 * T * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        if (raw_hd && !raw_dev)
+            SUBG_CUDA(cudaMemcpyAsync(raw_hd, d_raw, (size_t)T * ncol * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+        SUBG_CUDA(cudaStreamSynchronize(st));
+        if (!remap_dev) dfree(d_remap, st);
+        if (raw_hd && !raw_dev) dfree(d_raw, st);
+    } else {
+        SUBG_CUDA(cudaStreamSynchronize(st));
+    }
+    return SUBG_OK;
+}
+
+int spg_from_csr_impl(const int64_t *indptr_hd, const int32_t *indices_hd, const void *data_hd, int value_kind,
+                      int64_t n_rows, int64_t nnz, int device, cudaStream_t st, SpG **out) {
+    if (!out || n_rows < 0 || nnz < 0 || !indptr_hd || (nnz > 0 && (!indices_hd || !data_hd)))
+        return fail(SUBG_ERR_ARG, "Input parsing error.");
+    if (value_kind != 0 && value_kind != 1) return fail(SUBG_ERR_ARG, "value_kind must be 0 (int32) or 1 (float64)");
+    DeviceGuard guard(device);
+    SpG *s = new SpG();
+    s->device = device; s->n = n_rows; s->T = nnz; s->value_kind = value_kind;
+    cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, device);
+    const size_t vb = value_kind ? 8 : 4;
+    cudaError_t e = dmalloc(&s->indptr, (size_t)n_rows + 1, st);
+    if (e == cudaSuccess) e = dmalloc(&s->indices, (size_t)nnz + 16, st);
+    if (e == cudaSuccess) e = cudaMallocAsync(&s->data, ((size_t)nnz + 16) * vb, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s->indptr, indptr_hd, ((size_t)n_rows + 1) * 8, cudaMemcpyDefault, st);
+    if (e == cudaSuccess && nnz > 0) e = cudaMemcpyAsync(s->indices, indices_hd, (size_t)nnz * 4, cudaMemcpyDefault, st);
+    if (e == cudaSuccess && nnz > 0) e = cudaMemcpyAsync(s->data, data_hd, (size_t)nnz * vb, cudaMemcpyDefault, st);
+    // max set size (host side when the row pointer is host memory, else via a copy)
+    std::vector<int64_t> hp;
+    const int64_t *hptr = indptr_hd;
+    if (e == cudaSuccess && is_device_ptr(indptr_hd)) {
+        hp.resize((size_t)n_rows + 1);
+        e = cudaMemcpyAsync(hp.data(), indptr_hd, ((size_t)n_rows + 1) * 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        hptr = hp.data();
+    }
+    if (e != cudaSuccess) {
+        free_spg_arrays(s, st);
+        delete s;
+        return fail(e == cudaErrorMemoryAllocation ? SUBG_ERR_MEM : SUBG_ERR_CUDA, cudaGetErrorString(e));
+    }
+    int64_t mx = 0;
+    for (int64_t i = 0; i < n_rows; i++) mx = std::max(mx, hptr[i + 1] - hptr[i]);
+    if (hptr[0] != 0 || hptr[n_rows] != nnz) {
+        free_spg_arrays(s, st);
+        delete s;
+        return fail(SUBG_ERR_ARG, "indptr does not describe nnz entries");
+    }
+    s->max_set = (int32_t)std::min<int64_t>(mx, INT32_MAX);
+    SUBG_CUDA(cudaStreamSynchronize(st));
+    *out = s;
+    return SUBG_OK;
+}
+
+void spg_free_impl(SpG *s) {
+    if (!s) return;
+    DeviceGuard guard(s->device);
+    free_spg_arrays(s, 0);
+    delete s;
+}
+
+}  // namespace subg

@@ -1,0 +1,366 @@
+// SpJoin on the device: outer-join of the sorted sets of a query's endpoints.
+//
+// Replaces (file:line relative to /root/reference)
+//   bgather / gather / pgather   train.py:13-45, 75-111   (pair queries)
+//   hgather                      train.py:48-72           (triplet queries, 4 segments)
+// Row contract (train.py:34-36, 57-68; model.py:76-83): for every segment, the rows of the
+// left set in ascending node id, each row = [value in own set, value in the other set or 0];
+// segments are laid out [all left | all right] (pairs) and [u|w, w|u, v|w, w|v] (triplets).
+//
+// B200 design: one CTA per task (a, b).  The four row slices (ids and values of both sets)
+// are staged in shared memory by 1-D TMA bulk copies (cp.async.bulk, 16-byte aligned windows
+// around the rows) completing on one mbarrier; every element of S_a then does a binary search
+// in S_b, writes its own row, and drops its value at the match position so that the rows of
+// S_b need no second search.  Output rows are written coalesced (8 B per row, or 2k floats
+// per row when the LP table lookup `encode[xz]` of train.py:37 is fused in).
+#include <algorithm>
+
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace subg {
+
+constexpr int kJoinThreads = 128;
+
+struct JoinArgs {
+    const long long *indptr;
+    const int32_t *indices;
+    const void *data;
+    int64_t n_rows;
+    const long long *edge;
+    int64_t B;
+    int arity;
+    const long long *seg_ptr;
+    const float *enc;
+    int k;
+    void *out;
+    long long *segid;
+    int64_t ntask;
+    int cap;  // staged elements per row slice
+};
+
+__device__ __forceinline__ void task_nodes(const JoinArgs &p, int64_t t, int64_t &a, int64_t &b, int64_t &segA,
+                                           int64_t &segB) {
+    if (p.arity == 2) {
+        a = p.edge[t];
+        b = p.edge[p.B + t];
+        segA = t;
+        segB = p.B + t;
+    } else {
+        const bool second = t >= p.B;
+        const int64_t q = second ? t - p.B : t;
+        a = p.edge[(second ? p.B : 0) + q];
+        b = p.edge[2 * p.B + q];
+        segA = (second ? 2 * p.B : 0) + q;
+        segB = (second ? 3 * p.B : p.B) + q;
+    }
+}
+
+// ------------------------------------------------------------------ plan: segment sizes
+__global__ void join_sizes_kernel(const long long *indptr, int64_t n_rows, const long long *edge, int64_t B, int arity,
+                                  int32_t *sizes, uint32_t *bad) {
+    const int64_t nseg = arity == 2 ? 2 * B : 4 * B;
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < nseg; g += (int64_t)gridDim.x * blockDim.x) {
+        int64_t node;
+        if (arity == 2) node = edge[g];
+        else {
+            const int64_t blk = g / B, q = g - blk * B;
+            const int64_t rowsel = blk == 0 ? 0 : (blk == 2 ? 1 : 2);  // u, w, v, w
+            node = edge[rowsel * B + q];
+        }
+        if (node < 0 || node >= n_rows) {
+            atomicOr(bad, 1u);
+            sizes[g] = 0;
+        } else {
+            sizes[g] = (int32_t)(indptr[node + 1] - indptr[node]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ TMA / mbarrier PTX
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk copy global -> shared; both addresses 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <typename V>
+struct ValTraits;
+template <>
+struct ValTraits<int32_t> {
+    static constexpr int align_elems = 4;  // 16 B
+};
+template <>
+struct ValTraits<double> {
+    static constexpr int align_elems = 2;
+};
+
+struct TaskDesc {
+    long long pa, pb;      // row starts
+    int sa, sb;            // set sizes
+    int ia, ib;            // offset of the row inside the staged id window
+    int va, vb;            // same for the value window
+    long long offA, offB;  // output row offsets
+    long long segA, segB;
+};
+
+// ------------------------------------------------------------------ the join kernel
+// MODE 0: int32 [N,2] pointers   MODE 1: float32 [N,2,k] fused table lookup   MODE 2: float32 [N,2] values
+template <typename V, int MODE>
+__global__ void __launch_bounds__(kJoinThreads) spjoin_kernel(const JoinArgs p) {
+    extern __shared__ __align__(128) unsigned char sm[];
+    const int cap = p.cap;
+    int32_t *idA = (int32_t *)sm;
+    int32_t *idB = idA + cap;
+    V *vA = (V *)(idB + cap);
+    V *vB = vA + cap;
+    V *rev = vB + cap;      // value of the S_a member matched at each S_b position (0 = none)
+    V *mat = rev + cap;     // MODE 1 only: value of the S_b member matched by each S_a element
+    __shared__ uint64_t bar;
+    __shared__ TaskDesc td;
+    const V *gdata = (const V *)p.data;
+    constexpr int AE = ValTraits<V>::align_elems;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+
+    for (int64_t t = blockIdx.x; t < p.ntask; t += gridDim.x) {
+        if (threadIdx.x == 0) {
+            int64_t a, b, segA, segB;
+            task_nodes(p, t, a, b, segA, segB);
+            TaskDesc d;
+            d.pa = p.indptr[a]; d.sa = (int)(p.indptr[a + 1] - d.pa);
+            d.pb = p.indptr[b]; d.sb = (int)(p.indptr[b + 1] - d.pb);
+            d.offA = p.seg_ptr[segA]; d.offB = p.seg_ptr[segB];
+            d.segA = segA; d.segB = segB;
+            const long long a0 = d.pa & ~3ll, b0 = d.pb & ~3ll;
+            const long long av0 = d.pa & ~(long long)(AE - 1), bv0 = d.pb & ~(long long)(AE - 1);
+            d.ia = (int)(d.pa - a0); d.ib = (int)(d.pb - b0);
+            d.va = (int)(d.pa - av0); d.vb = (int)(d.pb - bv0);
+            const uint32_t nia = d.sa ? (uint32_t)(((d.pa + d.sa + 3) & ~3ll) - a0) * 4u : 0u;
+            const uint32_t nib = d.sb ? (uint32_t)(((d.pb + d.sb + 3) & ~3ll) - b0) * 4u : 0u;
+            const uint32_t nva = d.sa ? (uint32_t)(((d.pa + d.sa + AE - 1) & ~(long long)(AE - 1)) - av0) * (uint32_t)sizeof(V) : 0u;
+            const uint32_t nvb = d.sb ? (uint32_t)(((d.pb + d.sb + AE - 1) & ~(long long)(AE - 1)) - bv0) * (uint32_t)sizeof(V) : 0u;
+            td = d;
+            if (nia + nib) {
+                mbar_expect_tx(&bar, nia + nib + nva + nvb);
+                if (nia) { tma_load_1d(idA, p.indices + a0, nia, &bar); tma_load_1d(vA, gdata + av0, nva, &bar); }
+                if (nib) { tma_load_1d(idB, p.indices + b0, nib, &bar); tma_load_1d(vB, gdata + bv0, nvb, &bar); }
+            }
+        }
+        __syncthreads();
+        const TaskDesc d = td;
+        for (int j = threadIdx.x; j < d.sb; j += kJoinThreads) rev[j] = (V)0;
+        if (d.sa + d.sb) {
+            mbar_wait(&bar, phase);
+            phase ^= 1u;
+        }
+        __syncthreads();
+
+        const int32_t *A = idA + d.ia, *Bq = idB + d.ib;
+        const V *VA = vA + d.va, *VB = vB + d.vb;
+        // ---- S_a side: search every member in S_b
+        for (int j = threadIdx.x; j < d.sa; j += kJoinThreads) {
+            const int32_t w = A[j];
+            int lo = 0, hi = d.sb;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (Bq[mid] < w) lo = mid + 1;
+                else hi = mid;
+            }
+            const bool hit = lo < d.sb && Bq[lo] == w;
+            const V own = VA[j];
+            const V other = hit ? VB[lo] : (V)0;
+            if (hit) rev[lo] = own;
+            if (MODE == 0) {
+                ((int2 *)p.out)[d.offA + j] = make_int2((int)own, (int)other);
+            } else if (MODE == 2) {
+                const double o = ((double)other + 1.0) - 1.0;  // train.py:33,38 rounding in float64
+                ((float2 *)p.out)[d.offA + j] = make_float2((float)own, (float)o);
+            } else {
+                mat[j] = other;
+            }
+            if (p.segid) p.segid[d.offA + j] = d.segA;
+        }
+        __syncthreads();
+        // ---- S_b side: the match (if any) was dropped at its position
+        if (MODE == 1) {
+            const int k = p.k, k2 = 2 * p.k;
+            float *out = (float *)p.out;
+            for (int e = threadIdx.x; e < d.sa * k2; e += kJoinThreads) {
+                const int r = e / k2, rem = e - r * k2;
+                const int side = rem >= k, c = rem - side * k;
+                const int ptr = side ? (int)mat[r] : (int)VA[r];
+                out[(d.offA + r) * k2 + rem] = __ldg(p.enc + (int64_t)ptr * k + c);
+            }
+            for (int e = threadIdx.x; e < d.sb * k2; e += kJoinThreads) {
+                const int r = e / k2, rem = e - r * k2;
+                const int side = rem >= k, c = rem - side * k;
+                const int ptr = side ? (int)rev[r] : (int)VB[r];
+                out[(d.offB + r) * k2 + rem] = __ldg(p.enc + (int64_t)ptr * k + c);
+            }
+            if (p.segid)
+                for (int j = threadIdx.x; j < d.sb; j += kJoinThreads) p.segid[d.offB + j] = d.segB;
+        } else {
+            for (int j = threadIdx.x; j < d.sb; j += kJoinThreads) {
+                const V own = VB[j];
+                const V other = rev[j];
+                if (MODE == 0) {
+                    ((int2 *)p.out)[d.offB + j] = make_int2((int)own, (int)other);
+                } else {
+                    const double o = ((double)other + 1.0) - 1.0;
+                    ((float2 *)p.out)[d.offB + j] = make_float2((float)own, (float)o);
+                }
+                if (p.segid) p.segid[d.offB + j] = d.segB;
+            }
+        }
+        __syncthreads();  // smem is reused by the next task
+    }
+}
+
+// ------------------------------------------------------------------ generic path (sets too large for smem)
+template <typename V, int MODE>
+__global__ void __launch_bounds__(kJoinThreads) spjoin_global_kernel(const JoinArgs p) {
+    const V *gdata = (const V *)p.data;
+    for (int64_t t = blockIdx.x; t < p.ntask; t += gridDim.x) {
+        int64_t a, b, segA, segB;
+        task_nodes(p, t, a, b, segA, segB);
+        for (int dir = 0; dir < 2; dir++) {
+            const int64_t x = dir ? b : a, y = dir ? a : b;
+            const int64_t seg = dir ? segB : segA;
+            const long long px = p.indptr[x], py = p.indptr[y];
+            const int64_t sx = p.indptr[x + 1] - px, sy = p.indptr[y + 1] - py;
+            const long long off = p.seg_ptr[seg];
+            for (int64_t j = threadIdx.x; j < sx; j += kJoinThreads) {
+                const int32_t w = p.indices[px + j];
+                int64_t lo = 0, hi = sy;
+                while (lo < hi) {
+                    const int64_t mid = (lo + hi) >> 1;
+                    if (p.indices[py + mid] < w) lo = mid + 1;
+                    else hi = mid;
+                }
+                const bool hit = lo < sy && p.indices[py + lo] == w;
+                const V own = gdata[px + j];
+                const V other = hit ? gdata[py + lo] : (V)0;
+                if (MODE == 0) {
+                    ((int2 *)p.out)[off + j] = make_int2((int)own, (int)other);
+                } else if (MODE == 2) {
+                    const double o = ((double)other + 1.0) - 1.0;
+                    ((float2 *)p.out)[off + j] = make_float2((float)own, (float)o);
+                } else {
+                    float *out = (float *)p.out + (off + j) * 2 * p.k;
+                    for (int c = 0; c < p.k; c++) out[c] = __ldg(p.enc + (int64_t)own * p.k + c);
+                    for (int c = 0; c < p.k; c++) out[p.k + c] = __ldg(p.enc + (int64_t)other * p.k + c);
+                }
+                if (p.segid) p.segid[off + j] = seg;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ host side
+int spjoin_plan_impl(const SpG *s, const int64_t *edge_hd, int64_t B, int arity, int64_t *edge_dev,
+                     int64_t *indptr_dev, int64_t *N_out, cudaStream_t st) {
+    if (!s || !edge_hd || !indptr_dev || !N_out || B < 0 || (arity != 2 && arity != 3))
+        return fail(SUBG_ERR_ARG, "Input parsing error.");
+    DeviceGuard guard(s->device);
+    const int64_t nseg = (arity == 2 ? 2 : 4) * B;
+    const long long *edge = (const long long *)edge_hd;
+    if (!is_device_ptr(edge_hd)) {
+        if (!edge_dev) return fail(SUBG_ERR_ARG, "host edge list needs a device staging buffer");
+        SUBG_CUDA(cudaMemcpyAsync(edge_dev, edge_hd, (size_t)arity * B * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        edge = (const long long *)edge_dev;
+    } else if (edge_dev && edge_dev != edge_hd) {
+        SUBG_CUDA(cudaMemcpyAsync(edge_dev, edge_hd, (size_t)arity * B * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    }
+    int32_t *sizes = nullptr;
+    long long *scratch = nullptr;
+    uint32_t *bad = nullptr;
+    SUBG_CUDA(dmalloc(&sizes, (size_t)nseg, st));
+    SUBG_CUDA(dmalloc(&scratch, (size_t)std::max(1, scan_num_blocks(nseg)), st));
+    SUBG_CUDA(dmalloc(&bad, 1, st));
+    SUBG_CUDA(cudaMemsetAsync(bad, 0, sizeof(uint32_t), st));
+    if (nseg > 0) {
+        const unsigned blocks = (unsigned)std::min<int64_t>((nseg + 255) / 256, 4 * (int64_t)s->num_sms);
+        join_sizes_kernel<<<blocks, 256, 0, st>>>((const long long *)s->indptr, s->n, edge, B, arity, sizes, bad);
+    }
+    SUBG_CUDA(exclusive_scan_i32_i64(sizes, (long long *)indptr_dev, nseg, 0, scratch, st));
+    long long N = 0;
+    uint32_t hbad = 0;
+    SUBG_CUDA(cudaMemcpyAsync(&N, indptr_dev + nseg, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    SUBG_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SUBG_CUDA(cudaStreamSynchronize(st));
+    dfree(sizes, st); dfree(scratch, st); dfree(bad, st);
+    if (hbad) return fail(SUBG_ERR_ARG, "query node id outside the SpG");
+    *N_out = N;
+    return SUBG_OK;
+}
+
+template <typename V, int MODE>
+static cudaError_t launch_join(const SpG *s, JoinArgs &p, cudaStream_t st) {
+    if (p.ntask <= 0) return cudaSuccess;
+    int dev_smem = 0;
+    cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device);
+    const int cap = ((s->max_set + 3) & ~3) + 8;
+    const size_t smem = (size_t)cap * (8 + 4 * sizeof(V)) + 128;
+    if ((int64_t)smem <= std::min<int64_t>(dev_smem - 1024, 96 * 1024)) {
+        p.cap = cap;
+        auto kern = spjoin_kernel<V, MODE>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kJoinThreads, smem);
+        if (e != cudaSuccess) return e;
+        const int64_t blocks = std::min<int64_t>(p.ntask, (int64_t)s->num_sms * std::max(per_sm, 1));
+        kern<<<(unsigned)blocks, kJoinThreads, smem, st>>>(p);
+    } else {
+        const int64_t blocks = std::min<int64_t>(p.ntask, (int64_t)s->num_sms * 16);
+        spjoin_global_kernel<V, MODE><<<(unsigned)blocks, kJoinThreads, 0, st>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+int spjoin_run_impl(const SpG *s, const int64_t *edge_dev, int64_t B, int arity, const int64_t *indptr_dev,
+                    const float *enc_table_dev, int k, void *out_dev, int64_t *segid_dev, cudaStream_t st) {
+    if (!s || !edge_dev || !indptr_dev || B < 0 || (arity != 2 && arity != 3)) return fail(SUBG_ERR_ARG, "Input parsing error.");
+    if (B > 0 && !out_dev) return fail(SUBG_ERR_ARG, "null output");
+    if (enc_table_dev && (s->value_kind != 0 || k < 1)) return fail(SUBG_ERR_ARG, "table lookup needs an int SpG and k >= 1");
+    DeviceGuard guard(s->device);
+    JoinArgs p{};
+    p.indptr = (const long long *)s->indptr; p.indices = s->indices; p.data = s->data; p.n_rows = s->n;
+    p.edge = (const long long *)edge_dev; p.B = B; p.arity = arity; p.seg_ptr = (const long long *)indptr_dev;
+    p.enc = enc_table_dev; p.k = k; p.out = out_dev; p.segid = (long long *)segid_dev;
+    p.ntask = arity == 2 ? B : 2 * B;
+    cudaError_t e;
+    if (s->value_kind == 1) e = launch_join<double, 2>(s, p, st);
+    else if (enc_table_dev) e = launch_join<int32_t, 1>(s, p, st);
+    else e = launch_join<int32_t, 0>(s, p, st);
+    if (e != cudaSuccess) return fail(SUBG_ERR_CUDA, cudaGetErrorString(e));
+    return SUBG_OK;
+}
+
+}  // namespace subg

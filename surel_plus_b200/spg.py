@@ -1,0 +1,215 @@
+"""Device-resident graph and SpG (CSR-of-sets) handles over the C ABI.
+
+`SpG` stands where the reference keeps a scipy CSR (`z` of
+sampler/random_walks.py:79): row u = sorted node set S_u, data = LP-row id + 1
+(or a float64 structural value in PPR/SPD mode).  It stays in HBM; SpJoin reads it
+in place (surel_plus_b200/train.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi
+
+
+def _dev_index(device) -> int:
+    d = torch.device(device) if not isinstance(device, torch.device) else device
+    if d.type != "cuda":
+        raise RuntimeError("surel_plus_b200 runs on CUDA devices only (no CPU fallback)")
+    return d.index if d.index is not None else torch.cuda.current_device()
+
+
+def _stream(dev: int) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _ptr(a) -> int:
+    """Raw address of a numpy array / torch tensor (host or device)."""
+    if isinstance(a, torch.Tensor):
+        return a.data_ptr()
+    return a.ctypes.data
+
+
+class _DevView:
+    """Zero-copy view of library-owned device memory for torch.as_tensor()."""
+
+    def __init__(self, ptr: int, shape, typestr: str, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 2}
+        self._owner = owner
+
+
+def _view(ptr, shape, typestr, dev, owner):
+    if ptr is None or any(s == 0 for s in shape):
+        dt = {"<i8": torch.int64, "<i4": torch.int32, "<i2": torch.int16, "<u2": torch.uint16, "<f8": torch.float64}[typestr]
+        return torch.empty(shape, dtype=dt, device=f"cuda:{dev}")
+    return torch.as_tensor(_DevView(ptr, shape, typestr, owner), device=f"cuda:{dev}")
+
+
+class DeviceGraph:
+    """CSR adjacency resident in HBM (replaces the `indptr, indices` numpy arguments of
+    gset_sampler, subg_acc/subg_acc.c:655-671)."""
+
+    def __init__(self, indptr, indices, device="cuda"):
+        self._lib = _capi.load()
+        self.device = _dev_index(device)
+        self._h = C.c_void_p()
+        if isinstance(indptr, torch.Tensor):
+            if indptr.dtype not in (torch.int32, torch.int64) or indices.dtype != torch.int32:
+                raise TypeError("indptr must be int32/int64 and indices int32")
+            indptr, indices = indptr.contiguous(), indices.contiguous()
+            is64 = indptr.dtype == torch.int64
+            n1, E = indptr.numel(), indices.numel()
+        else:
+            indptr = np.asarray(indptr)
+            if indptr.dtype not in (np.int32, np.int64):
+                raise TypeError(f"Cannot cast indptr from {indptr.dtype} to int32/int64")
+            indptr = np.ascontiguousarray(indptr)
+            indices = np.asarray(indices)
+            if not np.can_cast(indices.dtype, np.int32, "safe") and indices.size and indices.max() >= 2 ** 31:
+                raise TypeError("indices must fit int32")
+            indices = np.ascontiguousarray(indices, dtype=np.int32)
+            is64 = indptr.dtype == np.int64
+            n1, E = indptr.size, indices.size
+        self.N, self.E = n1 - 1, E
+        self._keep = (indptr, indices)
+        _capi.check(self._lib.subg_graph_create(_ptr(indptr), int(is64), _ptr(indices), self.N, self.E, self.device,
+                                                _stream(self.device), C.byref(self._h)))
+        self._keep = None
+
+    @classmethod
+    def from_scipy(cls, G, device="cuda"):
+        return cls(G.indptr, G.indices, device)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.subg_graph_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SpG:
+    """Handle of a device SpG.  Attributes: n rows, T entries, c unique LP rows, ncol,
+    max_set, status, value_kind (0 int pointers, 1 float64 values), shape (scipy-like)."""
+
+    def __init__(self, handle: C.c_void_p, device: int, n_nodes: int | None = None, num_walks: int | None = None):
+        self._lib = _capi.load()
+        self._h = handle
+        self.device = device
+        n, T = C.c_int64(), C.c_int64()
+        c, ncol, mx, vk = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        st = C.c_uint32()
+        _capi.check(self._lib.subg_spg_info(handle, C.byref(n), C.byref(T), C.byref(c), C.byref(ncol), C.byref(mx),
+                                            C.byref(st), C.byref(vk)))
+        self.n, self.T, self.c, self.ncol = n.value, T.value, c.value, ncol.value
+        self.max_set, self.status, self.value_kind = mx.value, st.value, vk.value
+        self.num_walks = num_walks
+        self.shape = (self.n, n_nodes if n_nodes is not None else self.n)
+        self.nnz = self.T
+
+    # ---- construction -------------------------------------------------------
+    @classmethod
+    def sample(cls, graph: DeviceGraph, query, num_walks=100, num_steps=3, bucket=-1, seed=111413,
+               rng_mode=_capi.SUBG_RNG_PHILOX, walks=None) -> "SpG":
+        """Walk-based set sampling + LP encoding + SpG build on the device
+        (subg_acc.c:649-1034 and random_walks.py:79).  `num_steps` is the walk length m."""
+        lib = _capi.load()
+        if isinstance(query, torch.Tensor):
+            q = query.to(torch.int32).contiguous()
+            n = q.numel()
+        else:
+            q = np.ascontiguousarray(np.asarray(query).astype(np.int32, copy=False))
+            n = q.size
+        w = None
+        if rng_mode == _capi.SUBG_RNG_TRACE:
+            if walks is None:
+                raise TypeError("trace mode needs walks[n, num_walks, num_steps]")
+            w = walks.to(torch.int32).contiguous() if isinstance(walks, torch.Tensor) else np.ascontiguousarray(walks, dtype=np.int32)
+            if (w.numel() if isinstance(w, torch.Tensor) else w.size) != n * num_walks * num_steps:
+                raise TypeError("walks must have n*num_walks*num_steps entries")
+        h = C.c_void_p()
+        _capi.check(lib.subg_gset_sample(graph._h, _ptr(q), n, int(num_walks), int(num_steps), int(bucket),
+                                         int(seed) & 0xFFFFFFFFFFFFFFFF, int(rng_mode), _ptr(w) if w is not None else None,
+                                         _stream(graph.device), C.byref(h)))
+        return cls(h, graph.device, n_nodes=graph.N, num_walks=num_walks)
+
+    @classmethod
+    def from_scipy(cls, x, device="cuda") -> "SpG":
+        """Upload a scipy CSR produced by the reference's subg_matrix / topk_ppr_matrix+encoding."""
+        lib = _capi.load()
+        dev = _dev_index(device)
+        x = x.tocsr()
+        if not x.has_sorted_indices:
+            x = x.sorted_indices()
+        indptr = np.ascontiguousarray(x.indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(x.indices, dtype=np.int32)
+        if np.issubdtype(x.data.dtype, np.floating):
+            data, kind = np.ascontiguousarray(x.data, dtype=np.float64), 1
+        else:
+            data, kind = np.ascontiguousarray(x.data, dtype=np.int32), 0
+        h = C.c_void_p()
+        _capi.check(lib.subg_spg_from_csr(_ptr(indptr), _ptr(indices), _ptr(data), kind, x.shape[0], indices.size, dev,
+                                          _stream(dev), C.byref(h)))
+        return cls(h, dev, n_nodes=x.shape[1])
+
+    # ---- views / export -----------------------------------------------------
+    def views(self) -> dict:
+        """Zero-copy torch views of the device arrays (valid while this object lives)."""
+        p = [C.c_void_p() for _ in range(6)]
+        _capi.check(self._lib.subg_spg_views(self._h, *[C.byref(x) for x in p]))
+        d = self.device
+        out = {
+            "indptr": _view(p[0].value, (self.n + 1,), "<i8", d, self),
+            "indices": _view(p[1].value, (self.T,), "<i4", d, self),
+            "data": _view(p[2].value, (self.T,), "<f8" if self.value_kind else "<i4", d, self),
+        }
+        if not self.value_kind and p[3].value:
+            out["slot"] = _view(p[3].value, (self.T,), "<u2", d, self)
+            out["enc"] = _view(p[4].value, (self.c, self.ncol), "<i2", d, self)
+            out["nsize"] = _view(p[5].value, (self.n,), "<i4", d, self)
+        return out
+
+    def export_reference(self, want_raw: bool = False):
+        """[nsize, remap, enc(, raw_enc)] exactly as gset_sampler returns them
+        (subg_acc.c:1017-1024).  Host numpy arrays (filled through pinned memory)."""
+        nsize = torch.empty(self.n, dtype=torch.int32, pin_memory=True)
+        remap = torch.empty((2, self.T), dtype=torch.int32, pin_memory=True)
+        enc = torch.empty((self.c, self.ncol), dtype=torch.int16, pin_memory=True)
+        raw = torch.empty((self.T, self.ncol), dtype=torch.int16, pin_memory=True) if want_raw else None
+        _capi.check(self._lib.subg_spg_export(self._h, nsize.data_ptr(), remap.data_ptr(), enc.data_ptr(),
+                                              raw.data_ptr() if want_raw else None, _stream(self.device)))
+        out = [nsize.numpy(), remap.numpy(), enc.numpy()]
+        if want_raw:
+            out.append(raw.numpy())
+        return out
+
+    def enc_table(self) -> np.ndarray:
+        """int16 [c+1, ncol] LP table with the all-zero row 0 (random_walks.py:81)."""
+        v = self.views()
+        enc = v["enc"].cpu().numpy() if "enc" in v else np.zeros((0, self.ncol), np.int16)
+        return np.concatenate([np.zeros((1, self.ncol), np.int16), enc], axis=0)
+
+    def to_scipy(self):
+        """The equivalent scipy CSR (what the reference's subg_matrix returns)."""
+        import scipy.sparse as sp
+        v = self.views()
+        return sp.csr_matrix((v["data"].cpu().numpy(), v["indices"].cpu().numpy(), v["indptr"].cpu().numpy()),
+                             shape=self.shape)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.subg_spg_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

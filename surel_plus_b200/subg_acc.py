@@ -1,0 +1,91 @@
+"""Drop-in for the reference's `subg_acc` CPython extension (subg_acc/subg_acc.c:1036-1059),
+backed by the CUDA library through the C ABI.  Same function names, keyword names,
+return layout and exception classes; `sampler/random_walks.py:18` can import it unchanged:
+
+    from subg_acc import gset_sampler, walk_sampler
+
+RNG: the reference draws from glibc rand_r on one word shared by all OpenMP threads
+(subg_acc.c:731-732), so it is only reproducible with nthread=1.  Here
+  nthread == 1  -> SUBG_RNG_RAND_R: that single-thread stream replayed in parallel on the
+                   GPU, bit-identical output to the reference;
+  otherwise     -> SUBG_RNG_PHILOX: counter-based Philox4x32-10 (same sampling law, fast path).
+`SUBG_RNG=philox|rand_r` overrides the choice.
+"""
+from __future__ import annotations
+
+import os
+import time
+
+import numpy as np
+
+from . import _capi
+from .spg import DeviceGraph, SpG
+
+__all__ = ["gset_sampler", "walk_sampler", "walk_join", "batch_sampler"]
+
+
+def _say(msg: str) -> None:
+    if os.environ.get("SUBG_QUIET", "0") != "1":
+        print(msg, flush=True)
+
+
+def _rng_mode(nthread: int) -> int:
+    env = os.environ.get("SUBG_RNG", "").lower()
+    if env == "philox":
+        return _capi.SUBG_RNG_PHILOX
+    if env == "rand_r":
+        return _capi.SUBG_RNG_RAND_R
+    return _capi.SUBG_RNG_RAND_R if nthread == 1 else _capi.SUBG_RNG_PHILOX
+
+
+def gset_sampler(indptr, indices, query, num_walks=100, num_steps=3, bucket=-1, nthread=-1, seed=111413,
+                 debug=-1, device="cuda"):
+    """Walk-based node-set sampling with the LP structure encoder (subg_acc.c:649-1034).
+
+    Returns the list [nsize int32[n], remap int32[2,T], enc int16[c,num_steps+1]] and, when
+    debug > 0, raw_enc int16[T,num_steps+1] -- the reference's layout (subg_acc.c:1017-1024).
+    """
+    try:
+        indptr = np.asarray(indptr)
+        indices = np.asarray(indices)
+        query = np.asarray(query).astype(np.int32, copy=False)  # NPY_ARRAY_FORCECAST, subg_acc.c:673
+        num_walks, num_steps, bucket, nthread, seed, debug = (int(num_walks), int(num_steps), int(bucket),
+                                                              int(nthread), int(seed), int(debug))
+    except Exception as e:  # subg_acc.c:656-660
+        raise TypeError("Input parsing error.\n") from e
+    t0 = time.perf_counter()
+    graph = DeviceGraph(indptr, indices, device)
+    spg = SpG.sample(graph, query, num_walks=num_walks, num_steps=num_steps, bucket=bucket,
+                     seed=seed & 0xFFFFFFFF, rng_mode=_rng_mode(nthread))
+    t1 = time.perf_counter()
+    n = max(len(query), 1)
+    stride = num_walks * num_steps + 1 if bucket < 0 else bucket
+    if spg.status & _capi.STATUS_BUCKET_OVERFLOW:  # subg_acc.c:835-836 (per key there; once here)
+        _say(f"#SubGAcc: some keys exceed the buffer, try a larger bucket size > {stride}.")
+    if spg.status & _capi.STATUS_DEAD_END:
+        _say("#SubGAcc: rand_r replay met a node without out-neighbours; output is a valid sample "
+             "but no longer the reference's nthread=1 stream.")
+    _say(f"#SubGAcc: #total {spg.T}; #max_set {spg.max_set} of {stride}; "
+         f"buffer usage {spg.T / n / stride * 100:.2f}%; dT_w {t1 - t0:.2f}s")
+    out = spg.export_reference(want_raw=debug > 0)
+    t2 = time.perf_counter()
+    _say(f"#SubGAcc: #enc_unique {spg.c}; compression ratio {spg.T / max(spg.c, 1):.2f}, dT_e {t2 - t1:.2f}s")
+    spg.close()
+    graph.close()
+    return out
+
+
+def walk_sampler(ptr, neighs, query, num_walks=100, num_steps=3, nthread=-1, seed=111413, replacement=-1):
+    """SUREL-v1 walk + RPE sampler (subg_acc.c:144-389).  Not on the SUREL+ hot path
+    (SURVEY.md section 8f, row 2); the symbol exists because sampler/random_walks.py:18 imports it."""
+    raise NotImplementedError("walk_sampler (SUREL v1) is not part of the B200 hot path yet")
+
+
+def walk_join(*args, **kwargs):
+    """SUREL-v1 walk joining (subg_acc.c:509-647): no caller in the reference; out of scope."""
+    raise NotImplementedError("walk_join (SUREL v1) is out of scope of the B200 hot path")
+
+
+def batch_sampler(*args, **kwargs):
+    """Serial mini-batch node sampler (subg_acc.c:391-507): no caller in the reference; out of scope."""
+    raise NotImplementedError("batch_sampler is out of scope of the B200 hot path")

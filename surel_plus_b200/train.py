@@ -1,0 +1,128 @@
+"""Host mirror of the SpJoin operators of the reference's train.py (gather :13-45,
+hgather :48-72, bgather :75-85, pgather :88-111), running on the device SpG.
+
+Same names, argument meaning and return values: `x` may be a surel_plus_b200.SpG (stays in
+HBM) or the scipy CSR the reference builds (uploaded once and cached); `edge` is the [2,B] /
+[3,B] int64 index tensor (torch CPU/CUDA tensor or numpy); the outputs are device tensors
+consumed by Net.forward(x, ptr) (model.py:76-90).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+
+import numpy as np
+import torch
+
+from . import _capi
+from .spg import SpG, _dev_index, _stream
+
+_uploaded: "weakref.WeakValueDictionary[int, SpG]" = weakref.WeakValueDictionary()
+_upload_keep: dict = {}
+
+
+def _as_spg(x, device) -> SpG:
+    if isinstance(x, SpG):
+        return x
+    key = id(x)
+    hit = _upload_keep.get(key)
+    if hit is not None and hit[0]() is x:
+        return hit[1]
+    spg = SpG.from_scipy(x, device)
+    try:
+        _upload_keep[key] = (weakref.ref(x, lambda _r, k=key: _upload_keep.pop(k, None)), spg)
+    except TypeError:
+        pass
+    return spg
+
+
+def _edge_arg(edge, arity: int):
+    """-> (object keeping the memory alive, raw pointer, B, is_device)."""
+    if isinstance(edge, torch.Tensor):
+        e = edge.to(torch.int64).contiguous()
+        if e.dim() != 2 or e.shape[0] != arity:
+            raise TypeError(f"edge must have shape [{arity}, B]")
+        return e, e.data_ptr(), e.shape[1], e.is_cuda
+    e = np.ascontiguousarray(np.asarray(edge), dtype=np.int64)
+    if e.ndim != 2 or e.shape[0] != arity:
+        raise TypeError(f"edge must have shape [{arity}, B]")
+    return e, e.ctypes.data, e.shape[1], False
+
+
+def _join(edge, x, device, arity, encode=None, want_segid=False, want_ptr=True):
+    spg = _as_spg(x, device)
+    lib = _capi.load()
+    dev = spg.device
+    keep, eptr, B, on_dev = _edge_arg(edge, arity)
+    tdev = torch.device("cuda", dev)
+    nseg = (2 if arity == 2 else 4) * B
+    edge_dev = keep if on_dev else torch.empty((arity, B), dtype=torch.int64, device=tdev)
+    indptr = torch.empty(nseg + 1, dtype=torch.int64, device=tdev)
+    N = C.c_int64(0)
+    st = _stream(dev)
+    _capi.check(lib.subg_spjoin_plan(spg._h, eptr, B, arity, edge_dev.data_ptr(), indptr.data_ptr(), C.byref(N), st))
+    N = N.value
+    table = None
+    if spg.value_kind == 1:
+        if encode is not None:
+            raise TypeError("a value SpG (PPR/SPD) is joined without an LP table")
+        out = torch.empty((N, 2), dtype=torch.float32, device=tdev)
+        k = 0
+    elif encode is not None:
+        table = encode if (isinstance(encode, torch.Tensor) and encode.is_cuda and encode.dtype == torch.float32
+                           and encode.is_contiguous()) else torch.as_tensor(encode, dtype=torch.float32, device=tdev).contiguous()
+        k = table.shape[1]
+        out = torch.empty((N, 2, k), dtype=torch.float32, device=tdev)
+    else:
+        out = torch.empty((N, 2), dtype=torch.int32, device=tdev)
+        k = 0
+    segid = torch.empty(N, dtype=torch.int64, device=tdev) if want_segid else None
+    _capi.check(lib.subg_spjoin_run(spg._h, edge_dev.data_ptr(), B, arity, indptr.data_ptr(),
+                                    table.data_ptr() if table is not None else None, k, out.data_ptr(),
+                                    segid.data_ptr() if segid is not None else None, st))
+    return out, indptr, segid
+
+
+def gather(edge, x, device, ptr=True, encode=None):
+    """train.py:13-45.  Returns (xz, indptr) with xz float32 [N,2,k] = encode[pointer pairs]
+    (or [N,2,1] raw values when encode is None) and indptr int64 [2B+1] (ptr=True) or the
+    per-row segment id int64 [N] (ptr=False)."""
+    out, indptr, segid = _join(edge, x, device, 2, encode=encode, want_segid=not ptr)
+    if encode is None:
+        out = out.float().unsqueeze(dim=-1)
+    return out, (indptr if ptr else segid)
+
+
+def hgather(hedge, x, device, encode=None):
+    """train.py:48-72.  Returns (xz float32 [N,2,k], ind int64 [N]) with segments
+    [u|w, w|u, v|w, w|v] numbered 0..4B-1."""
+    if encode is None:
+        raise NotImplementedError  # train.py:69-70
+    out, _, segid = _join(hedge, x, device, 3, encode=encode, want_segid=True)
+    assert out.size(0) == segid.size(0)
+    return out, segid
+
+
+def bgather(edge, x, out):
+    """train.py:75-85: fills out[0..3] = (xl [Su,2], xr [Sv,2], sizes_l [B], sizes_r [B]) as host
+    numpy arrays (pointer pairs, no table lookup)."""
+    spg = _as_spg(x, "cuda")
+    xz, indptr, _ = _join(edge, spg, None, 2)
+    B = (indptr.numel() - 1) // 2
+    ip = indptr.cpu().numpy()
+    xz = xz.cpu().numpy()
+    nl = int(ip[B])
+    out[0], out[1] = xz[:nl], xz[nl:]
+    sizes = np.diff(ip)
+    out[2], out[3] = sizes[:B], sizes[B:]
+
+
+def pgather(edge, M, device, encode, gather_func=None, ptr=True, njobs=4):
+    """train.py:88-111.  The reference splits the batch over `njobs` Python threads and
+    re-concatenates [all left blocks, all right blocks]; that order equals gather()'s, so the
+    device join is one launch and `gather_func` / `njobs` are accepted for signature
+    compatibility only."""
+    out, indptr, segid = _join(edge, M, device, 2, encode=encode, want_segid=not ptr)
+    if encode is None:
+        out = out.float().unsqueeze(dim=-1)
+    return out, (indptr if ptr else segid)

@@ -1,0 +1,116 @@
+"""GPU parity: SpJoin (pair, triplet, fused table lookup, value mode) vs the oracle (bit-exact)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import pyoracle as po
+
+
+@pytest.fixture(scope="module")
+def lp_spg(mid_graph):
+    from surel_plus_b200 import DeviceGraph, SpG, _capi
+    A = mid_graph
+    n = A.shape[0]
+    g = DeviceGraph.from_scipy(A)
+    M, m = 100, 3
+    spg = SpG.sample(g, np.arange(n), M, m, seed=3, rng_mode=_capi.SUBG_RNG_PHILOX)
+    z = spg.to_scipy()
+    xpe = torch.from_numpy(spg.enc_table()).float().cuda() / M
+    return spg, z, xpe
+
+
+def _edges(n, B, arity, seed=0):
+    rng = np.random.default_rng(seed)
+    e = rng.integers(0, n, (arity, B))
+    e[:, 0] = e[0, 0]               # u == v query
+    if B > 1:
+        e[:, 1] = n - 1 - np.arange(arity) % 3  # isolated nodes (sets of size 1)
+    return e
+
+
+@pytest.mark.parametrize("B", [1, 7, 1024])
+def test_pair_join_index_and_fused(lp_spg, B):
+    from surel_plus_b200 import gather, pgather, bgather
+    spg, z, xpe = lp_spg
+    edge = _edges(z.shape[0], B, 2, seed=B)
+    exz, sl, sr = po.spjoin_pair(z, edge)
+    out = np.empty(4, dtype=object)
+    bgather(edge, spg, out)
+    assert np.array_equal(np.vstack([out[0], out[1]]), exz)
+    assert np.array_equal(out[2], sl) and np.array_equal(out[3], sr)
+    for fn in (gather, lambda e, x, d, ptr, encode: pgather(e, x, d, encode, bgather, ptr=ptr)):
+        xz, ptr = fn(torch.from_numpy(edge), spg, "cuda", ptr=True, encode=xpe)
+        assert xz.dtype == torch.float32 and tuple(xz.shape) == (len(exz), 2, xpe.shape[1])
+        assert torch.equal(xz.cpu(), xpe.cpu()[torch.from_numpy(exz).long()])
+        assert np.array_equal(ptr.cpu().numpy(), po.pair_index(sl, sr, True))
+        xz2, ind = fn(edge, spg, "cuda", ptr=False, encode=xpe)
+        assert torch.equal(xz2, xz)
+        assert np.array_equal(ind.cpu().numpy(), po.pair_index(sl, sr, False))
+
+
+def test_pair_join_accepts_scipy_and_cuda_edges(lp_spg):
+    from surel_plus_b200 import gather
+    spg, z, xpe = lp_spg
+    edge = _edges(z.shape[0], 300, 2, seed=11)
+    exz, sl, sr = po.spjoin_pair(z, edge)
+    a, _ = gather(torch.from_numpy(edge).cuda(), spg, "cuda", True, xpe)
+    b, _ = gather(edge, z, "cuda", True, xpe)          # scipy CSR uploaded once
+    c, _ = gather(edge, z, "cuda", True, xpe)          # cached
+    exp = xpe.cpu()[torch.from_numpy(exz).long()]
+    assert torch.equal(a.cpu(), exp) and torch.equal(b.cpu(), exp) and torch.equal(c.cpu(), exp)
+
+
+@pytest.mark.parametrize("B", [1, 5, 2048])
+def test_triplet_join(lp_spg, B):
+    from surel_plus_b200 import hgather
+    spg, z, xpe = lp_spg
+    hedge = _edges(z.shape[0], B, 3, seed=100 + B)
+    exz, sizes = po.spjoin_triplet(z, hedge)
+    xz, ind = hgather(torch.from_numpy(hedge), spg, "cuda", encode=xpe)
+    assert torch.equal(xz.cpu(), xpe.cpu()[torch.from_numpy(exz).long()])
+    assert np.array_equal(ind.cpu().numpy(), np.repeat(np.arange(4 * B), sizes))
+    with pytest.raises(NotImplementedError):
+        hgather(hedge, spg, "cuda", encode=None)
+
+
+def test_value_join_float64(mid_graph):
+    """PPR/SPD mode: float64 store, (x+1)-1 rounding of train.py:33, float32 output [N,2,1]."""
+    import scipy.sparse as sp
+    from surel_plus_b200 import gather
+    A = mid_graph
+    rng = np.random.default_rng(1)
+    n = A.shape[0]
+    X = sp.random(n, n, density=30 / n, format="csr", random_state=3, dtype=np.float64)
+    X.data = rng.random(X.nnz) * 0.9 + 1e-3
+    X.sort_indices()
+    edge = _edges(n, 500, 2, seed=4)
+    exz, sl, sr = po.spjoin_pair(X, edge)
+    xz, ptr = gather(edge, X, "cuda", ptr=True, encode=None)
+    assert tuple(xz.shape) == (len(exz), 2, 1)
+    assert torch.equal(xz.squeeze(-1).cpu(), torch.from_numpy(exz).float())
+    assert np.array_equal(ptr.cpu().numpy(), po.pair_index(sl, sr, True))
+
+
+def test_large_sets_use_global_path():
+    """Sets far larger than shared memory take the generic kernel; same rows."""
+    import scipy.sparse as sp
+    from surel_plus_b200 import gather
+    n = 60000
+    rng = np.random.default_rng(2)
+    rows = np.repeat(np.arange(4), 30000)
+    cols = np.concatenate([np.sort(rng.choice(n, 30000, replace=False)) for _ in range(4)])
+    X = sp.csr_matrix((rng.integers(1, 1000, rows.size).astype(np.int32), (rows, cols)), shape=(n, n))
+    X.sort_indices()
+    edge = np.array([[0, 1, 2, 3, 5], [1, 2, 3, 0, 0]])
+    exz, sl, sr = po.spjoin_pair(X, edge)
+    xz, ptr = gather(edge, X, "cuda", ptr=True, encode=None)
+    assert torch.equal(xz.squeeze(-1).cpu(), torch.from_numpy(exz).float())
+
+
+def test_bad_query_raises(lp_spg):
+    from surel_plus_b200 import gather
+    spg, z, xpe = lp_spg
+    with pytest.raises(TypeError):
+        gather(np.array([[0], [z.shape[0] + 5]]), spg, "cuda", True, xpe)
