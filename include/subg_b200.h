@@ -134,6 +134,20 @@ int subg_ppr_topk(const subg_graph *g, const int32_t *seeds_hd, int64_t n, float
                   float eps, int topk, int normalization, int encoder, void *stream,
                   subg_spg **out);
 
+/* ---- measurement hooks (bench.py / profiles) -------------------------------------
+ * When enabled, the library brackets its dominant kernels with CUDA events on the
+ * launching stream.  subg_timing_read synchronises those events, returns the summed
+ * device time and number of launches of kernel class `which` since the last read and
+ * clears them.  which: 0 set-sampler kernel, 1 SpJoin kernel, 2 SpG build (scan,
+ * compaction, unique ranking, id remap).  subg_launch_count: kernels launched by the
+ * library since load (all classes). */
+#define SUBG_TIMING_SAMPLER 0
+#define SUBG_TIMING_SPJOIN  1
+#define SUBG_TIMING_BUILD   2
+int subg_timing_enable(int enable);
+int subg_timing_read(int which, double *ms, int64_t *launches);
+int64_t subg_launch_count(void);
+
 /* pinned host memory helpers (so numpy arrays handed back by the Python shim can be
  * filled with asynchronous copies) */
 int subg_host_alloc(void **ptr, int64_t bytes);

@@ -23,6 +23,7 @@ SYMBOLS = [
     "subg_spg_from_csr", "subg_spg_free",
     "subg_spjoin_plan", "subg_spjoin_run",
     "subg_ppr_topk",
+    "subg_timing_enable", "subg_timing_read", "subg_launch_count",
     "subg_host_alloc", "subg_host_free",
 ]
 
@@ -61,6 +62,10 @@ def load() -> C.CDLL:
     L.subg_spjoin_plan.argtypes = [vp, vp, i64, i32, vp, vp, C.POINTER(i64), vp]
     L.subg_spjoin_run.argtypes = [vp, vp, i64, i32, vp, vp, i32, vp, vp, vp]
     L.subg_ppr_topk.argtypes = [vp, vp, i64, C.c_float, C.c_float, i32, i32, i32, vp, C.POINTER(vp)]
+    L.subg_timing_enable.argtypes = [i32]
+    L.subg_timing_read.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(i64)]
+    L.subg_launch_count.restype = i64
+    L.subg_launch_count.argtypes = []
     L.subg_host_alloc.argtypes = [C.POINTER(vp), i64]
     L.subg_host_free.argtypes = [vp]
     L.subg_host_free.restype = None
@@ -70,6 +75,21 @@ def load() -> C.CDLL:
             fn.restype = C.c_int
     _lib = L
     return L
+
+
+def timing_enable(on: bool) -> None:
+    load().subg_timing_enable(int(on))
+
+
+def timing_read(which: int):
+    """-> (summed device ms, launches) of kernel class `which` since the last read."""
+    ms, cnt = C.c_double(0), C.c_int64(0)
+    load().subg_timing_read(which, C.byref(ms), C.byref(cnt))
+    return ms.value, cnt.value
+
+
+def launch_count() -> int:
+    return int(load().subg_launch_count())
 
 
 def check(rc: int) -> None:

@@ -1,6 +1,9 @@
 // extern "C" surface of libsubg_b200.so (declared in include/subg_b200.h).
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -11,6 +14,40 @@ void set_error(const std::string &msg) { g_last_error = msg; }
 int fail(int code, const std::string &msg) {
     g_last_error = msg;
     return code;
+}
+
+// ---- measurement hooks
+struct TimedRegion {
+    cudaEvent_t a, b;
+    int which;
+    bool closed;
+};
+static std::mutex g_tm_mutex;
+static std::vector<TimedRegion> g_regions;
+static bool g_timing = false;
+static std::atomic<long long> g_launches{0};
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+void timing_begin(int which, cudaStream_t st) {
+    if (!g_timing) return;
+    TimedRegion r{};
+    r.which = which;
+    r.closed = false;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+    std::lock_guard<std::mutex> lk(g_tm_mutex);
+    g_regions.push_back(r);
+}
+void timing_end(int which, cudaStream_t st) {
+    if (!g_timing) return;
+    std::lock_guard<std::mutex> lk(g_tm_mutex);
+    for (size_t i = g_regions.size(); i-- > 0;)
+        if (g_regions[i].which == which && !g_regions[i].closed) {
+            cudaEventRecord(g_regions[i].b, st);
+            g_regions[i].closed = true;
+            return;
+        }
 }
 
 bool is_device_ptr(const void *p) {
@@ -198,6 +235,35 @@ int subg_ppr_topk(const subg_graph *g, const int32_t *seeds_hd, int64_t n, float
     return ppr_topk_impl(reinterpret_cast<const Graph *>(g), seeds_hd, n, alpha, eps, topk, normalization, encoder,
                          (cudaStream_t)stream, reinterpret_cast<SpG **>(out));
 }
+
+int subg_timing_enable(int enable) {
+    g_timing = enable != 0;
+    return SUBG_OK;
+}
+int subg_timing_read(int which, double *ms, int64_t *launches) {
+    std::lock_guard<std::mutex> lk(g_tm_mutex);
+    double tot = 0;
+    int64_t cnt = 0;
+    std::vector<TimedRegion> keep;
+    for (auto &r : g_regions) {
+        if (r.which != which || !r.closed) {
+            keep.push_back(r);
+            continue;
+        }
+        float t = 0.f;
+        cudaEventSynchronize(r.b);
+        cudaEventElapsedTime(&t, r.a, r.b);
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+        tot += t;
+        cnt++;
+    }
+    g_regions.swap(keep);
+    if (ms) *ms = tot;
+    if (launches) *launches = cnt;
+    return SUBG_OK;
+}
+int64_t subg_launch_count(void) { return g_launches.load(); }
 
 int subg_host_alloc(void **ptr, int64_t bytes) {
     if (!ptr || bytes < 0) return fail(SUBG_ERR_ARG, "bad host allocation request");

@@ -46,6 +46,11 @@ struct DeviceGuard {
 
 bool is_device_ptr(const void *p);
 
+// measurement hooks (capi.cu)
+void count_launch(int n = 1);
+void timing_begin(int which, cudaStream_t st);
+void timing_end(int which, cudaStream_t st);
+
 // stream-ordered scratch allocation
 template <typename T>
 inline cudaError_t dmalloc(T **p, size_t count, cudaStream_t st) {

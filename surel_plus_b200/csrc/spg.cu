@@ -257,9 +257,14 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, int M, 
                 a.tab_key = tab_key; a.tab_pos = tab_pos; a.tab_mask = tab_cap - 1;
                 a.tab_count = d_flags + 1; a.status = d_flags;
                 a.rec_cap = pl.rec_cap; a.nbw = pl.nbw; a.fy_cap = pl.fy_cap; a.smem_per_warp = pl.smem_per_warp;
+                timing_begin(SUBG_TIMING_SAMPLER, st);
                 CK(pl.key64 ? launch_gset_sample_k64(a, pl.WT, pl.MS, g->num_sms, st)
                             : launch_gset_sample_k32(a, pl.WT, pl.MS, g->num_sms, st));
+                timing_end(SUBG_TIMING_SAMPLER, st);
+                count_launch(1);
+                timing_begin(SUBG_TIMING_BUILD, st);
                 CK(exclusive_scan_i32_i64(s->nsize + base, (long long *)s->indptr + base, nc, T, scan_scratch, st));
+                count_launch(3);
                 long long T_new = 0;
                 uint32_t flags[3];
                 CK(cudaMemcpyAsync(&T_new, s->indptr + base + nc, sizeof(long long), cudaMemcpyDeviceToHost, st));
@@ -287,6 +292,8 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, int M, 
                 compact_rows_kernel<<<(unsigned)std::max<int64_t>(cblocks, 1), 256, 0, st>>>(
                     st_node, st_prov, st_rank, pl.S_pad, s->nsize + base, (const long long *)s->indptr + base, nc,
                     s->indices, (int32_t *)s->data, s->slot, d_maxset);
+                timing_end(SUBG_TIMING_BUILD, st);
+                count_launch(1);
                 T = T_new;
             }
             if (table_full) {
@@ -307,6 +314,7 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, int M, 
             s->c = (int32_t)c;
             CK(dmalloc(&s->enc, (size_t)c * (m + 1), st));
             if (c > 0) {
+                timing_begin(SUBG_TIMING_BUILD, st);
                 CK(dmalloc(&u_pos, (size_t)c, st)); CK(dmalloc(&u_pos2, (size_t)c, st));
                 CK(dmalloc(&u_slot, (size_t)c, st)); CK(dmalloc(&u_slot2, (size_t)c, st));
                 CK(dmalloc(&rank_of_slot, (size_t)tab_cap, st));
@@ -320,6 +328,8 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, int M, 
                     const int64_t rb = std::min<int64_t>((T + 255) / 256, 16 * (int64_t)g->num_sms);
                     remap_ids_kernel<<<(unsigned)rb, 256, 0, st>>>((int32_t *)s->data, T, rank_of_slot);
                 }
+                timing_end(SUBG_TIMING_BUILD, st);
+                count_launch(3);
             }
             int32_t mx = 0;
             CK(cudaMemcpyAsync(&mx, d_maxset, sizeof(int32_t), cudaMemcpyDeviceToHost, st));

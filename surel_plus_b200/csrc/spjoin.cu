@@ -309,6 +309,7 @@ int spjoin_plan_impl(const SpG *s, const int64_t *edge_hd, int64_t B, int arity,
         join_sizes_kernel<<<blocks, 256, 0, st>>>((const long long *)s->indptr, s->n, edge, B, arity, sizes, bad);
     }
     SUBG_CUDA(exclusive_scan_i32_i64(sizes, (long long *)indptr_dev, nseg, 0, scratch, st));
+    count_launch(4);
     long long N = 0;
     uint32_t hbad = 0;
     SUBG_CUDA(cudaMemcpyAsync(&N, indptr_dev + nseg, sizeof(long long), cudaMemcpyDeviceToHost, st));
@@ -356,9 +357,12 @@ int spjoin_run_impl(const SpG *s, const int64_t *edge_dev, int64_t B, int arity,
     p.enc = enc_table_dev; p.k = k; p.out = out_dev; p.segid = (long long *)segid_dev;
     p.ntask = arity == 2 ? B : 2 * B;
     cudaError_t e;
+    timing_begin(SUBG_TIMING_SPJOIN, st);
     if (s->value_kind == 1) e = launch_join<double, 2>(s, p, st);
     else if (enc_table_dev) e = launch_join<int32_t, 1>(s, p, st);
     else e = launch_join<int32_t, 0>(s, p, st);
+    timing_end(SUBG_TIMING_SPJOIN, st);
+    count_launch(1);
     if (e != cudaSuccess) return fail(SUBG_ERR_CUDA, cudaGetErrorString(e));
     return SUBG_OK;
 }
