@@ -49,6 +49,12 @@ extern "C" {
 /* status bits reported by subg_spg_info */
 #define SUBG_STATUS_BUCKET_OVERFLOW 1u /* a set hit `bucket`; reference prints a warning (subg_acc.c:835-836) */
 #define SUBG_STATUS_DEAD_END        2u /* RAND_R replay met a node without out-neighbours: stream no longer matches */
+#define SUBG_STATUS_PPR_SECOND_PASS 4u /* some PPR seeds outgrew the first-pass workspace and were re-run (result unaffected) */
+
+/* structure encoders of utils.py:20-39 (the 'DEG' branch is broken upstream and not provided) */
+#define SUBG_ENCODER_NONE 0
+#define SUBG_ENCODER_PPR  1 /* utils.py:35-36 */
+#define SUBG_ENCODER_SPD  2 /* utils.py:29-34 */
 
 typedef struct subg_graph subg_graph; /* CSR graph resident in HBM (int64 or int32 rowptr, int32 col) */
 typedef struct subg_spg subg_spg;     /* SpG: CSR-of-sets resident in HBM */
@@ -77,6 +83,22 @@ void subg_graph_free(subg_graph *g);
 int subg_gset_sample(const subg_graph *g, const int32_t *seeds_hd, int64_t n,
                      int num_walks, int num_steps, int bucket, uint64_t seed,
                      int rng_mode, const int32_t *walks_hd, void *stream, subg_spg **out);
+
+/* Multi-GPU shard of the same call: seeds_hd is the WHOLE query (n_all entries)
+ * and only the sets of the contiguous window [lo, hi) are sampled.  Seed indices stay global
+ * (Philox counters, rand_r call offsets, first-occurrence positions of the LP rows), so the shards
+ * of a range-partitioned query concatenate to exactly what one subg_gset_sample call returns.
+ * walks_hd (TRACE mode) holds the walks of the window only: int32[hi-lo, num_walks, num_steps]. */
+int subg_gset_sample_shard(const subg_graph *g, const int32_t *seeds_hd, int64_t n_all, int64_t lo,
+                           int64_t hi, int num_walks, int num_steps, int bucket, uint64_t seed,
+                           int rng_mode, const int32_t *walks_hd, void *stream, subg_spg **out);
+
+/* Re-label the LP rows of a shard after the unique tables of all shards were merged in rank
+ * order (= the first-occurrence order of subg_acc.c:957-978 over the whole query):
+ * data <- id_map[data-1] + 1 for the c old ids, enc <- enc_hd int16[c_new, ncol].  Also attaches
+ * a table to an SpG wrapped by subg_spg_from_csr (id_map_hd NULL, ncol > 0); ncol <= 0 keeps the width. */
+int subg_spg_set_lp_table(subg_spg *s, const int32_t *id_map_hd, const int16_t *enc_hd,
+                          int32_t c_new, int32_t ncol, void *stream);
 
 /* n = sets, T = total entries, c = unique LP rows, ncol = num_steps+1 */
 int subg_spg_info(const subg_spg *s, int64_t *n, int64_t *T, int32_t *c, int32_t *ncol,
@@ -127,23 +149,42 @@ int subg_spjoin_run(const subg_spg *s, const int64_t *edge_dev, int64_t B, int a
 
 /* ---- PPR set sampler -----------------------------------------------------------
  * Replaces topk_ppr_matrix (sampler/pprgo.py:83-111): ACL forward push per seed
- * (pprgo.py:9-38), top-k by score, optional normalisation (0 row, 1 sym, 2 col),
- * result as a float64 value SpG with rows in seed order and ascending node ids.
- * encoder: 0 none, 1 'PPR' rescale (utils.py:35-36), 2 'SPD' (utils.py:29-34). */
+ * (_calc_ppr_node, pprgo.py:9-38: LIFO queue, float32 p and r, float64 intermediate for the
+ * pushed amount), top-k by score (pprgo.py:59; ties at the k-th score, which the reference's
+ * unstable argsort leaves unspecified, go to the later-inserted node), CSR assembly and
+ * normalisation (0 'row', 1 'sym', 2 'col'; pprgo.py:87-106, float64).  The result is a
+ * float64 value SpG with rows in seed order and ascending node ids.
+ *   norm_deg_hd  float64[N] = adj_matrix.sum(1) (the weighted degree used by 'sym'/'col'),
+ *                or NULL to use the row length (unweighted adjacency).
+ *   encoder      SUBG_ENCODER_*: applied after the normalisation (main.py:181-183).
+ * The push needs CSR rows with strictly ascending columns (scipy canonical format); the
+ * degree used inside the push is the row length (np.sum(adj > 0), pprgo.py:68).
+ * Synchronises the stream. */
 int subg_ppr_topk(const subg_graph *g, const int32_t *seeds_hd, int64_t n, float alpha,
-                  float eps, int topk, int normalization, int encoder, void *stream,
-                  subg_spg **out);
+                  float eps, int topk, int normalization, const double *norm_deg_hd,
+                  int encoder, void *stream, subg_spg **out);
+
+/* encoding(x, adj, 'PPR' | 'SPD') (utils.py:29-36) on a value SpG; returns a new SpG.
+ * 'PPR': (x + 0.1) / (max(x) + 0.1) with the global max; g may be NULL.
+ * 'SPD': 1*[w in N(u)] + 0.5*[w in S_u and two-hop(u,w)] + 0.3*[w in S_u], diagonal 2.3;
+ *        the set becomes N(u) U S_u U {u}; needs one SpG row per graph node (idx = arange(N)). */
+int subg_spg_encode(const subg_graph *g, const subg_spg *x, int encoder, void *stream,
+                    subg_spg **out);
+
+/* forward pushes performed while building a PPR SpG (0 for other SpGs) */
+int subg_spg_pushes(const subg_spg *s, int64_t *pushes);
 
 /* ---- measurement hooks (bench.py / profiles) -------------------------------------
  * When enabled, the library brackets its dominant kernels with CUDA events on the
  * launching stream.  subg_timing_read synchronises those events, returns the summed
  * device time and number of launches of kernel class `which` since the last read and
  * clears them.  which: 0 set-sampler kernel, 1 SpJoin kernel, 2 SpG build (scan,
- * compaction, unique ranking, id remap).  subg_launch_count: kernels launched by the
+ * compaction, unique ranking, id remap), 3 PPR push kernel.  subg_launch_count: kernels launched by the
  * library since load (all classes). */
 #define SUBG_TIMING_SAMPLER 0
 #define SUBG_TIMING_SPJOIN  1
 #define SUBG_TIMING_BUILD   2
+#define SUBG_TIMING_PPR     3
 int subg_timing_enable(int enable);
 int subg_timing_read(int which, double *ms, int64_t *launches);
 int64_t subg_launch_count(void);

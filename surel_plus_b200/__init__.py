@@ -8,5 +8,7 @@ from .spg import DeviceGraph, SpG
 from .sampler import subg_matrix
 from .train import gather, hgather, bgather, pgather
 from .subg_acc import gset_sampler
+from .pprgo import topk_ppr_matrix, encoding
 
-__all__ = ["DeviceGraph", "SpG", "subg_matrix", "gather", "hgather", "bgather", "pgather", "gset_sampler", "_capi"]
+__all__ = ["DeviceGraph", "SpG", "subg_matrix", "gather", "hgather", "bgather", "pgather", "gset_sampler", "topk_ppr_matrix",
+           "encoding", "_capi"]

@@ -21,28 +21,36 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
 
-def _digest() -> str:
+def _sha(paths, extra="") -> str:
     h = hashlib.sha256()
-    for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
-        for name in sorted(os.listdir(root)):
-            with open(os.path.join(root, name), "rb") as f:
-                h.update(name.encode())
-                h.update(f.read())
-    h.update(" ".join(FLAGS).encode())
+    for path in paths:
+        with open(path, "rb") as f:
+            h.update(os.path.basename(path).encode())
+            h.update(f.read())
+    h.update(extra.encode())
     return h.hexdigest()
 
 
+def _headers():
+    inc = os.path.join(os.path.dirname(HERE), "include")
+    hs = [os.path.join(CSRC, n) for n in sorted(os.listdir(CSRC)) if n.endswith((".cuh", ".inc", ".h"))]
+    return hs + [os.path.join(inc, n) for n in sorted(os.listdir(inc))]
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Incremental: an object is recompiled when its .cu, any header or the flags changed."""
     os.makedirs(LIBDIR, exist_ok=True)
-    stamp = os.path.join(LIBDIR, "build.sha256")
-    dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
-        return LIB
     objdir = os.path.join(LIBDIR, "obj")
     os.makedirs(objdir, exist_ok=True)
+    headers = _headers()
+    flags = " ".join(FLAGS)
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        stamp = obj + ".sha256"
+        dig = _sha([os.path.join(CSRC, src)] + headers, flags)
+        if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+            return obj, False
         cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
@@ -51,16 +59,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
             f.write(r.stderr)
         if verbose:
             sys.stderr.write(r.stderr)
-        return obj
+        with open(stamp, "w") as f:
+            f.write(dig)
+        return obj, True
 
     with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
-        objs = list(ex.map(compile_one, SOURCES))
+        res = list(ex.map(compile_one, SOURCES))
+    objs = [o for o, _ in res]
+    if not any(c for _, c in res) and os.path.exists(LIB) and not force:
+        return LIB
     cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    with open(stamp, "w") as f:
-        f.write(dig)
     return LIB
 
 

@@ -60,19 +60,21 @@ bool is_device_ptr(const void *p) {
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
-int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, int M, int m, int bucket, uint64_t seed,
-                     int rng_mode, const int32_t *walks_hd, cudaStream_t st, SpG **out);
+int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int64_t lo, int64_t hi, int M, int m,
+                     int bucket, uint64_t seed, int rng_mode, const int32_t *walks_hd, cudaStream_t st, SpG **out);
+int spg_set_lp_table_impl(SpG *s, const int32_t *id_map_hd, const int16_t *enc_hd, int32_t c_new, int32_t ncol,
+                          cudaStream_t st);
 int spg_export_impl(const SpG *s, int32_t *nsize_hd, int32_t *remap_hd, int16_t *enc_hd, int16_t *raw_hd,
                     cudaStream_t st);
 int spg_from_csr_impl(const int64_t *indptr_hd, const int32_t *indices_hd, const void *data_hd, int value_kind,
                       int64_t n_rows, int64_t nnz, int device, cudaStream_t st, SpG **out);
-void spg_free_impl(SpG *s);
 int spjoin_plan_impl(const SpG *s, const int64_t *edge_hd, int64_t B, int arity, int64_t *edge_dev,
                      int64_t *indptr_dev, int64_t *N_out, cudaStream_t st);
 int spjoin_run_impl(const SpG *s, const int64_t *edge_dev, int64_t B, int arity, const int64_t *indptr_dev,
                     const float *enc_table_dev, int k, void *out_dev, int64_t *segid_dev, cudaStream_t st);
 int ppr_topk_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, float alpha, float eps, int topk,
-                  int normalization, int encoder, cudaStream_t st, SpG **out);
+                  int normalization, const double *norm_deg_hd, cudaStream_t st, SpG **out);
+int spg_encode_impl(const Graph *g, const SpG *x, int encoder, cudaStream_t st, SpG **out);
 
 __global__ void widen_rowptr_kernel(const int32_t *in, long long *out, int64_t n) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = in[i];
@@ -173,8 +175,20 @@ void subg_graph_free(subg_graph *g_) {
 int subg_gset_sample(const subg_graph *g, const int32_t *seeds_hd, int64_t n, int num_walks, int num_steps,
                      int bucket, uint64_t seed, int rng_mode, const int32_t *walks_hd, void *stream,
                      subg_spg **out) {
-    return gset_sample_impl(reinterpret_cast<const Graph *>(g), seeds_hd, n, num_walks, num_steps, bucket, seed,
+    return gset_sample_impl(reinterpret_cast<const Graph *>(g), seeds_hd, n, 0, n, num_walks, num_steps, bucket, seed,
                             rng_mode, walks_hd, (cudaStream_t)stream, reinterpret_cast<SpG **>(out));
+}
+
+int subg_gset_sample_shard(const subg_graph *g, const int32_t *seeds_hd, int64_t n_all, int64_t lo, int64_t hi,
+                           int num_walks, int num_steps, int bucket, uint64_t seed, int rng_mode,
+                           const int32_t *walks_hd, void *stream, subg_spg **out) {
+    return gset_sample_impl(reinterpret_cast<const Graph *>(g), seeds_hd, n_all, lo, hi, num_walks, num_steps, bucket,
+                            seed, rng_mode, walks_hd, (cudaStream_t)stream, reinterpret_cast<SpG **>(out));
+}
+
+int subg_spg_set_lp_table(subg_spg *s, const int32_t *id_map_hd, const int16_t *enc_hd, int32_t c_new, int32_t ncol,
+                          void *stream) {
+    return spg_set_lp_table_impl(reinterpret_cast<SpG *>(s), id_map_hd, enc_hd, c_new, ncol, (cudaStream_t)stream);
 }
 
 int subg_spg_info(const subg_spg *s_, int64_t *n, int64_t *T, int32_t *c, int32_t *ncol, int32_t *max_set,
@@ -231,9 +245,37 @@ int subg_spjoin_run(const subg_spg *s, const int64_t *edge_dev, int64_t B, int a
 }
 
 int subg_ppr_topk(const subg_graph *g, const int32_t *seeds_hd, int64_t n, float alpha, float eps, int topk,
-                  int normalization, int encoder, void *stream, subg_spg **out) {
-    return ppr_topk_impl(reinterpret_cast<const Graph *>(g), seeds_hd, n, alpha, eps, topk, normalization, encoder,
-                         (cudaStream_t)stream, reinterpret_cast<SpG **>(out));
+                  int normalization, const double *norm_deg_hd, int encoder, void *stream, subg_spg **out) {
+    if (encoder < SUBG_ENCODER_NONE || encoder > SUBG_ENCODER_SPD) return fail(SUBG_ERR_UNSUPPORTED, "unknown encoder");
+    SpG *raw = nullptr;
+    int rc = ppr_topk_impl(reinterpret_cast<const Graph *>(g), seeds_hd, n, alpha, eps, topk, normalization, norm_deg_hd,
+                           (cudaStream_t)stream, &raw);
+    if (rc != SUBG_OK) return rc;
+    if (encoder == SUBG_ENCODER_NONE) {
+        *out = reinterpret_cast<subg_spg *>(raw);
+        return SUBG_OK;
+    }
+    SpG *enc = nullptr;
+    rc = spg_encode_impl(reinterpret_cast<const Graph *>(g), raw, encoder, (cudaStream_t)stream, &enc);
+    if (rc == SUBG_OK) {
+        enc->pushes = raw->pushes;
+        enc->status |= raw->status;
+        *out = reinterpret_cast<subg_spg *>(enc);
+    }
+    spg_free_impl(raw);
+    return rc;
+}
+
+int subg_spg_encode(const subg_graph *g, const subg_spg *x, int encoder, void *stream, subg_spg **out) {
+    return spg_encode_impl(reinterpret_cast<const Graph *>(g), reinterpret_cast<const SpG *>(x), encoder,
+                           (cudaStream_t)stream, reinterpret_cast<SpG **>(out));
+}
+
+int subg_spg_pushes(const subg_spg *s_, int64_t *pushes) {
+    const SpG *s = reinterpret_cast<const SpG *>(s_);
+    if (!s || !pushes) return fail(SUBG_ERR_ARG, "null SpG");
+    *pushes = s->pushes;
+    return SUBG_OK;
 }
 
 int subg_timing_enable(int enable) {

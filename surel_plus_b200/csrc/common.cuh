@@ -68,6 +68,8 @@ struct Graph {
     void *rowptr = nullptr;  // int32[N+1] or int64[N+1]
     int32_t *col = nullptr;  // int32[E]
     int num_sms = 148;
+    // lazily computed structure properties (-1 unknown): rows strictly ascending; adjacency symmetric
+    mutable int sorted_state = -1, sym_state = -1;
 };
 
 struct SpG {
@@ -87,8 +89,11 @@ struct SpG {
     int16_t *enc = nullptr;      // [c, ncol]
     int32_t *nsize = nullptr;    // [n]
     int32_t *seeds = nullptr;    // [n] node id of each row
+    int64_t pushes = 0;          // PPR sampler: forward pushes performed (measurement)
     int num_sms = 148;
 };
+
+void spg_free_impl(SpG *s);
 
 // ------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__

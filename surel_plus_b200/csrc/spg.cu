@@ -89,6 +89,16 @@ __global__ void remap_ids_kernel(int32_t *data, int64_t T, const int32_t *rank_o
         data[i] = rank_of_slot[data[i]] + 1;
 }
 
+__global__ void relabel_ids_kernel(int32_t *data, int64_t T, const int32_t *id_map, int32_t c_old, int32_t c_new) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < T; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t d = data[i];
+        if (d >= 1 && d <= c_old) {
+            const int32_t g = id_map[d - 1];
+            data[i] = (g >= 0 && g < c_new) ? g + 1 : 0;
+        }
+    }
+}
+
 // reference layout: entries of a set in first-visit order, ids without the +1
 __global__ void export_remap_kernel(const long long *indptr, const int32_t *indices, const int32_t *data,
                                     const uint16_t *slot, int64_t n, int64_t T, int32_t *remap,
@@ -157,9 +167,14 @@ static int make_plan(const Graph *g, int M, int m, int bucket, SamplePlan *p) {
     return SUBG_OK;
 }
 
-int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, int M, int m, int bucket,
-                     uint64_t seed, int rng_mode, const int32_t *walks_hd, cudaStream_t st, SpG **out) {
-    if (!g || !out || n < 0 || (n > 0 && !seeds_hd)) return fail(SUBG_ERR_ARG, "Input parsing error.");
+// seeds_hd holds the whole query (n_all entries); the sets of the window [lo, hi) are sampled.  Seed
+// indices stay global (Philox counters, rand_r call offsets, first-occurrence positions), so the
+// shards of a range-partitioned query concatenate to exactly the single-call result.
+int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int64_t lo, int64_t hi, int M, int m,
+                     int bucket, uint64_t seed, int rng_mode, const int32_t *walks_hd, cudaStream_t st, SpG **out) {
+    if (!g || !out || n_all < 0 || (n_all > 0 && !seeds_hd) || lo < 0 || hi < lo || hi > n_all)
+        return fail(SUBG_ERR_ARG, "Input parsing error.");
+    const int64_t n = hi - lo;
     if (rng_mode < 0 || rng_mode > 2) return fail(SUBG_ERR_ARG, "unknown rng_mode");
     if (rng_mode == SUBG_RNG_TRACE && !walks_hd && n > 0) return fail(SUBG_ERR_ARG, "trace mode needs walks");
     SamplePlan pl;
@@ -171,6 +186,7 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, int M, 
 
     // everything below that is not part of the SpG is scratch
     int32_t *d_walks = nullptr, *d_calls = nullptr, *st_node = nullptr, *st_prov = nullptr, *rank_of_slot = nullptr;
+    int32_t *d_all_seeds = nullptr;
     uint16_t *st_rank = nullptr;
     long long *call_base = nullptr, *scan_scratch = nullptr;
     unsigned long long *tab_key = nullptr, *tab_pos = nullptr, *u_pos = nullptr, *u_pos2 = nullptr;
@@ -200,18 +216,29 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, int M, 
         CK(cudaMemsetAsync(d_flags, 0, 4 * sizeof(uint32_t), st));
         CK(cudaMemsetAsync(d_maxset, 0, sizeof(int32_t), st));
         if (n > 0) {
-            CK(cudaMemcpyAsync(s->seeds, seeds_hd, (size_t)n * sizeof(int32_t), cudaMemcpyDefault, st));
+            CK(cudaMemcpyAsync(s->seeds, seeds_hd + lo, (size_t)n * sizeof(int32_t), cudaMemcpyDefault, st));
             check_seeds_kernel<<<std::min<int64_t>((n + 255) / 256, 4 * g->num_sms), 256, 0, st>>>(s->seeds, n, g->N, d_flags + 2);
         }
         const int nscan = std::max(1, scan_num_blocks(n));
         CK(dmalloc(&scan_scratch, (size_t)nscan, st));
 
         if (rng_mode == SUBG_RNG_RAND_R && n > 0) {
-            CK(dmalloc(&d_calls, (size_t)n, st));
-            CK(dmalloc(&call_base, (size_t)n + 1, st));
-            rand_r_calls_kernel<<<std::min<int64_t>((n + 255) / 256, 4 * g->num_sms), 256, 0, st>>>(
-                g->rowptr, g->rowptr64 ? 1 : 0, s->seeds, n, M, m, d_calls);
-            CK(exclusive_scan_i32_i64(d_calls, call_base, n, 0, scan_scratch, st));
+            // the single rand_r stream is consumed seed by seed: offsets are a prefix over the WHOLE query
+            const int32_t *all_seeds = s->seeds;
+            if (n_all != n) {
+                CK(dmalloc(&d_all_seeds, (size_t)n_all, st));
+                CK(cudaMemcpyAsync(d_all_seeds, seeds_hd, (size_t)n_all * sizeof(int32_t), cudaMemcpyDefault, st));
+                check_seeds_kernel<<<std::min<int64_t>((n_all + 255) / 256, 4 * g->num_sms), 256, 0, st>>>(d_all_seeds, n_all, g->N, d_flags + 2);
+                all_seeds = d_all_seeds;
+            }
+            long long *scratch_all = nullptr;
+            CK(dmalloc(&d_calls, (size_t)n_all, st));
+            CK(dmalloc(&call_base, (size_t)n_all + 1, st));
+            CK(dmalloc(&scratch_all, (size_t)std::max(1, scan_num_blocks(n_all)), st));
+            rand_r_calls_kernel<<<std::min<int64_t>((n_all + 255) / 256, 4 * g->num_sms), 256, 0, st>>>(
+                g->rowptr, g->rowptr64 ? 1 : 0, all_seeds, n_all, M, m, d_calls);
+            CK(exclusive_scan_i32_i64(d_calls, call_base, n_all, 0, scratch_all, st));
+            dfree(scratch_all, st);
         }
         if (rng_mode == SUBG_RNG_TRACE && n > 0) {
             if (is_device_ptr(walks_hd)) d_walks = const_cast<int32_t *>(walks_hd);
@@ -247,7 +274,7 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, int M, 
                 const int64_t nc = std::min(chunk, n - base);
                 SamplerArgs a{};
                 a.rowptr = g->rowptr; a.rowptr64 = g->rowptr64 ? 1 : 0; a.col = g->col;
-                a.seeds = s->seeds + base; a.n_chunk = nc; a.seed_base = base;
+                a.seeds = s->seeds + base; a.n_chunk = nc; a.seed_base = lo + base;
                 a.M = M; a.m = m; a.stride = pl.stride; a.OB = pl.OB; a.SHIFT = pl.SHIFT;
                 a.rng_mode = rng_mode; a.rng_lo = (uint32_t)seed; a.rng_hi = (uint32_t)(seed >> 32);
                 a.call_base = (const int64_t *)call_base;
@@ -344,7 +371,7 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, int M, 
 done:
 #undef CK
     if (walks_owned) dfree(d_walks, st);
-    dfree(d_calls, st); dfree(call_base, st); dfree(scan_scratch, st);
+    dfree(d_calls, st); dfree(call_base, st); dfree(scan_scratch, st); dfree(d_all_seeds, st);
     dfree(st_node, st); dfree(st_prov, st); dfree(st_rank, st);
     dfree(tab_key, st); dfree(tab_pos, st); dfree(u_pos, st); dfree(u_pos2, st);
     dfree(u_slot, st); dfree(u_slot2, st); dfree(rank_of_slot, st);
@@ -355,6 +382,35 @@ done:
         return rc;
     }
     *out = s;
+    return SUBG_OK;
+}
+
+// Re-label the LP rows of a shard: data <- id_map[data - 1] + 1, enc <- the merged table.
+// (multi-GPU: local first-occurrence ids -> ids of the table merged over all shards in rank order)
+int spg_set_lp_table_impl(SpG *s, const int32_t *id_map_hd, const int16_t *enc_hd, int32_t c_new, int32_t ncol,
+                          cudaStream_t st) {
+    if (!s || c_new < 0 || (s->c > 0 && !id_map_hd) || (c_new > 0 && !enc_hd)) return fail(SUBG_ERR_ARG, "Input parsing error.");
+    if (s->value_kind != 0) return fail(SUBG_ERR_ARG, "LP table of a value SpG");
+    if (ncol > 0) s->ncol = ncol;
+    if (s->ncol < 1) return fail(SUBG_ERR_ARG, "LP table width unknown");
+    DeviceGuard guard(s->device);
+    int32_t *d_map = nullptr;
+    int16_t *d_enc = nullptr;
+    SUBG_CUDA(dmalloc(&d_map, (size_t)s->c + 1, st));
+    SUBG_CUDA(dmalloc(&d_enc, (size_t)c_new * s->ncol, st));
+    if (s->c > 0) SUBG_CUDA(cudaMemcpyAsync(d_map, id_map_hd, (size_t)s->c * 4, cudaMemcpyDefault, st));
+    if (c_new > 0) SUBG_CUDA(cudaMemcpyAsync(d_enc, enc_hd, (size_t)c_new * s->ncol * 2, cudaMemcpyDefault, st));
+    if (s->T > 0) {
+        const int64_t rb = std::min<int64_t>((s->T + 255) / 256, 16 * (int64_t)s->num_sms);
+        relabel_ids_kernel<<<(unsigned)rb, 256, 0, st>>>((int32_t *)s->data, s->T, d_map, s->c, c_new);
+        SUBG_CUDA(cudaGetLastError());
+        count_launch(1);
+    }
+    SUBG_CUDA(cudaStreamSynchronize(st));
+    dfree(d_map, st);
+    dfree(s->enc, st);
+    s->enc = d_enc;
+    s->c = c_new;
     return SUBG_OK;
 }
 

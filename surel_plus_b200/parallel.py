@@ -1,0 +1,195 @@
+"""Multi-GPU SubGAcc: one process per GPU (torch.distributed), graph replicated in every GPU's
+HBM, seeds range-partitioned, SpG shards all-gathered once (NCCL over NVLink/NVSwitch), queries
+then joined locally on the replicated SpG.  The reference has no
+distributed code at all; this is the B200 scaling path of the same operators.
+
+Exchange step (the only collectives on the path):
+  1. all-gather of the shard sizes (n_r, T_r, c_r);
+  2. all-gather of the per-shard unique LP tables (c_r x ncol int16, KBs) -> every rank merges
+     them in rank order, which reproduces the first-occurrence order of the single-process scan
+     (subg_acc.c:957-978) because shards are contiguous seed ranges; local LP ids are re-labelled
+     on the device (subg_spg_set_lp_table);
+  3. variable-size all-gather of nsize / indices / data (8 B per set entry) straight into the
+     slices of the final arrays.
+The host-side logic below is device-agnostic (it is exercised with gloo on CPU tensors in
+tests/test_parallel_gloo.py); the sampling itself is CUDA only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _capi
+
+
+# ------------------------------------------------------------------------------ partitioning
+def partition(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous seed range [lo, hi) of `rank`: the first n % world ranks get one extra seed."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def partition_by_work(weights: np.ndarray, world: int) -> np.ndarray:
+    """Contiguous ranges balanced by a per-seed work estimate (e.g. min(deg, M) + M*(m-1)):
+    returns the world+1 range boundaries."""
+    cum = np.concatenate([[0], np.cumsum(weights, dtype=np.float64)])
+    targets = cum[-1] * np.arange(1, world) / world
+    cuts = np.searchsorted(cum, targets, side="left")
+    return np.concatenate([[0], cuts, [len(weights)]]).astype(np.int64)
+
+
+# ------------------------------------------------------------------------------ LP table merge
+def merge_lp_tables(tables: List[np.ndarray]) -> Tuple[np.ndarray, List[np.ndarray]]:
+    """tables[r]: int16 [c_r, ncol] unique LP rows of shard r in local first-occurrence order.
+    Returns (merged int16 [c, ncol] in global first-occurrence order, [id_map_r int32 [c_r]])."""
+    ncol = tables[0].shape[1] if tables else 0
+    cat = np.ascontiguousarray(np.concatenate(tables, axis=0), dtype=np.int16) if tables else np.zeros((0, 0), np.int16)
+    if cat.shape[0] == 0:
+        return cat.reshape(0, ncol), [np.zeros(0, np.int32) for _ in tables]
+    keys = cat.view(np.dtype((np.void, cat.dtype.itemsize * ncol))).ravel()
+    _, first, inv = np.unique(keys, return_index=True, return_inverse=True)
+    order = np.argsort(first, kind="stable")          # unique rows by first occurrence in rank order
+    rank_of_unique = np.empty(len(order), np.int32)
+    rank_of_unique[order] = np.arange(len(order), dtype=np.int32)
+    gid = rank_of_unique[inv.ravel()]
+    merged = cat[np.sort(first)]
+    maps, off = [], 0
+    for t in tables:
+        maps.append(np.ascontiguousarray(gid[off:off + t.shape[0]], dtype=np.int32))
+        off += t.shape[0]
+    return merged, maps
+
+
+# ------------------------------------------------------------------------------ collectives
+def _group_info(group):
+    return dist.get_world_size(group), dist.get_rank(group), dist.get_backend(group)
+
+
+def all_gather_sizes(vals: List[int], device, group=None) -> np.ndarray:
+    """[world, len(vals)] int64 matrix of every rank's values."""
+    world, _, _ = _group_info(group)
+    t = torch.tensor(vals, dtype=torch.int64, device=device)
+    out = torch.empty(world * len(vals), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(out, t, group=group)
+    return out.view(world, len(vals)).cpu().numpy()
+
+
+def all_gather_varlen(local: torch.Tensor, counts: np.ndarray, out: torch.Tensor, group=None) -> torch.Tensor:
+    """Concatenate the ranks' `local` (rank r contributes counts[r] leading-dim rows) into `out`.
+    NCCL: the output slices are handed to all_gather directly (uneven sizes become grouped
+    ncclBroadcasts that write in place, no staging copy).  Other backends (gloo in the CPU tests):
+    padded all-gather, then compaction."""
+    world, rank, backend = _group_info(group)
+    offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    assert local.shape[0] == counts[rank] and out.shape[0] == offs[-1]
+    if backend == "nccl":
+        slices = [out[offs[r]:offs[r + 1]] for r in range(world)]
+        dist.all_gather(slices, local.contiguous(), group=group)
+        return out
+    # bytes on the wire (gloo has no int16): rows -> uint8 [rows, bytes_per_row]
+    per_row = int(np.prod(local.shape[1:], dtype=np.int64))
+    width = per_row * local.element_size()
+    rows = (local.contiguous().reshape(local.shape[0], per_row).view(torch.uint8) if local.shape[0]
+            else torch.zeros((0, width), dtype=torch.uint8, device=local.device))
+    mx = int(max(counts.max(), 1))
+    pad = torch.zeros((mx, width), dtype=torch.uint8, device=local.device)
+    pad[:rows.shape[0]] = rows
+    buf = torch.empty((world * mx, width), dtype=torch.uint8, device=local.device)
+    dist.all_gather_into_tensor(buf, pad, group=group)
+    out_rows = out.reshape(out.shape[0], per_row).view(torch.uint8) if out.shape[0] else None
+    for r in range(world):
+        if counts[r]:
+            out_rows[offs[r]:offs[r + 1]] = buf[r * mx:r * mx + int(counts[r])]
+    return out
+
+
+def assemble_shards(nsize: torch.Tensor, indices: torch.Tensor, data: torch.Tensor, enc: torch.Tensor,
+                    relabel: Optional[Callable[[np.ndarray, np.ndarray], torch.Tensor]] = None, group=None) -> dict:
+    """The exchange step on plain tensors.  Inputs are this rank's shard: nsize int32 [n_r],
+    indices int32 [T_r] (ascending per set), data int32 [T_r] (local LP id + 1), enc int16 [c_r, ncol].
+    `relabel(id_map, merged_enc)` must return the shard's data with global ids (+1); default: torch indexing.
+    Returns dict(indptr int64 [n+1], indices, data, enc int16 [c, ncol], nsize, counts=[world,3], bytes)."""
+    world, rank, _ = _group_info(group)
+    dev = indices.device
+    ncol = enc.shape[1]
+    counts = all_gather_sizes([nsize.shape[0], indices.shape[0], enc.shape[0]], dev, group)
+    n_r, T_r, c_r = counts[:, 0], counts[:, 1], counts[:, 2]
+    # (2) unique LP tables
+    enc_all = torch.empty((int(c_r.sum()), ncol), dtype=torch.int16, device=dev)
+    all_gather_varlen(enc.contiguous(), c_r, enc_all, group)
+    enc_np = enc_all.cpu().numpy()
+    offs = np.concatenate([[0], np.cumsum(c_r)])
+    merged, maps = merge_lp_tables([enc_np[offs[r]:offs[r + 1]] for r in range(world)])
+    if relabel is not None:
+        data = relabel(maps[rank], merged)
+    elif data.numel():
+        m = torch.from_numpy(maps[rank]).to(dev)
+        data = (m[(data - 1).long()] + 1).to(torch.int32)
+    # (3) the shards themselves
+    n, T = int(n_r.sum()), int(T_r.sum())
+    g_nsize = torch.empty(n, dtype=torch.int32, device=dev)
+    g_indices = torch.empty(T, dtype=torch.int32, device=dev)
+    g_data = torch.empty(T, dtype=torch.int32, device=dev)
+    all_gather_varlen(nsize, n_r, g_nsize, group)
+    all_gather_varlen(indices, T_r, g_indices, group)
+    all_gather_varlen(data, T_r, g_data, group)
+    indptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(g_nsize, 0, out=indptr[1:])
+    wire = 8 * T + 4 * n + 2 * ncol * int(c_r.sum())
+    return {"indptr": indptr, "indices": g_indices, "data": g_data, "enc": merged, "nsize": g_nsize,
+            "counts": counts, "bytes_gathered": wire}
+
+
+# ------------------------------------------------------------------------------ the CUDA path
+def sharded_sample(graph, query, num_walks=100, num_steps=3, bucket=-1, seed=111413, rng_mode=None, group=None,
+                   bounds: Optional[np.ndarray] = None):
+    """Sample this rank's seed range on its GPU and exchange shards: returns the full SpG (replicated
+    on every rank), identical to SpG.sample(graph, query, ...) of a single process (bit for bit in
+    RAND_R / TRACE-free modes: seed indices, rand_r offsets and LP ids are global)."""
+    from .spg import SpG, _ptr, _stream
+    lib = _capi.load()
+    world, rank, _ = _group_info(group)
+    q = np.ascontiguousarray(np.asarray(query).astype(np.int32, copy=False))
+    n = q.size
+    lo, hi = partition(n, world, rank) if bounds is None else (int(bounds[rank]), int(bounds[rank + 1]))
+    h = C.c_void_p()
+    mode = _capi.SUBG_RNG_PHILOX if rng_mode is None else rng_mode
+    _capi.check(lib.subg_gset_sample_shard(graph._h, _ptr(q), n, lo, hi, int(num_walks), int(num_steps), int(bucket),
+                                           int(seed) & 0xFFFFFFFFFFFFFFFF, int(mode), None, _stream(graph.device),
+                                           C.byref(h)))
+    shard = SpG(h, graph.device, n_nodes=graph.N, num_walks=num_walks)
+    v = shard.views()
+
+    def relabel(id_map: np.ndarray, merged: np.ndarray) -> torch.Tensor:
+        m = np.ascontiguousarray(merged, dtype=np.int16)
+        _capi.check(lib.subg_spg_set_lp_table(shard._h, _ptr(id_map), _ptr(m), m.shape[0], -1, _stream(graph.device)))
+        return v["data"]
+
+    enc_local = v["enc"] if "enc" in v else torch.zeros((0, num_steps + 1), dtype=torch.int16, device=v["indices"].device)
+    nsize_local = v["nsize"] if "nsize" in v else torch.zeros(0, dtype=torch.int32, device=v["indices"].device)
+    parts = assemble_shards(nsize_local, v["indices"], v["data"], enc_local, relabel=relabel, group=group)
+    status = shard.status
+    if world > 1:
+        status = int(np.bitwise_or.reduce(all_gather_sizes([shard.status], parts["indices"].device, group)[:, 0]))
+    shard.close()
+    full = SpG.from_device_csr(parts["indptr"], parts["indices"], parts["data"], n_nodes=graph.N, enc=parts["enc"],
+                               num_walks=num_walks, status=status)
+    full.exchange_bytes = parts["bytes_gathered"]
+    return full
+
+
+def sharded_subg_matrix(G, train_idx, num_walks=200, num_steps=4, device=None, seed=111413, rng_mode=None, group=None):
+    """Multi-GPU subg_matrix (sampler/random_walks.py:74-82): (z, enc) with z the replicated device SpG."""
+    from .spg import DeviceGraph
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    graph = DeviceGraph.from_scipy(G, device)
+    z = sharded_sample(graph, np.asarray(train_idx), num_walks=num_walks, num_steps=num_steps - 1, seed=seed,
+                       rng_mode=rng_mode, group=group)
+    graph.close()
+    return z, z.enc_table()

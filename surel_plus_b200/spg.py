@@ -159,6 +159,28 @@ class SpG:
                                           _stream(dev), C.byref(h)))
         return cls(h, dev, n_nodes=x.shape[1])
 
+    @classmethod
+    def from_device_csr(cls, indptr, indices, data, n_nodes=None, enc=None, num_walks=None, status=0) -> "SpG":
+        """Wrap device tensors (indptr int64 [n+1], indices int32 [T] ascending per row, data int32 [T] =
+        LP id + 1 or float64 [T]) as an SpG; the arrays are copied into library-owned HBM.  `enc`: int16
+        [c, ncol] LP table (numpy or tensor) attached to the handle."""
+        lib = _capi.load()
+        dev = indices.device.index if indices.device.index is not None else torch.cuda.current_device()
+        indptr = indptr.to(torch.int64).contiguous()
+        indices = indices.to(torch.int32).contiguous()
+        kind = 1 if data.dtype.is_floating_point else 0
+        data = data.to(torch.float64 if kind else torch.int32).contiguous()
+        h = C.c_void_p()
+        _capi.check(lib.subg_spg_from_csr(indptr.data_ptr(), indices.data_ptr(), data.data_ptr(), kind,
+                                          indptr.numel() - 1, indices.numel(), dev, _stream(dev), C.byref(h)))
+        if enc is not None and not kind:
+            e = enc.cpu().numpy() if isinstance(enc, torch.Tensor) else np.asarray(enc)
+            e = np.ascontiguousarray(e, dtype=np.int16)
+            _capi.check(lib.subg_spg_set_lp_table(h, None, _ptr(e), e.shape[0], e.shape[1], _stream(dev)))
+        out = cls(h, dev, n_nodes=n_nodes, num_walks=num_walks)
+        out.status = status
+        return out
+
     # ---- views / export -----------------------------------------------------
     def views(self) -> dict:
         """Zero-copy torch views of the device arrays (valid while this object lives)."""
@@ -170,10 +192,13 @@ class SpG:
             "indices": _view(p[1].value, (self.T,), "<i4", d, self),
             "data": _view(p[2].value, (self.T,), "<f8" if self.value_kind else "<i4", d, self),
         }
-        if not self.value_kind and p[3].value:
-            out["slot"] = _view(p[3].value, (self.T,), "<u2", d, self)
-            out["enc"] = _view(p[4].value, (self.c, self.ncol), "<i2", d, self)
-            out["nsize"] = _view(p[5].value, (self.n,), "<i4", d, self)
+        if not self.value_kind:
+            if p[3].value:
+                out["slot"] = _view(p[3].value, (self.T,), "<u2", d, self)
+            if p[4].value and self.ncol > 0:
+                out["enc"] = _view(p[4].value, (self.c, self.ncol), "<i2", d, self)
+            if p[5].value:
+                out["nsize"] = _view(p[5].value, (self.n,), "<i4", d, self)
         return out
 
     def export_reference(self, want_raw: bool = False):
@@ -195,6 +220,13 @@ class SpG:
         v = self.views()
         enc = v["enc"].cpu().numpy() if "enc" in v else np.zeros((0, self.ncol), np.int16)
         return np.concatenate([np.zeros((1, self.ncol), np.int16), enc], axis=0)
+
+    @property
+    def pushes(self) -> int:
+        """Forward pushes performed while sampling a PPR SpG (0 otherwise)."""
+        v = C.c_int64(0)
+        _capi.check(self._lib.subg_spg_pushes(self._h, C.byref(v)))
+        return v.value
 
     def to_scipy(self):
         """The equivalent scipy CSR (what the reference's subg_matrix returns)."""

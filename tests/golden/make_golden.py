@@ -140,7 +140,7 @@ def gen_spjoin(out):
 def gen_ppr(out):
     pprgo = ref.pprgo()
     encoding = reference_encoding()
-    A = small_graph().astype(np.float32)  # dataloader.py builds float adjacency; sums are degree counts
+    A = small_graph().astype(np.int64)  # dataloader.py:112-113,119 builds the adjacency from np.ones(dtype=int)
     n = A.shape[0]
     idx = np.arange(n)
     alpha, eps, topk = 0.1, 1e-4, 32

@@ -1,0 +1,88 @@
+"""GPU: the multi-GPU building blocks.  (1) shards of a range-partitioned query sampled with
+subg_gset_sample_shard + LP-table merge + relabel concatenate to exactly the single-call SpG (one GPU
+is enough for that); (2) the full exchange over NCCL with one process per GPU, when >= 2 GPUs exist."""
+import ctypes as C
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import pyoracle as po
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _shard(graph, q, lo, hi, M, m, seed, mode):
+    from surel_plus_b200 import SpG, _capi
+    from surel_plus_b200.spg import _ptr, _stream
+    h = C.c_void_p()
+    _capi.check(_capi.load().subg_gset_sample_shard(graph._h, _ptr(q), q.size, lo, hi, M, m, -1, seed, mode, None,
+                                                     _stream(graph.device), C.byref(h)))
+    return SpG(h, graph.device, n_nodes=graph.N, num_walks=M)
+
+
+@pytest.mark.parametrize("mode_name", ["RAND_R", "PHILOX"])
+@pytest.mark.parametrize("cuts", [(0.5,), (0.1, 0.35, 0.9)])
+def test_shards_concatenate_to_single_call(mid_graph, mode_name, cuts):
+    from surel_plus_b200 import DeviceGraph, SpG, _capi
+    from surel_plus_b200 import parallel as par
+    from surel_plus_b200.spg import _ptr, _stream
+    A = mid_graph
+    n = A.shape[0]
+    M, m, seed = 50, 3, 7
+    mode = getattr(_capi, f"SUBG_RNG_{mode_name}")
+    q = np.random.default_rng(1).permutation(n).astype(np.int32)
+    g = DeviceGraph.from_scipy(A)
+    full = SpG.sample(g, q, M, m, seed=seed, rng_mode=mode)
+    fv = full.views()
+    bounds = [0] + [int(c * n) for c in cuts] + [n]
+    shards = [_shard(g, q, bounds[i], bounds[i + 1], M, m, seed, mode) for i in range(len(bounds) - 1)]
+    tables = [s.views()["enc"].cpu().numpy() for s in shards]
+    merged, maps = par.merge_lp_tables(tables)
+    assert np.array_equal(merged, fv["enc"].cpu().numpy())
+    lib = _capi.load()
+    for s, mp_ in zip(shards, maps):
+        _capi.check(lib.subg_spg_set_lp_table(s._h, _ptr(mp_), _ptr(np.ascontiguousarray(merged)), merged.shape[0], -1,
+                                              _stream(g.device)))
+    for key in ("indices", "data", "nsize"):
+        cat = torch.cat([s.views()[key] for s in shards])
+        assert torch.equal(cat, fv[key]), key
+    if mode_name == "RAND_R":  # and that equals the reference's single stream (oracle replay)
+        nsize, remap, enc = po.gset_sampler_replay(A.indptr, A.indices, q, M, m, -1, seed)
+        assert np.array_equal(fv["nsize"].cpu().numpy(), nsize) and np.array_equal(merged, enc)
+
+
+def test_from_device_csr_roundtrip(mid_graph):
+    from surel_plus_b200 import DeviceGraph, SpG, gather
+    A = mid_graph
+    g = DeviceGraph.from_scipy(A)
+    spg = SpG.sample(g, np.arange(A.shape[0]), 40, 2, seed=3)
+    v = spg.views()
+    twin = SpG.from_device_csr(v["indptr"], v["indices"], v["data"], n_nodes=A.shape[0], enc=v["enc"], num_walks=40)
+    assert twin.T == spg.T and twin.c == spg.c and twin.max_set == spg.max_set
+    assert np.array_equal(twin.enc_table(), spg.enc_table())
+    xpe = torch.from_numpy(spg.enc_table()).float().cuda() / 40
+    edge = np.random.default_rng(0).integers(0, A.shape[0], (2, 500))
+    a, pa = gather(edge, spg, "cuda", True, xpe)
+    b, pb = gather(edge, twin, "cuda", True, xpe)
+    assert torch.equal(a, b) and torch.equal(pa, pb)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_sharded_sample_nccl_two_gpus():
+    """One process per GPU over NCCL: replicated SpG equals the single-GPU one on every rank."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    world = min(torch.cuda.device_count(), 4)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port),
+                        os.path.join(ROOT, "tests", "multi_gpu_worker.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("SHARDED_OK") == world

@@ -115,7 +115,7 @@ def test_triplet_join_equals_reference_hgather(spjoin):
 
 def _adj(gset):
     n = len(gset["graph_indptr"]) - 1
-    return sp.csr_matrix((np.ones(len(gset["graph_indices"]), np.float32), gset["graph_indices"], gset["graph_indptr"]),
+    return sp.csr_matrix((np.ones(len(gset["graph_indices"]), np.int64), gset["graph_indices"], gset["graph_indptr"]),
                          shape=(n, n))
 
 
