@@ -676,8 +676,7 @@ int ppr_topk_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, float alph
             CKG(dmalloc(&ws.r, (size_t)nw * R, st)); CKG(dmalloc(&ws.p, (size_t)nw * R, st));
             CKG(dmalloc(&ws.inq, (size_t)nw * R, st));
             fill_empty_kernel<<<8 * g->num_sms, 256, 0, st>>>(ws.htab, nw * (int64_t)H);
-            CKG(cudaMemsetAsync(counter, 0, (pass == 0 ? 4 : 1) * sizeof(unsigned long long), st));
-            if (pass == 1) CKG(cudaMemsetAsync(counter + 2, 0, sizeof(unsigned long long), st));
+            CKG(cudaMemsetAsync(counter, 0, 4 * sizeof(unsigned long long), st));
             PprArgs a{};
             a.rowptr = g->rowptr; a.rowptr64 = g->rowptr64 ? 1 : 0; a.col = g->col; a.seeds = s->seeds;
             a.work = pass == 0 ? nullptr : work; a.nwork = nwork;
