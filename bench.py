@@ -42,49 +42,55 @@ def log(*a):
 
 # ------------------------------------------------------------------------------ helpers
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled through NVML every 5 ms while the timed region runs
+    (the B200_PROFILING.md clocks line; nvidia-smi itself takes longer to start than a run lasts)."""
 
     def __init__(self, gpu_index: int):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.gpu, self.rows, self.th, self.stop_flag = gpu_index, [], None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+        except Exception:
+            self.nv = None
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
-            self.th = threading.Thread(target=self._pump, daemon=True)
-            self.th.start()
-        except Exception:
-            self.proc = None
+        if self.nv is None:
+            return
+        self.th = threading.Thread(target=self._pump, daemon=True)
+        self.th.start()
 
     def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self) -> dict:
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        nv = self.nv
+        while not self.stop_flag:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-                for nm, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
+                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)))
             except Exception:
                 pass
-        hi = sorted(sm)[len(sm) // 2:] if sm else []
-        return {"sm_mhz": float(np.median(hi)) if hi else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            time.sleep(0.005)
+
+    def stop(self) -> dict:
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        self.stop_flag = True
+        if self.th:
+            self.th.join(timeout=2)
+        nv = self.nv
+        try:
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception:
+            mx = None
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        sm = [float(r[0]) for r in self.rows]
+        reasons = sorted(k for k, bit in names.items() if any(r[1] & bit for r in self.rows))
+        hi = sorted(sm)[len(sm) // 2:] if sm else []  # samples under load = the upper half
+        return {"sm_mhz": float(np.median(hi)) if hi else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm)}
 
 
 def make_graph(workload: str, scale: float):
@@ -228,7 +234,9 @@ def run_ours(args):
 
     # ---- value: graph resident in HBM, SpG left in HBM --------------------------------------
     def step(i):
-        return SpG.sample(graph, q_dev, num_walks=M, num_steps=m, seed=base_seed + i, rng_mode=_capi.SUBG_RNG_PHILOX)
+        # what subg_matrix builds: the SpG (sorted CSR-of-sets + LP table), resident and joinable
+        return SpG.sample(graph, q_dev, num_walks=M, num_steps=m, seed=base_seed + i, rng_mode=_capi.SUBG_RNG_PHILOX,
+                          first_visit_ranks=False)
 
     for i in range(args.warmup):
         step(i).close()
@@ -330,7 +338,7 @@ def bench_spjoin(args, torch, dev, spg, A, M, k, gather, _capi, peaks, barrier, 
     batches = [make_queries(A, B, k, rng) for _ in range(nb)]
     dev_batches = [torch.from_numpy(b).to(dev) for b in batches]
     pin_batches = [torch.from_numpy(b).pin_memory() for b in batches]
-    sizes = np.diff(spg.views()["indptr"].cpu().numpy())
+    sizes = spg.set_sizes().cpu().numpy()
     rows = [int(sizes[b[0]].sum() + sizes[b[1]].sum()) for b in batches]
     # device-resident edges, fused fp32 feature output [N,2,k]
     for i in range(3):

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SUBG_ABI_VERSION 1
+#define SUBG_ABI_VERSION 2
 
 #define SUBG_OK          0
 #define SUBG_ERR_ARG    -1
@@ -50,6 +50,10 @@ extern "C" {
 #define SUBG_STATUS_BUCKET_OVERFLOW 1u /* a set hit `bucket`; reference prints a warning (subg_acc.c:835-836) */
 #define SUBG_STATUS_DEAD_END        2u /* RAND_R replay met a node without out-neighbours: stream no longer matches */
 #define SUBG_STATUS_PPR_SECOND_PASS 4u /* some PPR seeds outgrew the first-pass workspace and were re-run (result unaffected) */
+
+/* flags of subg_gset_sample* */
+#define SUBG_SAMPLE_NO_RANKS 1 /* skip the first-visit ranks (`slot`): the SpG (sorted CSR-of-sets + LP table, what
+                                  subg_matrix builds) is identical, only subg_spg_export needs the ranks */
 
 /* structure encoders of utils.py:20-39 (the 'DEG' branch is broken upstream and not provided) */
 #define SUBG_ENCODER_NONE 0
@@ -79,10 +83,14 @@ void subg_graph_free(subg_graph *g);
  *   num_walks  M (1..32767), num_steps m >= 1 (walk length; CLI --num_steps - 1)
  *   bucket     < 0 -> M*m+1 slots per set, else the reference's `bucket` cap
  *   rng_mode   SUBG_RNG_*; walks_hd only for SUBG_RNG_TRACE
+ *   flags      SUBG_SAMPLE_* bits
+ * The sampler writes every set once, at a device-side cursor, into arrays sized for the worst case,
+ * so the rows of the returned SpG are 16-byte aligned but not back to back ("scattered" layout:
+ * subg_spg_rows); SpJoin reads that layout in place.  subg_spg_views compacts it into the CSR.
  * Synchronises the stream (set sizes decide allocations). */
 int subg_gset_sample(const subg_graph *g, const int32_t *seeds_hd, int64_t n,
                      int num_walks, int num_steps, int bucket, uint64_t seed,
-                     int rng_mode, const int32_t *walks_hd, void *stream, subg_spg **out);
+                     int rng_mode, const int32_t *walks_hd, int flags, void *stream, subg_spg **out);
 
 /* Multi-GPU shard of the same call: seeds_hd is the WHOLE query (n_all entries)
  * and only the sets of the contiguous window [lo, hi) are sampled.  Seed indices stay global
@@ -91,7 +99,7 @@ int subg_gset_sample(const subg_graph *g, const int32_t *seeds_hd, int64_t n,
  * walks_hd (TRACE mode) holds the walks of the window only: int32[hi-lo, num_walks, num_steps]. */
 int subg_gset_sample_shard(const subg_graph *g, const int32_t *seeds_hd, int64_t n_all, int64_t lo,
                            int64_t hi, int num_walks, int num_steps, int bucket, uint64_t seed,
-                           int rng_mode, const int32_t *walks_hd, void *stream, subg_spg **out);
+                           int rng_mode, const int32_t *walks_hd, int flags, void *stream, subg_spg **out);
 
 /* Re-label the LP rows of a shard after the unique tables of all shards were merged in rank
  * order (= the first-occurrence order of subg_acc.c:957-978 over the whole query):
@@ -114,11 +122,19 @@ int subg_spg_export(const subg_spg *s, int32_t *nsize_hd, int32_t *remap_hd,
 /* Device views of the sorted CSR-of-sets (what subg_matrix returns as scipy CSR,
  * sampler/random_walks.py:79): indptr int64[n+1], indices int32[T] ascending per
  * row, data int32[T] = LP-row id + 1 (0 = absent) or float64[T] for value SpGs,
- * slot uint16[T] first-visit rank, enc int16[c, ncol], nsize int32[n].  Any out
- * pointer may be NULL.  Views stay valid until subg_spg_free. */
-int subg_spg_views(const subg_spg *s, const int64_t **indptr, const int32_t **indices,
+ * slot uint16[T] first-visit rank (NULL without ranks), enc int16[c, ncol], nsize int32[n]
+ * (NULL for wrapped CSRs).  Any out pointer may be NULL.  A sampler-built SpG is compacted into
+ * this layout on the first call (one pass over its entries on `stream`, synchronised); earlier
+ * subg_spg_rows pointers become invalid.  Views stay valid until subg_spg_free. */
+int subg_spg_views(subg_spg *s, void *stream, const int64_t **indptr, const int32_t **indices,
                    const void **data, const uint16_t **slot, const int16_t **enc,
                    const int32_t **nsize);
+
+/* The row layout SpJoin reads, without compaction: row u = entries [rowbeg[u], rowbeg[u] + nsize[u])
+ * of indices/data (nsize == NULL for wrapped CSRs: the size is rowbeg[u+1] - rowbeg[u]);
+ * *extent = entries in use (>= T because scattered rows are padded to 16 bytes). */
+int subg_spg_rows(const subg_spg *s, const int64_t **rowbeg, const int32_t **nsize,
+                  const int32_t **indices, const void **data, int64_t *extent);
 
 /* Wrap an existing CSR (e.g. the scipy matrix produced by the reference's
  * subg_matrix / topk_ppr_matrix+encoding) as an SpG for the join.

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "_lib", "libsubg_b200.so")
 
 SUBG_RNG_PHILOX, SUBG_RNG_RAND_R, SUBG_RNG_TRACE = 0, 1, 2
 STATUS_BUCKET_OVERFLOW, STATUS_DEAD_END, STATUS_PPR_SECOND_PASS = 1, 2, 4
+SAMPLE_NO_RANKS = 1
 ENCODER_NONE, ENCODER_PPR, ENCODER_SPD = 0, 1, 2
 TIMING_SAMPLER, TIMING_SPJOIN, TIMING_BUILD, TIMING_PPR = 0, 1, 2, 3
 
@@ -21,7 +22,7 @@ TIMING_SAMPLER, TIMING_SPJOIN, TIMING_BUILD, TIMING_PPR = 0, 1, 2, 3
 SYMBOLS = [
     "subg_abi_version", "subg_last_error",
     "subg_graph_create", "subg_graph_info", "subg_graph_free",
-    "subg_gset_sample", "subg_gset_sample_shard", "subg_spg_set_lp_table", "subg_spg_info", "subg_spg_export", "subg_spg_views",
+    "subg_gset_sample", "subg_gset_sample_shard", "subg_spg_set_lp_table", "subg_spg_info", "subg_spg_export", "subg_spg_views", "subg_spg_rows",
     "subg_spg_from_csr", "subg_spg_free",
     "subg_spjoin_plan", "subg_spjoin_run",
     "subg_ppr_topk", "subg_spg_encode", "subg_spg_pushes",
@@ -53,13 +54,14 @@ def load() -> C.CDLL:
     L.subg_graph_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
     L.subg_graph_free.argtypes = [vp]
     L.subg_graph_free.restype = None
-    L.subg_gset_sample.argtypes = [vp, vp, i64, i32, i32, i32, u64, i32, vp, vp, C.POINTER(vp)]
-    L.subg_gset_sample_shard.argtypes = [vp, vp, i64, i64, i64, i32, i32, i32, u64, i32, vp, vp, C.POINTER(vp)]
+    L.subg_gset_sample.argtypes = [vp, vp, i64, i32, i32, i32, u64, i32, vp, i32, vp, C.POINTER(vp)]
+    L.subg_gset_sample_shard.argtypes = [vp, vp, i64, i64, i64, i32, i32, i32, u64, i32, vp, i32, vp, C.POINTER(vp)]
     L.subg_spg_set_lp_table.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, vp]
     L.subg_spg_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                 C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]
     L.subg_spg_export.argtypes = [vp, vp, vp, vp, vp, vp]
-    L.subg_spg_views.argtypes = [vp] + [C.POINTER(vp)] * 6
+    L.subg_spg_views.argtypes = [vp, vp] + [C.POINTER(vp)] * 6
+    L.subg_spg_rows.argtypes = [vp] + [C.POINTER(vp)] * 4 + [C.POINTER(i64)]
     L.subg_spg_from_csr.argtypes = [vp, vp, vp, i32, i64, i64, i32, vp, C.POINTER(vp)]
     L.subg_spg_free.argtypes = [vp]
     L.subg_spg_free.restype = None

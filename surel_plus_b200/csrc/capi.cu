@@ -61,7 +61,8 @@ bool is_device_ptr(const void *p) {
 }
 
 int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int64_t lo, int64_t hi, int M, int m,
-                     int bucket, uint64_t seed, int rng_mode, const int32_t *walks_hd, cudaStream_t st, SpG **out);
+                     int bucket, uint64_t seed, int rng_mode, const int32_t *walks_hd, int flags, cudaStream_t st,
+                     SpG **out);
 int spg_set_lp_table_impl(SpG *s, const int32_t *id_map_hd, const int16_t *enc_hd, int32_t c_new, int32_t ncol,
                           cudaStream_t st);
 int spg_export_impl(const SpG *s, int32_t *nsize_hd, int32_t *remap_hd, int16_t *enc_hd, int16_t *raw_hd,
@@ -81,6 +82,20 @@ __global__ void widen_rowptr_kernel(const int32_t *in, long long *out, int64_t n
 }
 __global__ void narrow_rowptr_kernel(const long long *in, int32_t *out, int64_t n) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (int32_t)in[i];
+}
+
+// {start, degree} of every row in one aligned word pair: a walk step costs one 8-byte (16-byte) load
+struct RowInfo32 { int32_t start; uint32_t deg; };
+struct RowInfo64 { long long start; uint32_t deg; uint32_t pad; };
+__global__ void rowinfo32_kernel(const int32_t *rowptr, RowInfo32 *out, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = RowInfo32{rowptr[i], (uint32_t)(rowptr[i + 1] - rowptr[i])};
+}
+__global__ void rowinfo64_kernel(const long long *rowptr, RowInfo64 *out, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const long long d = rowptr[i + 1] - rowptr[i];
+        out[i] = RowInfo64{rowptr[i], (uint32_t)(d > 0xffffffffll ? 0xffffffffll : d), 0u};
+    }
 }
 
 static int init_device(int device) {
@@ -142,11 +157,19 @@ int subg_graph_create(const void *rowptr_hd, int rowptr_is64, const int32_t *col
             }
         }
     }
+    if (e == cudaSuccess) e = cudaMallocAsync(&g->rowinfo, ((size_t)N + 1) * (g->rowptr64 ? 16 : 8), st);
+    if (e == cudaSuccess && N > 0) {
+        const unsigned blocks = (unsigned)std::min<int64_t>((N + 255) / 256, 4 * (int64_t)g->num_sms);
+        if (g->rowptr64) rowinfo64_kernel<<<blocks, 256, 0, st>>>((const long long *)g->rowptr, (RowInfo64 *)g->rowinfo, N);
+        else rowinfo32_kernel<<<blocks, 256, 0, st>>>((const int32_t *)g->rowptr, (RowInfo32 *)g->rowinfo, N);
+        e = cudaGetLastError();
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (tmp) cudaFreeAsync(tmp, st);
     if (e != cudaSuccess) {
         if (g->rowptr) cudaFreeAsync(g->rowptr, st);
         if (g->col) cudaFreeAsync(g->col, st);
+        if (g->rowinfo) cudaFreeAsync(g->rowinfo, st);
         delete g;
         return fail(e == cudaErrorMemoryAllocation ? SUBG_ERR_MEM : SUBG_ERR_CUDA, cudaGetErrorString(e));
     }
@@ -169,21 +192,22 @@ void subg_graph_free(subg_graph *g_) {
     DeviceGuard guard(g->device);
     if (g->rowptr) cudaFreeAsync(g->rowptr, 0);
     if (g->col) cudaFreeAsync(g->col, 0);
+    if (g->rowinfo) cudaFreeAsync(g->rowinfo, 0);
     delete g;
 }
 
 int subg_gset_sample(const subg_graph *g, const int32_t *seeds_hd, int64_t n, int num_walks, int num_steps,
-                     int bucket, uint64_t seed, int rng_mode, const int32_t *walks_hd, void *stream,
+                     int bucket, uint64_t seed, int rng_mode, const int32_t *walks_hd, int flags, void *stream,
                      subg_spg **out) {
     return gset_sample_impl(reinterpret_cast<const Graph *>(g), seeds_hd, n, 0, n, num_walks, num_steps, bucket, seed,
-                            rng_mode, walks_hd, (cudaStream_t)stream, reinterpret_cast<SpG **>(out));
+                            rng_mode, walks_hd, flags, (cudaStream_t)stream, reinterpret_cast<SpG **>(out));
 }
 
 int subg_gset_sample_shard(const subg_graph *g, const int32_t *seeds_hd, int64_t n_all, int64_t lo, int64_t hi,
                            int num_walks, int num_steps, int bucket, uint64_t seed, int rng_mode,
-                           const int32_t *walks_hd, void *stream, subg_spg **out) {
+                           const int32_t *walks_hd, int flags, void *stream, subg_spg **out) {
     return gset_sample_impl(reinterpret_cast<const Graph *>(g), seeds_hd, n_all, lo, hi, num_walks, num_steps, bucket,
-                            seed, rng_mode, walks_hd, (cudaStream_t)stream, reinterpret_cast<SpG **>(out));
+                            seed, rng_mode, walks_hd, flags, (cudaStream_t)stream, reinterpret_cast<SpG **>(out));
 }
 
 int subg_spg_set_lp_table(subg_spg *s, const int32_t *id_map_hd, const int16_t *enc_hd, int32_t c_new, int32_t ncol,
@@ -210,10 +234,23 @@ int subg_spg_export(const subg_spg *s, int32_t *nsize_hd, int32_t *remap_hd, int
     return spg_export_impl(reinterpret_cast<const SpG *>(s), nsize_hd, remap_hd, enc_hd, raw_enc_hd, (cudaStream_t)stream);
 }
 
-int subg_spg_views(const subg_spg *s_, const int64_t **indptr, const int32_t **indices, const void **data,
-                   const uint16_t **slot, const int16_t **enc, const int32_t **nsize) {
+int subg_spg_rows(const subg_spg *s_, const int64_t **rowbeg, const int32_t **nsize, const int32_t **indices,
+                  const void **data, int64_t *extent) {
     const SpG *s = reinterpret_cast<const SpG *>(s_);
     if (!s) return fail(SUBG_ERR_ARG, "null SpG");
+    if (rowbeg) *rowbeg = s->rowbeg;
+    if (nsize) *nsize = s->nsize;
+    if (indices) *indices = s->indices;
+    if (data) *data = s->data;
+    if (extent) *extent = s->extent;
+    return SUBG_OK;
+}
+
+int subg_spg_views(subg_spg *s_, void *stream, const int64_t **indptr, const int32_t **indices, const void **data,
+                   const uint16_t **slot, const int16_t **enc, const int32_t **nsize) {
+    SpG *s = reinterpret_cast<SpG *>(s_);
+    if (!s) return fail(SUBG_ERR_ARG, "null SpG");
+    if (int rc = spg_ensure_csr(s, (cudaStream_t)stream)) return rc;
     if (indptr) *indptr = s->indptr;
     if (indices) *indices = s->indices;
     if (data) *data = s->data;

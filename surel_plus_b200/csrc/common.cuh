@@ -67,6 +67,7 @@ struct Graph {
     bool rowptr64 = false;
     void *rowptr = nullptr;  // int32[N+1] or int64[N+1]
     int32_t *col = nullptr;  // int32[E]
+    void *rowinfo = nullptr; // {start, degree} per node in one aligned word pair (8 B, or 16 B with a 64-bit start)
     int num_sms = 148;
     // lazily computed structure properties (-1 unknown): rows strictly ascending; adjacency symmetric
     mutable int sorted_state = -1, sym_state = -1;
@@ -82,10 +83,17 @@ struct SpG {
     int32_t max_set = 0;
     uint32_t status = 0;
     int value_kind = 0;    // 0 int32 pointers, 1 float64 values
+    // Row u occupies entries [rowbeg[u], rowbeg[u] + nsize[u]) of indices/data/slot.  Two layouts:
+    //   compact   indptr != null, rowbeg == indptr (CSR, rows back to back in seed order)
+    //   scattered indptr == null, rowbeg owned: rows sit where the sampler's cursor put them
+    //             (16-byte aligned, any order); ensure_csr() turns this into the compact layout.
     int64_t *indptr = nullptr;   // [n+1]
-    int32_t *indices = nullptr;  // [T] ascending per row
-    void *data = nullptr;        // int32[T] (id+1) or float64[T]
-    uint16_t *slot = nullptr;    // [T] first-visit rank (sampler-built SpGs only)
+    int64_t *rowbeg = nullptr;   // [n]
+    int64_t extent = 0;          // entries in use (== T when compact)
+    int64_t cap = 0;             // entries allocated
+    int32_t *indices = nullptr;  // ascending per row
+    void *data = nullptr;        // int32 (id+1) or float64
+    uint16_t *slot = nullptr;    // first-visit rank (sampler-built SpGs that asked for it)
     int16_t *enc = nullptr;      // [c, ncol]
     int32_t *nsize = nullptr;    // [n]
     int32_t *seeds = nullptr;    // [n] node id of each row
@@ -94,6 +102,7 @@ struct SpG {
 };
 
 void spg_free_impl(SpG *s);
+int spg_ensure_csr(SpG *s, cudaStream_t st);  // scattered -> compact (no-op when compact)
 
 // ------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__

@@ -716,7 +716,7 @@ int ppr_topk_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, float alph
         long long T = 0;
         CKG(cudaMemcpyAsync(&T, s->indptr + n, 8, cudaMemcpyDeviceToHost, st));
         CKG(cudaStreamSynchronize(st));
-        s->T = T;
+        s->T = T; s->rowbeg = s->indptr; s->extent = T; s->cap = T;
         CKG(dmalloc(&s->indices, (size_t)T + 16, st));
         CKG(cudaMallocAsync(&s->data, ((size_t)T + 16) * 8, st));
         if (n > 0) {
@@ -776,7 +776,7 @@ int spg_encode_impl(const Graph *g, const SpG *x, int encoder, cudaStream_t st, 
                 CKG(cudaGetLastError());
                 count_launch(2);
             }
-            s->T = T; s->max_set = x->max_set;
+            s->T = T; s->max_set = x->max_set; s->rowbeg = s->indptr; s->extent = T; s->cap = T;
             if (x->seeds) {
                 CKG(dmalloc(&s->seeds, (size_t)n, st));
                 if (n > 0) CKG(cudaMemcpyAsync(s->seeds, x->seeds, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
@@ -821,7 +821,7 @@ int spg_encode_impl(const Graph *g, const SpG *x, int encoder, cudaStream_t st, 
             int32_t mx = 0;
             CKG(cudaMemcpyAsync(&mx, d_max, 4, cudaMemcpyDeviceToHost, st));
             CKG(cudaStreamSynchronize(st));
-            s->T = To; s->max_set = mx;
+            s->T = To; s->max_set = mx; s->rowbeg = s->indptr; s->extent = To; s->cap = To;
         }
     }
 done:

@@ -1,5 +1,5 @@
-// Walk-based set sampler + LP encoder: one warp per seed, everything between the
-// CSR gathers and the staged set rows stays in registers / shared memory.
+// Walk-based set sampler + LP encoder: one warp per seed; a seed's walks, its dedup/sort and its
+// landing counts never leave the SM, and the finished set is written once, straight into the SpG.
 //
 // Reference behaviour reproduced (file:line relative to /root/reference):
 //   first hop without replacement, later hops uniform    subg_acc/subg_acc.c:763-809
@@ -8,12 +8,23 @@
 //   64-bit LP key, LEAD bit on the root                   subg_acc/subg_acc.c:900-955
 //   first-occurrence ids of unique LP rows                subg_acc/subg_acc.c:957-978
 //
-// B200 design: a seed's M*m visits are packed as (node << OB | order) keys, held
-// EPL per lane, sorted by a register/shuffle bitonic network (no shared-memory
-// traffic, no atomics), so equal nodes become runs: run head = first visit,
-// run population per step = landing counts, and the set comes out already in
-// ascending node order, which is the order the SpG CSR needs.
+// B200 design (per warp, per seed):
+//   1. walk: lanes own walks; every hop issues GW x 32 independent gathers (row info as one
+//      8/16-byte load with an L2 evict_last policy, neighbour column with evict_first), draws
+//      come from Philox4x32-10 (one call = one hop of four walks).  Every visit becomes a key
+//      (node << OB | order) in the warp's shared-memory key buffer; order = 0 for the root and
+//      ((walk + 1) << LS | step) otherwise, so ascending order == the reference's first-visit order.
+//   2. sort: blocked load (EPL keys per lane), register sorting network per lane, then five
+//      merge-path rounds through shared memory.  Equal nodes become runs: the run head carries
+//      the first visit, the run's population per step is the LP row.
+//   3. encode: per-lane packed (4 x 16 bit) step counts, a warp scan stitches runs that straddle
+//      lanes; members are compacted to (key, counts) records in shared memory.
+//   4. emit: the row is allocated with one atomic on a global cursor (16-byte aligned rows) and
+//      written coalesced in ascending node order, the order the SpG CSR-of-sets needs; the LP row
+//      is interned in an L2-resident hash table that also tracks its first stream position.
 #pragma once
+#include <utility>
+
 #include "common.cuh"
 
 namespace subg {
@@ -22,27 +33,32 @@ constexpr int kWarpsPerBlock = 4;
 constexpr uint64_t kEmptyKey = ~0ull;
 constexpr uint32_t kStatusTableFull = 1u << 31;  // internal status bit
 constexpr int kFirstHopCap = 1000000;  // NEBMAX, subg_acc.c:13,750
+constexpr int kGW = 4;                 // walks advanced together per lane
 
 struct SamplerArgs {
-    const void *rowptr;
+    const void *rowinfo;   // RowInfo32[N] or RowInfo64[N]
     int rowptr64;
     const int32_t *col;
     const int32_t *seeds;  // chunk-local [n_chunk]
     int64_t n_chunk;
     int64_t seed_base;     // global index of seeds[0]
-    int M, m, stride;      // stride = reference's bucket stride (cap on set size)
-    int OB;                // bits of the order field
+    int M, m, stride, Kt;  // stride = reference's bucket stride (cap on set size); Kt = M*m+1 keys per seed
+    int OB, LS;            // bits of the order field; log2 of the step slots per walk
     int SHIFT;             // 32 - clz(M), bits per LP column in the key
     int rng_mode;
     uint32_t rng_lo, rng_hi;
     const int64_t *call_base;  // RAND_R: exclusive prefix of rand_r calls, global seed index
     const int32_t *walks;      // TRACE: chunk-local [n_chunk, M, m]
-    // staging rows (chunk-local), row pitch S_pad
-    int32_t *st_node;
-    int32_t *st_prov;
-    uint16_t *st_rank;
-    int S_pad;
-    int32_t *nsize;  // chunk-local
+    // output rows: row i occupies [rowbeg[i], rowbeg[i] + nsize[i]) of the three arrays
+    int32_t *out_node;
+    int32_t *out_prov;
+    uint16_t *out_slot;        // nullable: first-visit ranks are not wanted
+    long long *rowbeg;         // chunk-local
+    int32_t *nsize;            // chunk-local
+    unsigned long long *ctr;   // [0] seed ticket  [1] row cursor (entries, rows padded to 4)  [2] sum of set sizes
+    int32_t *max_set;
+    int want_rank;
+    int hints;                 // bit 0: L2 evict_last on row info, bit 1: L2 evict_first on neighbour gathers
     // LP-key intern table (global, L2 resident)
     unsigned long long *tab_key;
     unsigned long long *tab_pos;
@@ -50,71 +66,165 @@ struct SamplerArgs {
     uint32_t *tab_count;
     uint32_t *status;
     // shared memory carve-up (per warp)
-    int rec_cap;  // records (multiple of 8)
-    int nbw;      // bitmap words
-    int fy_cap;   // Fisher-Yates overflow map capacity (power of two)
+    int nbw;         // bitmap words
+    int fy_cap;      // Fisher-Yates overflow map capacity (power of two)
+    int key_bytes;   // bytes of the key buffer (the Fisher-Yates scratch follows it)
+    int bitmap_off;  // byte offset of the rank bitmap
     int smem_per_warp;
 };
 
-__device__ __forceinline__ int64_t load_rowptr(const SamplerArgs &a, int64_t i) {
-    return a.rowptr64 ? __ldg((const long long *)a.rowptr + i) : (int64_t)__ldg((const int *)a.rowptr + i);
+struct RowInfo32 { int32_t start; uint32_t deg; };
+struct RowInfo64 { long long start; uint32_t deg; uint32_t pad; };
+
+// ---------------------------------------------------------------- cache-policy loads
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint2 ldg_v2_hint(const void *p, uint64_t pol) {
+    uint2 v;
+    asm("ld.global.nc.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ uint4 ldg_v4_hint(const void *p, uint64_t pol) {
+    uint4 v;
+    asm("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+        : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ uint32_t ldg_u32_stream(const void *p, uint64_t pol) {
+    uint32_t v;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
 }
 
-// ---------------------------------------------------------------- register bitonic sort
+struct Policies { uint64_t keep, stream; };
+
+__device__ __forceinline__ void load_row(const SamplerArgs &a, const Policies &pol, uint32_t v, int64_t &start,
+                                         uint32_t &deg) {
+    if (a.rowptr64) {
+        const RowInfo64 *p = (const RowInfo64 *)a.rowinfo + v;
+        uint4 q;
+        if (a.hints & 1) q = ldg_v4_hint(p, pol.keep);
+        else q = __ldg((const uint4 *)p);
+        start = (int64_t)(((uint64_t)q.y << 32) | q.x);
+        deg = q.z;
+    } else {
+        const RowInfo32 *p = (const RowInfo32 *)a.rowinfo + v;
+        uint2 q;
+        if (a.hints & 1) q = ldg_v2_hint(p, pol.keep);
+        else q = __ldg((const uint2 *)p);
+        start = (int64_t)(int32_t)q.x;
+        deg = q.y;
+    }
+}
+__device__ __forceinline__ uint32_t load_col(const SamplerArgs &a, const Policies &pol, int64_t e) {
+    if (a.hints & 2) return ldg_u32_stream(a.col + e, pol.stream);
+    return (uint32_t)__ldg(a.col + e);
+}
+
+// ---------------------------------------------------------------- warp merge sort
 template <typename K>
 __device__ __forceinline__ void cswap(K &a, K &b) {
-    K lo = a < b ? a : b;
-    K hi = a < b ? b : a;
+    const K lo = a < b ? a : b;
+    const K hi = a < b ? b : a;
     a = lo;
     b = hi;
 }
 
-// Sorts the 32*EPL keys held by a warp (lane L register r = element L*EPL + r) ascending.
-// "Flip" formulation of the bitonic network: every comparator keeps the minimum at the lower index.
+// Batcher odd-even merge sort network on EPL registers (any EPL: comparators that would touch
+// indices >= EPL are those of the next power of two with +inf inputs, i.e. no-ops).  The comparator
+// list is computed at compile time and applied through a pack expansion, so every register index is
+// a constant (a loop nest with these bounds is not reliably unrolled and would spill k[] to local memory).
+struct NetCE { int a, b; };
+constexpr NetCE net_walk(int n, int want, int *count) {
+    int c = 0;
+    for (int p = 1; p < n; p <<= 1)
+        for (int q = p; q >= 1; q >>= 1)
+            for (int j = q % p; j + q < n; j += 2 * q)
+                for (int i = 0; i < q && i + j + q < n; i++)
+                    if ((i + j) / (2 * p) == (i + j + q) / (2 * p)) {
+                        if (c == want) return NetCE{i + j, i + j + q};
+                        c++;
+                    }
+    if (count) *count = c;
+    return NetCE{0, 0};
+}
+constexpr int net_size(int n) {
+    int c = 0;
+    net_walk(n, -1, &c);
+    return c;
+}
+template <typename K, int EPL, int I>
+__device__ __forceinline__ void net_ce(K (&k)[EPL]) {
+    constexpr NetCE c = net_walk(EPL, I, nullptr);
+    cswap(k[c.a], k[c.b]);
+}
+template <typename K, int EPL, int... I>
+__device__ __forceinline__ void net_apply(K (&k)[EPL], std::integer_sequence<int, I...>) {
+    (net_ce<K, EPL, I>(k), ...);
+}
 template <typename K, int EPL>
-__device__ __forceinline__ void warp_sort(K (&k)[EPL], int lane) {
-    constexpr int NT = 32 * EPL;
+__device__ __forceinline__ void lane_sort(K (&k)[EPL]) {
+    net_apply<K, EPL>(k, std::make_integer_sequence<int, net_size(EPL)>{});
+}
+
+// Sorts the 32*EPL keys of a warp ascending.  In: lane L holds elements [L*EPL, (L+1)*EPL) of any
+// order.  Out: the same blocked layout, globally sorted.  buf: 32*EPL keys of shared memory owned by
+// the warp.  Keys are distinct except for the ~0 padding.
+template <typename K, int EPL>
+__device__ __forceinline__ void warp_merge_sort(K (&k)[EPL], K *buf, int lane) {
+    constexpr K SENT = ~(K)0;
+    lane_sort<K, EPL>(k);
+#pragma unroll 1
+    for (int r = 0; r < 5; r++) {
 #pragma unroll
-    for (int size = 2; size <= NT; size <<= 1) {
-        if (size <= EPL) {
-#pragma unroll
-            for (int r = 0; r < EPL; r++) {
-                const int p = r ^ (size - 1);
-                if (p > r) cswap(k[r], k[p]);
-            }
-        } else {
-            const int lm = size / EPL - 1;
-            const bool keep_min = (lane & (size / (2 * EPL))) == 0;
-            K nk[EPL];
-#pragma unroll
-            for (int r = 0; r < EPL; r++) {
-                const K o = __shfl_xor_sync(FULL, k[EPL - 1 - r], lm);
-                const K lo = k[r] < o ? k[r] : o;
-                const K hi = k[r] < o ? o : k[r];
-                nk[r] = keep_min ? lo : hi;
-            }
-#pragma unroll
-            for (int r = 0; r < EPL; r++) k[r] = nk[r];
+        for (int j = 0; j < EPL; j++) buf[lane * EPL + j] = k[j];
+        __syncwarp();
+        const int L = EPL << r;                  // run length
+        const int t = lane & ((2 << r) - 1);     // lane index inside the pair of runs
+        const K *A = buf + (lane - t) * EPL;
+        const K *B = A + L;
+        const int diag = t * EPL;
+        int lo = diag > L ? diag - L : 0;
+        int hi = diag < L ? diag : L;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (A[mid] <= B[diag - 1 - mid]) lo = mid + 1;
+            else hi = mid;
         }
+        int ia = lo, ib = diag - lo;
+        K ka = ia < L ? A[ia] : SENT;
+        K kb = ib < L ? B[ib] : SENT;
 #pragma unroll
-        for (int j = size >> 2; j > 0; j >>= 1) {
-            if (j < EPL) {
-#pragma unroll
-                for (int r = 0; r < EPL; r++)
-                    if ((r & j) == 0) cswap(k[r], k[r | j]);
+        for (int j = 0; j < EPL; j++) {
+            const bool ta = ka <= kb;
+            k[j] = ta ? ka : kb;
+            if (ta) {
+                ia++;
+                ka = ia < L ? A[ia] : SENT;
             } else {
-                const int lm = j / EPL;
-                const bool keep_min = (lane & lm) == 0;
-#pragma unroll
-                for (int r = 0; r < EPL; r++) {
-                    const K o = __shfl_xor_sync(FULL, k[r], lm);
-                    const K lo = k[r] < o ? k[r] : o;
-                    const K hi = k[r] < o ? o : k[r];
-                    k[r] = keep_min ? lo : hi;
-                }
+                ib++;
+                kb = ib < L ? B[ib] : SENT;
             }
         }
+        __syncwarp();
     }
+}
+
+__device__ __forceinline__ unsigned long long warp_incl_scan_u64(unsigned long long v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long t = __shfl_up_sync(FULL, v, d);
+        if (lane_id() >= d) v += t;
+    }
+    return v;
 }
 
 // ---------------------------------------------------------------- LP-key interning
@@ -144,59 +254,69 @@ __device__ __forceinline__ uint32_t intern_key(const SamplerArgs &a, unsigned lo
     return h;
 }
 
+template <typename K, int EPL>
+constexpr int sampler_min_blocks() {
+    constexpr int W = (int)sizeof(K) / 4;
+    constexpr int smem_warp = (12 * 32 * EPL > (int)sizeof(K) * 32 * EPL + 4096 ? 12 * 32 * EPL : (int)sizeof(K) * 32 * EPL + 4096) + 256;
+    constexpr int by_smem = 232448 / (kWarpsPerBlock * smem_warp);
+    constexpr int by_regs = 65536 / (kWarpsPerBlock * 32 * (EPL * W + 44));
+    constexpr int b = by_smem < by_regs ? by_smem : by_regs;
+    return b < 1 ? 1 : (b > 8 ? 8 : b);
+}
+
 // ---------------------------------------------------------------- the sampler kernel
-// WT walks per lane, MS step slots per walk (power of two >= m); EPL = WT*MS keys per lane.
-template <typename K, int WT, int MS>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) gset_sample_kernel(const SamplerArgs a) {
-    constexpr int EPL = WT * MS;
-    constexpr int LS = (MS == 1) ? 0 : (MS == 2 ? 1 : 2);
+template <typename K, int EPL>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL>()) gset_sample_kernel(const SamplerArgs a) {
     constexpr K SENT = ~(K)0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     unsigned char *wsm = smem_raw + (size_t)wib * a.smem_per_warp;
+    K *keys = (K *)wsm;
+    // member records alias the key buffer (the keys are in registers by then)
     unsigned long long *rec_cnt = (unsigned long long *)wsm;
-    int32_t *rec_node = (int32_t *)(rec_cnt + a.rec_cap);
-    uint16_t *rec_ord = (uint16_t *)(rec_node + a.rec_cap);
-    uint32_t *bitmap = (uint32_t *)(rec_ord + a.rec_cap);
-    uint32_t *bprefix = bitmap + a.nbw;
-    // Fisher-Yates scratch aliases the record area (used strictly before it)
-    int32_t *fy_pick = (int32_t *)wsm;
+    K *rec_key = (K *)(wsm + 8 * (size_t)a.Kt);
+    // Fisher-Yates scratch follows the key buffer
+    int32_t *fy_pick = (int32_t *)(wsm + a.key_bytes);
     int32_t *fy_dense = fy_pick + a.M;
     int32_t *fy_key = fy_dense + a.M;
     int32_t *fy_val = fy_key + a.fy_cap;
+    uint32_t *bitmap = (uint32_t *)(wsm + a.bitmap_off);
+    uint32_t *bprefix = bitmap + a.nbw;
 
-    const int M = a.M, m = a.m;
-    const uint32_t ord_mask = (1u << a.OB) - 1u;
-    const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+    const int M = a.M, m = a.m, OB = a.OB, LS = a.LS;
+    const uint32_t ord_mask = (1u << OB) - 1u;
+    const uint32_t step_mask = (1u << LS) - 1u;
+    const K no_node = SENT >> OB;
+    Policies pol;
+    pol.keep = l2_policy_evict_last();
+    pol.stream = l2_policy_evict_first();
+    int mx = 0;
 
-    for (int64_t i = (int64_t)blockIdx.x * kWarpsPerBlock + wib; i < a.n_chunk; i += nwarps) {
+    for (;;) {
+        unsigned long long ticket = 0;
+        if (lane == 0) ticket = atomicAdd(&a.ctr[0], 1ull);
+        const int64_t i = (int64_t)__shfl_sync(FULL, ticket, 0);
+        if (i >= a.n_chunk) break;
         const int64_t gi = a.seed_base + i;
         const int32_t u = __ldg(a.seeds + i);
-        K key[EPL];
-#pragma unroll
-        for (int r = 0; r < EPL; r++) key[r] = SENT;
+
+        if (a.want_rank)
+            for (int b = lane; b < a.nbw; b += 32) bitmap[b] = 0u;
 
         if (a.rng_mode == SUBG_RNG_TRACE) {
             const int32_t *wk = a.walks + i * (int64_t)M * m;
-#pragma unroll
-            for (int s = 0; s < MS; s++) {
-                if (s < m) {
-#pragma unroll
-                    for (int t = 0; t < WT; t++) {
-                        const int w = lane + 32 * t;
-                        if (w < M) {
-                            const uint32_t v = (uint32_t)__ldg(wk + (int64_t)w * m + s);
-                            key[s * WT + t] = ((K)v << a.OB) | (K)(1u + ((uint32_t)w << LS) + s);
-                        }
-                    }
-                }
+            for (int j = lane; j < M * m; j += 32) {
+                const uint32_t v = (uint32_t)__ldg(wk + j);
+                const int w = j / m, s = j - w * m;
+                keys[1 + j] = ((K)v << OB) | (K)((((uint32_t)w + 1u) << LS) | (uint32_t)s);
             }
         } else {
-            const int64_t rp0 = load_rowptr(a, u);
-            const int64_t dfull = load_rowptr(a, (int64_t)u + 1) - rp0;
-            const int d = dfull > kFirstHopCap ? kFirstHopCap : (int)dfull;
+            int64_t rp0;
+            uint32_t dfull;
+            load_row(a, pol, (uint32_t)u, rp0, dfull);
+            const int d = dfull > (uint32_t)kFirstHopCap ? kFirstHopCap : (int)dfull;
             const bool replay = a.rng_mode == SUBG_RNG_RAND_R;
             const uint32_t gi_lo = (uint32_t)gi, gi_hi = (uint32_t)((uint64_t)gi >> 32);
             int64_t calls0 = 0;
@@ -204,18 +324,26 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) gset_sample_kernel(const 
 
             // ---- first hop without replacement (subg_acc.c:763-776, 790-800)
             if (d > M) {
-                for (int k = lane; k < M; k += 32) {
-                    uint32_t pick;
-                    if (replay) {
+                if (replay) {
+                    for (int k = lane; k < M; k += 32) {
                         uint32_t st = lcg_jump(a.rng_lo, 3u * (uint32_t)(calls0 + k));
-                        pick = rand_r_dev(st) % (uint32_t)(d - k) + k;
-                    } else {
-                        const uint4 r4 = philox4x32_10(make_uint4(gi_lo, gi_hi, (uint32_t)k, 0x46597331u),
-                                                       make_uint2(a.rng_lo, a.rng_hi));
-                        pick = k + __umulhi(r4.x, (uint32_t)(d - k));
+                        fy_pick[k] = (int32_t)(rand_r_dev(st) % (uint32_t)(d - k) + k);
+                        fy_dense[k] = k;
                     }
-                    fy_pick[k] = (int32_t)pick;
-                    fy_dense[k] = k;
+                } else {
+                    for (int c = lane; 4 * c < M; c += 32) {
+                        const uint4 r4 = philox4x32_10(make_uint4(gi_lo, gi_hi, (uint32_t)c, 0x46597331u),
+                                                       make_uint2(a.rng_lo, a.rng_hi));
+                        const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const int k = 4 * c + q;
+                            if (k < M) {
+                                fy_pick[k] = (int32_t)(k + __umulhi(rr[q], (uint32_t)(d - k)));
+                                fy_dense[k] = k;
+                            }
+                        }
+                    }
                 }
                 for (int h = lane; h < a.fy_cap; h += 32) fy_key[h] = -1;
                 __syncwarp();
@@ -242,128 +370,144 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) gset_sample_kernel(const 
                 calls0 += M;
             }
 
-            // Walks are advanced in groups of GW per lane: all loads of one hop of a group are
-            // issued back to back (GW x 32 gathers in flight per warp), while only the group's
-            // RNG / row state is live in registers.
-            constexpr int GW = WT < 4 ? WT : 4;
+            // Walks are advanced in groups of kGW per lane: all loads of one hop of a group are
+            // issued back to back (kGW x 32 gathers in flight per warp).
+            const int rstep = d > 0 ? 32 % d : 0;   // w % d for w = lane + 32 t, kept incrementally
+            int rr0 = d > 0 ? lane % d : 0;
+            for (int g = 0; g * 32 < M; g += kGW) {
+                uint32_t cur[kGW];
 #pragma unroll
-            for (int g = 0; g < WT; g += GW) {
-                uint32_t cur[GW];
-#pragma unroll
-                for (int tt = 0; tt < GW; tt++) {
-                    const int t = g + tt;
-                    const int w = lane + 32 * t;
+                for (int tt = 0; tt < kGW; tt++) {
+                    const int w = lane + 32 * (g + tt);
                     cur[tt] = (uint32_t)u;
                     if (w < M && d > 0) {
-                        const int off = (d <= M) ? (w % d) : fy_dense[w];
-                        cur[tt] = (uint32_t)__ldg(a.col + rp0 + off);
+                        const int off = (d <= M) ? rr0 : fy_dense[w];
+                        cur[tt] = load_col(a, pol, rp0 + off);
                     }
-                    if (w < M) key[t] = ((K)cur[tt] << a.OB) | (K)(1u + ((uint32_t)w << LS));
+                    if (d > 0) {
+                        rr0 += rstep;
+                        if (rr0 >= d) rr0 -= d;
+                    }
+                    if (w < M) keys[1 + w] = ((K)cur[tt] << OB) | (K)(((uint32_t)w + 1u) << LS);
                 }
                 // ---- later hops, uniform with replacement (subg_acc.c:802-809)
-                uint32_t rst[GW];                  // RAND_R state per walk
-                uint32_t rx[GW], ry[GW], rz[GW];   // Philox draw per walk (steps 1..3)
-                if (m > 1) {
+                uint32_t rst[kGW];
+                if (replay && m > 1) {
 #pragma unroll
-                    for (int tt = 0; tt < GW; tt++) {
+                    for (int tt = 0; tt < kGW; tt++) {
                         const int w = lane + 32 * (g + tt);
-                        if (replay) {
-                            rst[tt] = lcg_jump(a.rng_lo, 3u * (uint32_t)(calls0 + (int64_t)w * (m - 1)));
-                        } else {
-                            const uint4 r4 = philox4x32_10(make_uint4(gi_lo, gi_hi, (uint32_t)w, 0x57414c4bu),
-                                                           make_uint2(a.rng_lo, a.rng_hi));
-                            rx[tt] = r4.x; ry[tt] = r4.y; rz[tt] = r4.z;
-                        }
+                        rst[tt] = lcg_jump(a.rng_lo, 3u * (uint32_t)(calls0 + (int64_t)w * (m - 1)));
                     }
                 }
+                for (int s = 1; s < m; s++) {
+                    int64_t rp[kGW];
+                    uint32_t dn[kGW];
 #pragma unroll
-                for (int s = 1; s < MS; s++) {
-                    if (s < m) {
-                        int64_t rp[GW];
-                        uint32_t dn[GW];
+                    for (int tt = 0; tt < kGW; tt++) load_row(a, pol, cur[tt], rp[tt], dn[tt]);
+                    uint32_t draw[kGW];
+                    if (!replay) {
+                        const uint4 r4 = philox4x32_10(
+                            make_uint4(gi_lo, gi_hi, (uint32_t)(lane + 8 * g) | ((uint32_t)s << 16), 0x57414c4bu),
+                            make_uint2(a.rng_lo, a.rng_hi));
+                        draw[0] = r4.x; draw[1] = r4.y; draw[2] = r4.z; draw[3] = r4.w;
+                    }
 #pragma unroll
-                        for (int tt = 0; tt < GW; tt++) {
-                            rp[tt] = load_rowptr(a, cur[tt]);
-                            dn[tt] = (uint32_t)(load_rowptr(a, (int64_t)cur[tt] + 1) - rp[tt]);
-                        }
-#pragma unroll
-                        for (int tt = 0; tt < GW; tt++) {
-                            const int t = g + tt;
-                            const int w = lane + 32 * t;
-                            if (w < M) {
-                                if (dn[tt] > 0) {
-                                    uint32_t off;
-                                    if (replay) {
-                                        off = rand_r_dev(rst[tt]) % dn[tt];
-                                    } else {
-                                        const uint32_t r = s == 1 ? rx[tt] : (s == 2 ? ry[tt] : rz[tt]);
-                                        off = __umulhi(r, dn[tt]);
-                                    }
-                                    cur[tt] = (uint32_t)__ldg(a.col + rp[tt] + off);
-                                } else if (replay && d > 0) {
-                                    atomicOr(a.status, SUBG_STATUS_DEAD_END);
-                                }
-                                key[s * WT + t] = ((K)cur[tt] << a.OB) | (K)(1u + ((uint32_t)w << LS) + s);
+                    for (int tt = 0; tt < kGW; tt++) {
+                        const int w = lane + 32 * (g + tt);
+                        if (w < M) {
+                            if (dn[tt] > 0) {
+                                uint32_t off;
+                                if (replay) off = rand_r_dev(rst[tt]) % dn[tt];
+                                else off = __umulhi(draw[tt], dn[tt]);
+                                cur[tt] = load_col(a, pol, rp[tt] + off);
+                            } else if (replay && d > 0) {
+                                atomicOr(a.status, SUBG_STATUS_DEAD_END);
                             }
+                            keys[1 + s * M + w] = ((K)cur[tt] << OB) | (K)((((uint32_t)w + 1u) << LS) | (uint32_t)s);
                         }
                     }
                 }
             }
-            __syncwarp();  // fy_dense reads done before the record area is reused
         }
-        // root: order 0, parked in the last register of lane 31 (free by template choice)
-        if (lane == 31) key[EPL - 1] = (K)(uint32_t)u << a.OB;
-
-        warp_sort<K, EPL>(key, lane);
-
-        // ---- runs of equal node = one set member each
-        const K prev_last = __shfl_up_sync(FULL, key[EPL - 1], 1);
-        uint32_t headmask = 0;  // EPL <= 32 bits per word; EPL == 64 uses two words
-        uint32_t headmask_hi = 0;
-#pragma unroll
-        for (int r = 0; r < EPL; r++) {
-            const K pk = r ? key[r - 1] : prev_last;
-            const bool valid = key[r] != SENT;
-            const bool head = valid && ((r == 0 && lane == 0) || ((pk >> a.OB) != (key[r] >> a.OB)));
-            if (head) {
-                if (r < 32) headmask |= 1u << (r & 31);
-                else headmask_hi |= 1u << (r & 31);
-            }
-        }
-        const uint32_t nhead = __popc(headmask) + __popc(headmask_hi);
-        const uint32_t incl = warp_incl_scan(nhead);
-        const int s_total = (int)__shfl_sync(FULL, incl, 31);
-        int idx = (int)(incl - nhead) - 1;
-
-        for (int t = lane; t < s_total; t += 32) rec_cnt[t] = 0ull;
-        for (int b = lane; b < a.nbw; b += 32) bitmap[b] = 0u;
+        if (lane == 0) keys[0] = (K)(uint32_t)u << OB;  // the root: order 0
+        for (int j = a.Kt + lane; j < 32 * EPL; j += 32) keys[j] = SENT;
         __syncwarp();
 
+        K k[EPL];
+#pragma unroll
+        for (int r = 0; r < EPL; r++) k[r] = keys[lane * EPL + r];
+        __syncwarp();
+        warp_merge_sort<K, EPL>(k, keys, lane);
+
+        // ---- runs of equal node = one set member each; heads per lane
+        const K prev_last = __shfl_up_sync(FULL, k[EPL - 1], 1);
+        const K pn0 = lane ? (prev_last >> OB) : no_node;
+        uint32_t nhead = 0;
+#pragma unroll
+        for (int r = 0; r < EPL; r++) {
+            const K pn = r ? (k[r - 1] >> OB) : pn0;
+            const bool head = k[r] != SENT && (k[r] >> OB) != pn;
+            nhead += head ? 1u : 0u;
+            if (a.want_rank && head) {
+                const uint32_t ord = (uint32_t)k[r] & ord_mask;
+                atomicOr(&bitmap[ord >> 5], 1u << (ord & 31));
+            }
+        }
+        const uint32_t incl = warp_incl_scan(nhead);
+        const int s_total = (int)__shfl_sync(FULL, incl, 31);
+        const int kept = s_total < a.stride ? s_total : a.stride;
+        const int kept4 = (kept + 3) & ~3;
+        unsigned long long base_u = 0;
+        if (lane == 0) {
+            base_u = atomicAdd(&a.ctr[1], (unsigned long long)kept4);
+            atomicAdd(&a.ctr[2], (unsigned long long)kept);
+            a.rowbeg[i] = (long long)base_u;
+            a.nsize[i] = kept;
+            if (kept < s_total) atomicOr(a.status, SUBG_STATUS_BUCKET_OVERFLOW);
+        }
+        mx = kept > mx ? kept : mx;
+
+        // ---- landing counts per run: packed 4 x 16 bit, runs that straddle lanes are stitched by a scan
         {
-            unsigned long long acc = 0ull;
+            unsigned long long acc = 0ull, lead = 0ull;
+            bool have = false;
+            K curk = 0;
+            int idx = (int)(incl - nhead) - 1;
 #pragma unroll
             for (int r = 0; r < EPL; r++) {
-                const bool valid = key[r] != SENT;
-                const bool head = r < 32 ? ((headmask >> (r & 31)) & 1u) : ((headmask_hi >> (r & 31)) & 1u);
-                if (valid) {
-                    const uint32_t ord = (uint32_t)key[r] & ord_mask;
-                    if (head) {
-                        if (acc) atomicAdd(&rec_cnt[idx], acc);
-                        acc = 0ull;
-                        idx++;
-                        rec_node[idx] = (int32_t)(key[r] >> a.OB);
-                        rec_ord[idx] = (uint16_t)ord;
-                        atomicOr(&bitmap[ord >> 5], 1u << (ord & 31));
+                const K pn = r ? (k[r - 1] >> OB) : pn0;
+                const bool valid = k[r] != SENT;
+                const bool head = valid && (k[r] >> OB) != pn;
+                if (head) {
+                    if (have) {
+                        rec_key[idx] = curk;
+                        rec_cnt[idx] = acc;
+                    } else {
+                        lead = acc;
                     }
-                    if (ord) acc += 1ull << (16 * ((ord - 1u) & (uint32_t)(MS - 1)));
+                    have = true;
+                    curk = k[r];
+                    acc = 0ull;
+                    idx++;
                 }
+                const uint32_t ord = (uint32_t)k[r] & ord_mask;
+                if (valid && ord) acc += 1ull << (16 * (ord & step_mask));
             }
-            if (acc) atomicAdd(&rec_cnt[idx], acc);
+            if (!have) lead = acc;
+            const unsigned long long S = warp_incl_scan_u64(lead);
+            const uint32_t H = __ballot_sync(FULL, have);
+            const uint32_t above = lane == 31 ? 0u : (H & ~((2u << lane) - 1u));
+            const int nh = above ? (__ffs((int)above) - 1) : 31;
+            const unsigned long long S_nh = __shfl_sync(FULL, S, nh);
+            if (have) {
+                rec_key[idx] = curk;
+                rec_cnt[idx] = acc + (S_nh - S);
+            }
         }
         __syncwarp();
 
         // ---- first-visit rank of every member = popcount prefix over the order bitmap
-        {
+        if (a.want_rank) {
             uint32_t running = 0;
             for (int b0 = 0; b0 < a.nbw; b0 += 32) {
                 const int b = b0 + lane;
@@ -372,41 +516,51 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) gset_sample_kernel(const 
                 if (b < a.nbw) bprefix[b] = running + inc - cnt;
                 running += __shfl_sync(FULL, inc, 31);
             }
+            __syncwarp();
         }
-        __syncwarp();
 
         // ---- emit the set: ascending node id, provisional LP id, first-visit rank
-        int kept = 0;
-        const int64_t row = i * (int64_t)a.S_pad;
+        const long long base = (long long)__shfl_sync(FULL, base_u, 0);
+        const bool overflow = kept < s_total;
+        int done = 0;
         for (int t0 = 0; t0 < s_total; t0 += 32) {
             const int t = t0 + lane;
             const bool act = t < s_total;
-            uint32_t ord = 0, rank = 0;
+            K kk = 0;
+            unsigned long long cnt = 0ull;
             if (act) {
-                ord = rec_ord[t];
-                rank = bprefix[ord >> 5] + __popc(bitmap[ord >> 5] & ((1u << (ord & 31)) - 1u));
+                kk = rec_key[t];
+                cnt = rec_cnt[t];
             }
-            const bool keep = act && (int)rank < a.stride;
-            const uint32_t km = __ballot_sync(FULL, keep);
+            const uint32_t ord = (uint32_t)kk & ord_mask;
+            uint32_t rank = 0;
+            if (a.want_rank && act) rank = bprefix[ord >> 5] + __popc(bitmap[ord >> 5] & ((1u << (ord & 31)) - 1u));
+            bool keep = act;
+            int o = t;
+            if (overflow) {
+                keep = act && (int)rank < a.stride;
+                const uint32_t km = __ballot_sync(FULL, keep);
+                o = done + __popc(km & ((1u << lane) - 1u));
+                done += __popc(km);
+            }
             if (keep) {
-                const int o = kept + __popc(km & ((1u << lane) - 1u));
-                const unsigned long long cnt = rec_cnt[t];
                 unsigned long long lp = 0ull;
                 for (int j = 0; j < m; j++) lp = (lp << a.SHIFT) | ((cnt >> (16 * j)) & 0xffffull);
                 if (ord == 0) lp |= 1ull << (m * a.SHIFT);
-                const uint32_t prov = intern_key(a, lp, ((unsigned long long)gi << 16) | rank);
-                a.st_node[row + o] = rec_node[t];
-                a.st_prov[row + o] = (int32_t)prov;
-                a.st_rank[row + o] = (uint16_t)rank;
+                const uint32_t prov = intern_key(a, lp, ((unsigned long long)gi << 16) | ord);
+                a.out_node[base + o] = (int32_t)(kk >> OB);
+                a.out_prov[base + o] = (int32_t)prov;
+                if (a.out_slot) a.out_slot[base + o] = (uint16_t)rank;
             }
-            kept += __popc(km);
         }
-        if (lane == 0) {
-            a.nsize[i] = kept;
-            if (kept < s_total) atomicOr(a.status, SUBG_STATUS_BUCKET_OVERFLOW);
+        if (lane < kept4 - kept) {  // keep the row padding defined (ids are remapped in place later)
+            a.out_node[base + kept + lane] = 0x7fffffff;
+            a.out_prov[base + kept + lane] = 0;
+            if (a.out_slot) a.out_slot[base + kept + lane] = 0;
         }
-        __syncwarp();  // record area is reused by the next seed
+        __syncwarp();  // the record area is the next seed's key buffer
     }
+    if (lane == 0 && mx > 0) atomicMax(a.max_set, mx);
 }
 
 // rand_r calls consumed per seed in the reference's single stream:

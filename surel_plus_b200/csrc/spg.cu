@@ -1,7 +1,8 @@
 // SpG construction on the device: sampler launch, set-size scan, row compaction,
 // first-occurrence ranking of the unique LP rows, export in the reference's layout.
 //
-//   dense compaction            subg_acc/subg_acc.c:848-872  -> compact_rows_kernel
+//   dense compaction            subg_acc/subg_acc.c:848-872  -> rows are written once at a cursor by the sampler;
+//                                                               compact_rows_kernel only for CSR views / chunked runs
 //   unique ids / enc table      subg_acc/subg_acc.c:957-1000 -> collect/finalize kernels + remap
 //   CSR-of-sets (sorted cols)   sampler/random_walks.py:79-80 -> rows leave the sampler sorted
 //   return list                 subg_acc/subg_acc.c:1017-1024 -> export kernels
@@ -16,9 +17,25 @@
 
 namespace subg {
 
-// implemented in sampler_k32.cu / sampler_k64.cu
-cudaError_t launch_gset_sample_k32(const SamplerArgs &a, int WT, int MS, int num_sms, cudaStream_t st);
-cudaError_t launch_gset_sample_k64(const SamplerArgs &a, int WT, int MS, int num_sms, cudaStream_t st);
+// implemented in sampler_k32*.cu / sampler_k64*.cu (EPL = keys per lane of the warp sort)
+#define SUBG_DECL(n) cudaError_t n(const SamplerArgs &a, int EPL, int num_sms, cudaStream_t st);
+SUBG_DECL(launch_gset_sample_k32a) SUBG_DECL(launch_gset_sample_k32b) SUBG_DECL(launch_gset_sample_k32c)
+SUBG_DECL(launch_gset_sample_k32d) SUBG_DECL(launch_gset_sample_k64a) SUBG_DECL(launch_gset_sample_k64b)
+SUBG_DECL(launch_gset_sample_k64c) SUBG_DECL(launch_gset_sample_k64d)
+#undef SUBG_DECL
+static cudaError_t launch_gset_sample_k32(const SamplerArgs &a, int EPL, int num_sms, cudaStream_t st) {
+    if (EPL <= 13) return launch_gset_sample_k32a(a, EPL, num_sms, st);
+    if (EPL <= 21) return launch_gset_sample_k32b(a, EPL, num_sms, st);
+    if (EPL <= 33) return launch_gset_sample_k32c(a, EPL, num_sms, st);
+    return launch_gset_sample_k32d(a, EPL, num_sms, st);
+}
+static cudaError_t launch_gset_sample_k64(const SamplerArgs &a, int EPL, int num_sms, cudaStream_t st) {
+    if (EPL <= 13) return launch_gset_sample_k64a(a, EPL, num_sms, st);
+    if (EPL <= 21) return launch_gset_sample_k64b(a, EPL, num_sms, st);
+    if (EPL <= 33) return launch_gset_sample_k64c(a, EPL, num_sms, st);
+    return launch_gset_sample_k64d(a, EPL, num_sms, st);
+}
+static const int kEplList[] = {3, 5, 7, 9, 11, 13, 15, 17, 19, 21, 25, 29, 33, 41, 49, 63};
 
 static int ceil_log2(uint64_t x) {
     int b = 0;
@@ -39,25 +56,22 @@ __global__ void fill_u64_kernel(unsigned long long *p, int64_t n, unsigned long 
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
-// staging rows (pitch S_pad) -> dense rows at indptr[i]; one warp per row
-__global__ void compact_rows_kernel(const int32_t *st_node, const int32_t *st_prov, const uint16_t *st_rank,
-                                    int S_pad, const int32_t *nsize, const long long *indptr, int64_t n_chunk,
-                                    int32_t *indices, int32_t *data, uint16_t *slot, int32_t *max_set) {
+// rows at rowbeg[i] (any order) -> dense rows at indptr[i]; one warp per row
+__global__ void compact_rows_kernel(const int32_t *src_node, const int32_t *src_data, const uint16_t *src_slot,
+                                    const long long *rowbeg, const int32_t *nsize, const long long *indptr,
+                                    int64_t n_rows, int32_t *indices, int32_t *data, uint16_t *slot) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    int mx = 0;
-    for (int64_t i = warp; i < n_chunk; i += nwarps) {
+    for (int64_t i = warp; i < n_rows; i += nwarps) {
         const int s = nsize[i];
-        const int64_t src = i * (int64_t)S_pad, dst = indptr[i];
+        const int64_t src = rowbeg[i], dst = indptr[i];
         for (int j = lane; j < s; j += 32) {
-            indices[dst + j] = st_node[src + j];
-            data[dst + j] = st_prov[src + j];
-            slot[dst + j] = st_rank[src + j];
+            indices[dst + j] = src_node[src + j];
+            data[dst + j] = src_data[src + j];
+            if (slot) slot[dst + j] = src_slot[src + j];
         }
-        mx = max(mx, s);
     }
-    if (lane == 0 && mx > 0) atomicMax(max_set, mx);
 }
 
 __global__ void collect_unique_kernel(const unsigned long long *tab_key, const unsigned long long *tab_pos,
@@ -99,17 +113,18 @@ __global__ void relabel_ids_kernel(int32_t *data, int64_t T, const int32_t *id_m
     }
 }
 
-// reference layout: entries of a set in first-visit order, ids without the +1
-__global__ void export_remap_kernel(const long long *indptr, const int32_t *indices, const int32_t *data,
-                                    const uint16_t *slot, int64_t n, int64_t T, int32_t *remap,
-                                    const int16_t *enc, int ncol, int16_t *raw) {
+// reference layout: entries of a set in first-visit order, ids without the +1.
+// dstptr: exclusive scan of the set sizes (== indptr of the compact layout)
+__global__ void export_remap_kernel(const long long *rowbeg, const int32_t *nsize, const long long *dstptr,
+                                    const int32_t *indices, const int32_t *data, const uint16_t *slot, int64_t n,
+                                    int64_t T, int32_t *remap, const int16_t *enc, int ncol, int16_t *raw) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t i = warp; i < n; i += nwarps) {
-        const int64_t b = indptr[i], e = indptr[i + 1];
+        const int64_t b = rowbeg[i], e = b + nsize[i], db = dstptr[i];
         for (int64_t j = b + lane; j < e; j += 32) {
-            const int64_t d = b + slot[j];
+            const int64_t d = db + slot[j];
             const int32_t id = data[j] - 1;
             remap[d] = indices[j];
             remap[T + d] = id;
@@ -119,15 +134,54 @@ __global__ void export_remap_kernel(const long long *indptr, const int32_t *indi
     }
 }
 
+__global__ void row_sizes_kernel(const long long *indptr, int64_t n, int32_t *nsize) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        nsize[i] = (int32_t)(indptr[i + 1] - indptr[i]);
+}
+
 static void free_spg_arrays(SpG *s, cudaStream_t st) {
+    if (s->rowbeg && (void *)s->rowbeg != (void *)s->indptr) dfree(s->rowbeg, st);
     dfree(s->indptr, st); dfree(s->indices, st); dfree(s->data, st); dfree(s->slot, st);
     dfree(s->enc, st); dfree(s->nsize, st); dfree(s->seeds, st);
-    s->indptr = nullptr; s->indices = nullptr; s->data = nullptr; s->slot = nullptr;
+    s->indptr = nullptr; s->rowbeg = nullptr; s->indices = nullptr; s->data = nullptr; s->slot = nullptr;
     s->enc = nullptr; s->nsize = nullptr; s->seeds = nullptr;
 }
 
+// scattered rows -> compact CSR (rows back to back in seed order); frees the slack of the cursor layout
+int spg_ensure_csr(SpG *s, cudaStream_t st) {
+    if (!s) return fail(SUBG_ERR_ARG, "null SpG");
+    if (s->indptr) return SUBG_OK;
+    DeviceGuard guard(s->device);
+    const int64_t n = s->n;
+    int64_t *indptr = nullptr;
+    long long *scratch = nullptr;
+    int32_t *ni = nullptr, *nd = nullptr;
+    uint16_t *ns = nullptr;
+    SUBG_CUDA(dmalloc(&indptr, (size_t)n + 1, st));
+    SUBG_CUDA(dmalloc(&scratch, (size_t)std::max(1, scan_num_blocks(n)), st));
+    SUBG_CUDA(exclusive_scan_i32_i64(s->nsize, (long long *)indptr, n, 0, scratch, st));
+    SUBG_CUDA(dmalloc(&ni, (size_t)s->T + 16, st));
+    SUBG_CUDA(dmalloc(&nd, (size_t)s->T + 16, st));
+    if (s->slot) SUBG_CUDA(dmalloc(&ns, (size_t)s->T + 16, st));
+    if (n > 0) {
+        const int64_t cblocks = std::min<int64_t>((n * 32 + 255) / 256, 8 * (int64_t)s->num_sms);
+        compact_rows_kernel<<<(unsigned)std::max<int64_t>(cblocks, 1), 256, 0, st>>>(
+            s->indices, (const int32_t *)s->data, s->slot, (const long long *)s->rowbeg, s->nsize,
+            (const long long *)indptr, n, ni, nd, ns);
+        SUBG_CUDA(cudaGetLastError());
+        count_launch(4);
+    }
+    SUBG_CUDA(cudaStreamSynchronize(st));
+    dfree(scratch, st);
+    dfree(s->indices, st); dfree(s->data, st); dfree(s->slot, st); dfree(s->rowbeg, st);
+    s->indices = ni; s->data = nd; s->slot = ns;
+    s->indptr = indptr; s->rowbeg = indptr;
+    s->extent = s->T; s->cap = s->T + 16;
+    return SUBG_OK;
+}
+
 struct SamplePlan {
-    int WT, MS, OB, SHIFT, stride, S_pad, rec_cap, nbw, fy_cap, smem_per_warp;
+    int EPL, OB, LS, SHIFT, stride, Kt, rowcap, nbw, fy_cap, key_bytes, bitmap_off, smem_per_warp;
     bool key64;
 };
 
@@ -139,31 +193,31 @@ static int make_plan(const Graph *g, int M, int m, int bucket, SamplePlan *p) {
     while ((M >> shift) != 0) shift++;
     if ((int64_t)m * shift + 1 > 64)  // subg_acc.c:905-915
         return fail(SUBG_ERR_ASSERT, "Longer width of type for hasing key needed > INT64.");
-    if (m > 4 || M > 512)
-        return fail(SUBG_ERR_UNSUPPORTED, "this build supports num_steps <= 4 and num_walks <= 512");
+    const int64_t Kt = (int64_t)M * m + 1;
+    const int max_epl = kEplList[sizeof(kEplList) / sizeof(int) - 1];
+    if (m > 4 || Kt > 32 * (int64_t)max_epl)
+        return fail(SUBG_ERR_UNSUPPORTED, "this build supports num_steps <= 4 and num_walks * num_steps <= 2015");
     p->SHIFT = shift;
-    p->MS = m <= 2 ? 2 : 4;
-    const int LS = p->MS == 2 ? 1 : 2;
-    int W = (M + 31) / 32, WT = 1;
-    while (WT < W) WT <<= 1;
-    if (m == p->MS && 32 * WT == M) WT <<= 1;  // keep lane 31's last register free for the root
-    if (WT > 16) return fail(SUBG_ERR_UNSUPPORTED, "num_walks too large for the register-resident sampler");
-    p->WT = WT;
-    const uint32_t max_ord = 1u + ((uint32_t)(M - 1) << LS) + (uint32_t)(m - 1);
+    p->Kt = (int)Kt;
+    p->LS = m <= 1 ? 0 : (m <= 2 ? 1 : 2);
+    p->EPL = max_epl;
+    for (int e : kEplList)
+        if (32 * e >= Kt) { p->EPL = e; break; }
+    const uint32_t max_ord = ((uint32_t)M << p->LS) | (uint32_t)(m - 1);
     p->OB = ceil_log2((uint64_t)max_ord + 1);
     p->key64 = !((uint64_t)g->N <= (1ull << (32 - p->OB)) - 1ull);
-    const int full = M * m + 1;
-    p->stride = bucket < 0 ? full : bucket;
-    const int eff = std::min(p->stride, full);
-    p->S_pad = (eff + 7) & ~7;
-    p->rec_cap = (full + 7) & ~7;
+    const int ksz = p->key64 ? 8 : 4;
+    p->stride = bucket < 0 ? (int)Kt : bucket;
+    p->rowcap = (std::min(p->stride, (int)Kt) + 3) & ~3;
     p->nbw = (int)((max_ord + 1 + 31) / 32);
     int fc = 16;
-    while (fc < 2 * M) fc <<= 1;
+    while (fc < M + M / 4) fc <<= 1;
     p->fy_cap = fc;
-    const int rec_bytes = p->rec_cap * 14 + p->nbw * 8;
+    p->key_bytes = ksz * 32 * p->EPL;
+    const int rec_bytes = (8 + ksz) * (int)Kt;
     const int fy_bytes = 8 * M + 8 * fc;
-    p->smem_per_warp = (std::max(rec_bytes, fy_bytes) + 15) & ~15;
+    p->bitmap_off = (std::max(rec_bytes, p->key_bytes + fy_bytes) + 15) & ~15;
+    p->smem_per_warp = (p->bitmap_off + 8 * p->nbw + 15) & ~15;
     return SUBG_OK;
 }
 
@@ -171,7 +225,8 @@ static int make_plan(const Graph *g, int M, int m, int bucket, SamplePlan *p) {
 // indices stay global (Philox counters, rand_r call offsets, first-occurrence positions), so the
 // shards of a range-partitioned query concatenate to exactly the single-call result.
 int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int64_t lo, int64_t hi, int M, int m,
-                     int bucket, uint64_t seed, int rng_mode, const int32_t *walks_hd, cudaStream_t st, SpG **out) {
+                     int bucket, uint64_t seed, int rng_mode, const int32_t *walks_hd, int flags, cudaStream_t st,
+                     SpG **out) {
     if (!g || !out || n_all < 0 || (n_all > 0 && !seeds_hd) || lo < 0 || hi < lo || hi > n_all)
         return fail(SUBG_ERR_ARG, "Input parsing error.");
     const int64_t n = hi - lo;
@@ -180,16 +235,18 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
     SamplePlan pl;
     if (int rc = make_plan(g, M, m, bucket, &pl)) return rc;
     DeviceGuard guard(g->device);
+    const bool want_slot = !(flags & SUBG_SAMPLE_NO_RANKS);
+    const bool want_rank = want_slot || pl.stride < pl.Kt;
 
     SpG *s = new SpG();
     s->device = g->device; s->n = n; s->ncol = m + 1; s->M = M; s->num_sms = g->num_sms; s->value_kind = 0;
 
     // everything below that is not part of the SpG is scratch
-    int32_t *d_walks = nullptr, *d_calls = nullptr, *st_node = nullptr, *st_prov = nullptr, *rank_of_slot = nullptr;
-    int32_t *d_all_seeds = nullptr;
-    uint16_t *st_rank = nullptr;
-    long long *call_base = nullptr, *scan_scratch = nullptr;
-    unsigned long long *tab_key = nullptr, *tab_pos = nullptr, *u_pos = nullptr, *u_pos2 = nullptr;
+    int32_t *d_walks = nullptr, *d_calls = nullptr, *rank_of_slot = nullptr, *d_all_seeds = nullptr;
+    int32_t *c_node = nullptr, *c_prov = nullptr;  // chunk rows (chunked mode only)
+    uint16_t *c_slot = nullptr;
+    long long *call_base = nullptr, *scan_scratch = nullptr, *c_rowbeg = nullptr;
+    unsigned long long *tab_key = nullptr, *tab_pos = nullptr, *u_pos = nullptr, *u_pos2 = nullptr, *d_ctr = nullptr;
     uint32_t *u_slot = nullptr, *u_slot2 = nullptr, *d_flags = nullptr;  // [0]=status [1]=tab_count [2]=bad seeds [3]=unique cnt
     int32_t *d_maxset = nullptr;
     void *cub_tmp = nullptr;
@@ -210,11 +267,10 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
     {
         CK(dmalloc(&s->seeds, (size_t)n, st));
         CK(dmalloc(&s->nsize, (size_t)n, st));
-        CK(dmalloc(&s->indptr, (size_t)n + 1, st));
         CK(dmalloc(&d_flags, 4, st));
         CK(dmalloc(&d_maxset, 1, st));
+        CK(dmalloc(&d_ctr, 4, st));
         CK(cudaMemsetAsync(d_flags, 0, 4 * sizeof(uint32_t), st));
-        CK(cudaMemsetAsync(d_maxset, 0, sizeof(int32_t), st));
         if (n > 0) {
             CK(cudaMemcpyAsync(s->seeds, seeds_hd + lo, (size_t)n * sizeof(int32_t), cudaMemcpyDefault, st));
             check_seeds_kernel<<<std::min<int64_t>((n + 255) / 256, 4 * g->num_sms), 256, 0, st>>>(s->seeds, n, g->N, d_flags + 2);
@@ -249,16 +305,40 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
                 CK(cudaMemcpyAsync(d_walks, walks_hd, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, st));
             }
         }
+        {   // the bad-seed flag must be known before any kernel indexes the graph with a seed
+            uint32_t bad = 0;
+            CK(cudaMemcpyAsync(&bad, d_flags + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (bad) { rc = fail(SUBG_ERR_ARG, "query contains node ids outside [0, N)"); goto done; }
+        }
 
-        // staging: chunk of seeds x S_pad entries x (node 4B + provisional id 4B + rank 2B)
-        const int64_t budget = env_i64("SUBG_STAGING_BYTES", 6ll << 30);
-        int64_t chunk = std::max<int64_t>(1, budget / ((int64_t)pl.S_pad * 10));
+        // Rows are written once, at a cursor, into arrays sized for the worst case (rowcap entries per
+        // seed).  If that does not fit the budget the seeds go through in chunks and every chunk is
+        // compacted into the growing CSR (the layout of the reference's dense `encoding`, subg_acc.c:848-872).
+        const int entry_bytes = want_slot ? 10 : 8;
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const int64_t budget = env_i64("SUBG_STAGING_BYTES", (int64_t)(free_b * 0.45));
+        int64_t chunk = std::max<int64_t>(1, budget / ((int64_t)pl.rowcap * entry_bytes));
         chunk = std::min<int64_t>(chunk, std::max<int64_t>(n, 1));
-        CK(dmalloc(&st_node, (size_t)chunk * pl.S_pad, st));
-        CK(dmalloc(&st_prov, (size_t)chunk * pl.S_pad, st));
-        CK(dmalloc(&st_rank, (size_t)chunk * pl.S_pad, st));
+        const bool chunked = chunk < n;
+        const int64_t rows_cap = chunk * pl.rowcap + 16;
+        if (chunked) {
+            CK(dmalloc(&c_node, (size_t)rows_cap, st));
+            CK(dmalloc(&c_prov, (size_t)rows_cap, st));
+            if (want_slot) CK(dmalloc(&c_slot, (size_t)rows_cap, st));
+            CK(dmalloc(&c_rowbeg, (size_t)chunk, st));
+            CK(dmalloc(&s->indptr, (size_t)n + 1, st));
+        } else {
+            CK(dmalloc(&s->indices, (size_t)rows_cap, st));
+            CK(dmalloc((int32_t **)&s->data, (size_t)rows_cap, st));
+            if (want_slot) CK(dmalloc(&s->slot, (size_t)rows_cap, st));
+            CK(dmalloc(&s->rowbeg, (size_t)std::max<int64_t>(n, 1), st));
+            cap = rows_cap;
+        }
 
         int tab_log2 = (int)env_i64("SUBG_LP_TABLE_LOG2", 20);
+        const int hints = (int)env_i64("SUBG_SAMPLER_HINTS", 3);
         for (int attempt = 0;; attempt++) {
             const uint32_t tab_cap = 1u << tab_log2;
             CK(dmalloc(&tab_key, (size_t)tab_cap, st));
@@ -268,60 +348,73 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
             CK(cudaMemsetAsync(d_flags, 0, 2 * sizeof(uint32_t), st));
             CK(cudaMemsetAsync(d_maxset, 0, sizeof(int32_t), st));
 
-            int64_t T = 0;
+            int64_t T = 0, extent = 0;
             bool table_full = false;
             for (int64_t base = 0; base < n; base += chunk) {
                 const int64_t nc = std::min(chunk, n - base);
+                CK(cudaMemsetAsync(d_ctr, 0, 4 * sizeof(unsigned long long), st));
                 SamplerArgs a{};
-                a.rowptr = g->rowptr; a.rowptr64 = g->rowptr64 ? 1 : 0; a.col = g->col;
+                a.rowinfo = g->rowinfo; a.rowptr64 = g->rowptr64 ? 1 : 0; a.col = g->col;
                 a.seeds = s->seeds + base; a.n_chunk = nc; a.seed_base = lo + base;
-                a.M = M; a.m = m; a.stride = pl.stride; a.OB = pl.OB; a.SHIFT = pl.SHIFT;
+                a.M = M; a.m = m; a.stride = pl.stride; a.Kt = pl.Kt; a.OB = pl.OB; a.LS = pl.LS; a.SHIFT = pl.SHIFT;
                 a.rng_mode = rng_mode; a.rng_lo = (uint32_t)seed; a.rng_hi = (uint32_t)(seed >> 32);
                 a.call_base = (const int64_t *)call_base;
                 a.walks = d_walks ? d_walks + base * (int64_t)M * m : nullptr;
-                a.st_node = st_node; a.st_prov = st_prov; a.st_rank = st_rank; a.S_pad = pl.S_pad;
+                a.out_node = chunked ? c_node : s->indices;
+                a.out_prov = chunked ? c_prov : (int32_t *)s->data;
+                a.out_slot = chunked ? c_slot : s->slot;
+                a.rowbeg = chunked ? c_rowbeg : (long long *)s->rowbeg;
                 a.nsize = s->nsize + base;
+                a.ctr = d_ctr; a.max_set = d_maxset; a.want_rank = want_rank ? 1 : 0; a.hints = hints;
                 a.tab_key = tab_key; a.tab_pos = tab_pos; a.tab_mask = tab_cap - 1;
                 a.tab_count = d_flags + 1; a.status = d_flags;
-                a.rec_cap = pl.rec_cap; a.nbw = pl.nbw; a.fy_cap = pl.fy_cap; a.smem_per_warp = pl.smem_per_warp;
+                a.nbw = pl.nbw; a.fy_cap = pl.fy_cap; a.key_bytes = pl.key_bytes; a.bitmap_off = pl.bitmap_off;
+                a.smem_per_warp = pl.smem_per_warp;
                 timing_begin(SUBG_TIMING_SAMPLER, st);
-                CK(pl.key64 ? launch_gset_sample_k64(a, pl.WT, pl.MS, g->num_sms, st)
-                            : launch_gset_sample_k32(a, pl.WT, pl.MS, g->num_sms, st));
+                CK(pl.key64 ? launch_gset_sample_k64(a, pl.EPL, g->num_sms, st)
+                            : launch_gset_sample_k32(a, pl.EPL, g->num_sms, st));
                 timing_end(SUBG_TIMING_SAMPLER, st);
                 count_launch(1);
+                unsigned long long hctr[3];
+                uint32_t flags_h[2];
+                CK(cudaMemcpyAsync(hctr, d_ctr, sizeof(hctr), cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(flags_h, d_flags, sizeof(flags_h), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                if (flags_h[1] > tab_cap / 2 || (flags_h[0] & kStatusTableFull)) { table_full = true; break; }
+                if (!chunked) {
+                    T = (int64_t)hctr[2];
+                    extent = (int64_t)hctr[1];
+                    break;
+                }
+                // ---- chunked mode: append the chunk's rows to the CSR
                 timing_begin(SUBG_TIMING_BUILD, st);
                 CK(exclusive_scan_i32_i64(s->nsize + base, (long long *)s->indptr + base, nc, T, scan_scratch, st));
                 count_launch(3);
-                long long T_new = 0;
-                uint32_t flags[3];
-                CK(cudaMemcpyAsync(&T_new, s->indptr + base + nc, sizeof(long long), cudaMemcpyDeviceToHost, st));
-                CK(cudaMemcpyAsync(flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
-                CK(cudaStreamSynchronize(st));
-                if (flags[2]) { rc = fail(SUBG_ERR_ARG, "query contains node ids outside [0, N)"); goto done; }
-                if (flags[1] > tab_cap / 2 || (flags[0] & kStatusTableFull)) { table_full = true; break; }
-                if (T_new > cap) {  // grow the dense arrays (exact when one chunk covers all seeds)
+                const int64_t T_new = T + (int64_t)hctr[2];
+                if (T_new > cap) {
                     int64_t want = T_new;
                     if (base + nc < n) want = std::max<int64_t>(T_new, (int64_t)((double)T_new * n / (base + nc) * 1.05) + 1024);
                     int32_t *ni = nullptr, *nd = nullptr; uint16_t *ns = nullptr;
                     CK(dmalloc(&ni, (size_t)want + 16, st));
                     CK(dmalloc(&nd, (size_t)want + 16, st));
-                    CK(dmalloc(&ns, (size_t)want + 16, st));
+                    if (want_slot) CK(dmalloc(&ns, (size_t)want + 16, st));
                     if (T > 0) {
                         CK(cudaMemcpyAsync(ni, s->indices, (size_t)T * 4, cudaMemcpyDeviceToDevice, st));
                         CK(cudaMemcpyAsync(nd, s->data, (size_t)T * 4, cudaMemcpyDeviceToDevice, st));
-                        CK(cudaMemcpyAsync(ns, s->slot, (size_t)T * 2, cudaMemcpyDeviceToDevice, st));
+                        if (want_slot) CK(cudaMemcpyAsync(ns, s->slot, (size_t)T * 2, cudaMemcpyDeviceToDevice, st));
                     }
                     dfree(s->indices, st); dfree(s->data, st); dfree(s->slot, st);
                     s->indices = ni; s->data = nd; s->slot = ns;
-                    cap = want;
+                    cap = want + 16;
                 }
                 const int64_t cblocks = std::min<int64_t>((nc * 32 + 255) / 256, 8 * (int64_t)g->num_sms);
                 compact_rows_kernel<<<(unsigned)std::max<int64_t>(cblocks, 1), 256, 0, st>>>(
-                    st_node, st_prov, st_rank, pl.S_pad, s->nsize + base, (const long long *)s->indptr + base, nc,
-                    s->indices, (int32_t *)s->data, s->slot, d_maxset);
+                    c_node, c_prov, c_slot, c_rowbeg, s->nsize + base, (const long long *)s->indptr + base, nc,
+                    s->indices, (int32_t *)s->data, s->slot);
                 timing_end(SUBG_TIMING_BUILD, st);
                 count_launch(1);
                 T = T_new;
+                extent = T_new;
             }
             if (table_full) {
                 dfree(tab_key, st); dfree(tab_pos, st); tab_key = nullptr; tab_pos = nullptr;
@@ -329,14 +422,17 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
                 if (tab_log2 > 30) { rc = fail(SUBG_ERR_MEM, "LP-row table exceeds 2^30 entries"); goto done; }
                 continue;
             }
-            if (n == 0) CK(cudaMemsetAsync(s->indptr, 0, sizeof(int64_t), st));
-            s->T = T;
+            if (chunked && n > 0) s->rowbeg = s->indptr;
+            s->T = T; s->extent = extent; s->cap = cap;
 
             // ---- unique LP rows in first-occurrence order
             uint32_t hflags[2];
+            int32_t mx = 0;
             CK(cudaMemcpyAsync(hflags, d_flags, sizeof(hflags), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(&mx, d_maxset, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             s->status = hflags[0] & ~kStatusTableFull;
+            s->max_set = mx;
             const uint32_t c = hflags[1];
             s->c = (int32_t)c;
             CK(dmalloc(&s->enc, (size_t)c * (m + 1), st));
@@ -345,37 +441,50 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
                 CK(dmalloc(&u_pos, (size_t)c, st)); CK(dmalloc(&u_pos2, (size_t)c, st));
                 CK(dmalloc(&u_slot, (size_t)c, st)); CK(dmalloc(&u_slot2, (size_t)c, st));
                 CK(dmalloc(&rank_of_slot, (size_t)tab_cap, st));
+                CK(cudaMemsetAsync(rank_of_slot, 0, (size_t)tab_cap * 4, st));
                 collect_unique_kernel<<<4 * g->num_sms, 256, 0, st>>>(tab_key, tab_pos, tab_cap, u_pos, u_slot, d_flags + 3);
                 size_t tmp_bytes = 0;
                 CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, u_pos, u_pos2, u_slot, u_slot2, (int)c, 0, 64, st));
                 CK(cudaMallocAsync(&cub_tmp, tmp_bytes ? tmp_bytes : 1, st));
                 CK(cub::DeviceRadixSort::SortPairs(cub_tmp, tmp_bytes, u_pos, u_pos2, u_slot, u_slot2, (int)c, 0, 64, st));
                 finalize_unique_kernel<<<(c + 255) / 256, 256, 0, st>>>(u_slot2, c, tab_key, M, m, pl.SHIFT, rank_of_slot, s->enc);
-                if (T > 0) {
-                    const int64_t rb = std::min<int64_t>((T + 255) / 256, 16 * (int64_t)g->num_sms);
-                    remap_ids_kernel<<<(unsigned)rb, 256, 0, st>>>((int32_t *)s->data, T, rank_of_slot);
+                if (extent > 0) {
+                    const int64_t rb = std::min<int64_t>((extent + 1023) / 1024, 16 * (int64_t)g->num_sms);
+                    remap_ids_kernel<<<(unsigned)rb, 256, 0, st>>>((int32_t *)s->data, extent, rank_of_slot);
                 }
                 timing_end(SUBG_TIMING_BUILD, st);
-                count_launch(3);
+                count_launch(4);
             }
-            int32_t mx = 0;
-            CK(cudaMemcpyAsync(&mx, d_maxset, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            s->max_set = mx;
             break;
         }
-        if (!s->indices) {  // n == 0 or all empty: keep valid (padded) arrays
-            CK(dmalloc(&s->indices, 16, st)); CK(dmalloc((int32_t **)&s->data, 16, st)); CK(dmalloc(&s->slot, 16, st));
+        if (!s->indices) {  // n == 0: keep valid (padded) arrays
+            CK(dmalloc(&s->indices, 16, st)); CK(dmalloc((int32_t **)&s->data, 16, st));
+            if (want_slot) CK(dmalloc(&s->slot, 16, st));
+            cap = 16;
+        }
+        if (n == 0) {
+            if (!s->indptr) CK(dmalloc(&s->indptr, 1, st));
+            CK(cudaMemsetAsync(s->indptr, 0, sizeof(int64_t), st));
+            if (s->rowbeg && (void *)s->rowbeg != (void *)s->indptr) dfree(s->rowbeg, st);
+            s->rowbeg = s->indptr;
+        }
+        CK(cudaStreamSynchronize(st));
+        // a mostly empty worst-case allocation is not worth keeping
+        if (!s->indptr && cap > s->extent + s->extent / 4 + (16ll << 20)) {
+            timing_begin(SUBG_TIMING_BUILD, st);
+            const int erc = spg_ensure_csr(s, st);
+            timing_end(SUBG_TIMING_BUILD, st);
+            if (erc != SUBG_OK) { rc = erc; goto done; }
         }
     }
 done:
 #undef CK
     if (walks_owned) dfree(d_walks, st);
     dfree(d_calls, st); dfree(call_base, st); dfree(scan_scratch, st); dfree(d_all_seeds, st);
-    dfree(st_node, st); dfree(st_prov, st); dfree(st_rank, st);
+    dfree(c_node, st); dfree(c_prov, st); dfree(c_slot, st); dfree(c_rowbeg, st);
     dfree(tab_key, st); dfree(tab_pos, st); dfree(u_pos, st); dfree(u_pos2, st);
     dfree(u_slot, st); dfree(u_slot2, st); dfree(rank_of_slot, st);
-    dfree(d_flags, st); dfree(d_maxset, st); dfree(cub_tmp, st);
+    dfree(d_flags, st); dfree(d_maxset, st); dfree(d_ctr, st); dfree(cub_tmp, st);
     if (rc != SUBG_OK) {
         free_spg_arrays(s, st);
         delete s;
@@ -400,9 +509,9 @@ int spg_set_lp_table_impl(SpG *s, const int32_t *id_map_hd, const int16_t *enc_h
     SUBG_CUDA(dmalloc(&d_enc, (size_t)c_new * s->ncol, st));
     if (s->c > 0) SUBG_CUDA(cudaMemcpyAsync(d_map, id_map_hd, (size_t)s->c * 4, cudaMemcpyDefault, st));
     if (c_new > 0) SUBG_CUDA(cudaMemcpyAsync(d_enc, enc_hd, (size_t)c_new * s->ncol * 2, cudaMemcpyDefault, st));
-    if (s->T > 0) {
-        const int64_t rb = std::min<int64_t>((s->T + 255) / 256, 16 * (int64_t)s->num_sms);
-        relabel_ids_kernel<<<(unsigned)rb, 256, 0, st>>>((int32_t *)s->data, s->T, d_map, s->c, c_new);
+    if (s->extent > 0) {
+        const int64_t rb = std::min<int64_t>((s->extent + 255) / 256, 16 * (int64_t)s->num_sms);
+        relabel_ids_kernel<<<(unsigned)rb, 256, 0, st>>>((int32_t *)s->data, s->extent, d_map, s->c, c_new);
         SUBG_CUDA(cudaGetLastError());
         count_launch(1);
     }
@@ -417,7 +526,8 @@ int spg_set_lp_table_impl(SpG *s, const int32_t *id_map_hd, const int16_t *enc_h
 int spg_export_impl(const SpG *s, int32_t *nsize_hd, int32_t *remap_hd, int16_t *enc_hd, int16_t *raw_hd,
                     cudaStream_t st) {
     if (!s) return fail(SUBG_ERR_ARG, "null SpG");
-    if (s->value_kind != 0 || !s->slot) return fail(SUBG_ERR_ARG, "export needs a sampler-built LP SpG");
+    if (s->value_kind != 0 || !s->slot)
+        return fail(SUBG_ERR_ARG, "export needs a sampler-built LP SpG with first-visit ranks (not SUBG_SAMPLE_NO_RANKS)");
     DeviceGuard guard(s->device);
     const int64_t T = s->T, n = s->n;
     const int ncol = s->ncol;
@@ -436,10 +546,18 @@ int spg_export_impl(const SpG *s, int32_t *nsize_hd, int32_t *remap_hd, int16_t 
             if (raw_dev) d_raw = raw_hd;
             else SUBG_CUDA(dmalloc(&d_raw, (size_t)T * ncol, st));
         }
+        long long *dstptr = (long long *)s->indptr, *scratch = nullptr;
+        if (!dstptr) {  // scattered rows: the reference's dense order is the scan of the set sizes
+            SUBG_CUDA(dmalloc(&dstptr, (size_t)n + 1, st));
+            SUBG_CUDA(dmalloc(&scratch, (size_t)std::max(1, scan_num_blocks(n)), st));
+            SUBG_CUDA(exclusive_scan_i32_i64(s->nsize, dstptr, n, 0, scratch, st));
+        }
         const int64_t blocks = std::min<int64_t>((n * 32 + 255) / 256, 8 * (int64_t)s->num_sms);
         export_remap_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), 256, 0, st>>>(
-            (const long long *)s->indptr, s->indices, (const int32_t *)s->data, s->slot, n, T, d_remap, s->enc, ncol, d_raw);
+            (const long long *)s->rowbeg, s->nsize, dstptr, s->indices, (const int32_t *)s->data, s->slot, n, T, d_remap,
+            s->enc, ncol, d_raw);
         SUBG_CUDA(cudaGetLastError());
+        if (!s->indptr) { dfree(dstptr, st); dfree(scratch, st); }
         if (remap_hd && !remap_dev)
             SUBG_CUDA(cudaMemcpyAsync(remap_hd, d_remap, (size_t)2 * T * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         if (raw_hd && !raw_dev)
@@ -491,6 +609,7 @@ int spg_from_csr_impl(const int64_t *indptr_hd, const int32_t *indices_hd, const
         return fail(SUBG_ERR_ARG, "indptr does not describe nnz entries");
     }
     s->max_set = (int32_t)std::min<int64_t>(mx, INT32_MAX);
+    s->rowbeg = s->indptr; s->extent = nnz; s->cap = nnz + 16;
     SUBG_CUDA(cudaStreamSynchronize(st));
     *out = s;
     return SUBG_OK;

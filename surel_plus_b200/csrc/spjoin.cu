@@ -23,7 +23,8 @@ namespace subg {
 constexpr int kJoinThreads = 128;
 
 struct JoinArgs {
-    const long long *indptr;
+    const long long *rowbeg;   // first entry of every row
+    const int32_t *nsize;      // row sizes, or null: compact CSR, size = rowbeg[u + 1] - rowbeg[u]
     const int32_t *indices;
     const void *data;
     int64_t n_rows;
@@ -38,6 +39,10 @@ struct JoinArgs {
     int64_t ntask;
     int cap;  // staged elements per row slice
 };
+
+__device__ __forceinline__ int row_size(const JoinArgs &p, int64_t u) {
+    return p.nsize ? p.nsize[u] : (int)(p.rowbeg[u + 1] - p.rowbeg[u]);
+}
 
 __device__ __forceinline__ void task_nodes(const JoinArgs &p, int64_t t, int64_t &a, int64_t &b, int64_t &segA,
                                            int64_t &segB) {
@@ -57,8 +62,8 @@ __device__ __forceinline__ void task_nodes(const JoinArgs &p, int64_t t, int64_t
 }
 
 // ------------------------------------------------------------------ plan: segment sizes
-__global__ void join_sizes_kernel(const long long *indptr, int64_t n_rows, const long long *edge, int64_t B, int arity,
-                                  int32_t *sizes, uint32_t *bad) {
+__global__ void join_sizes_kernel(const long long *rowbeg, const int32_t *nsize, int64_t n_rows, const long long *edge,
+                                  int64_t B, int arity, int32_t *sizes, uint32_t *bad) {
     const int64_t nseg = arity == 2 ? 2 * B : 4 * B;
     for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < nseg; g += (int64_t)gridDim.x * blockDim.x) {
         int64_t node;
@@ -72,7 +77,7 @@ __global__ void join_sizes_kernel(const long long *indptr, int64_t n_rows, const
             atomicOr(bad, 1u);
             sizes[g] = 0;
         } else {
-            sizes[g] = (int32_t)(indptr[node + 1] - indptr[node]);
+            sizes[g] = nsize ? nsize[node] : (int32_t)(rowbeg[node + 1] - rowbeg[node]);
         }
     }
 }
@@ -153,8 +158,8 @@ __global__ void __launch_bounds__(kJoinThreads) spjoin_kernel(const JoinArgs p) 
             int64_t a, b, segA, segB;
             task_nodes(p, t, a, b, segA, segB);
             TaskDesc d;
-            d.pa = p.indptr[a]; d.sa = (int)(p.indptr[a + 1] - d.pa);
-            d.pb = p.indptr[b]; d.sb = (int)(p.indptr[b + 1] - d.pb);
+            d.pa = p.rowbeg[a]; d.sa = row_size(p, a);
+            d.pb = p.rowbeg[b]; d.sb = row_size(p, b);
             d.offA = p.seg_ptr[segA]; d.offB = p.seg_ptr[segB];
             d.segA = segA; d.segB = segB;
             const long long a0 = d.pa & ~3ll, b0 = d.pb & ~3ll;
@@ -252,8 +257,8 @@ __global__ void __launch_bounds__(kJoinThreads) spjoin_global_kernel(const JoinA
         for (int dir = 0; dir < 2; dir++) {
             const int64_t x = dir ? b : a, y = dir ? a : b;
             const int64_t seg = dir ? segB : segA;
-            const long long px = p.indptr[x], py = p.indptr[y];
-            const int64_t sx = p.indptr[x + 1] - px, sy = p.indptr[y + 1] - py;
+            const long long px = p.rowbeg[x], py = p.rowbeg[y];
+            const int64_t sx = row_size(p, x), sy = row_size(p, y);
             const long long off = p.seg_ptr[seg];
             for (int64_t j = threadIdx.x; j < sx; j += kJoinThreads) {
                 const int32_t w = p.indices[px + j];
@@ -306,7 +311,8 @@ int spjoin_plan_impl(const SpG *s, const int64_t *edge_hd, int64_t B, int arity,
     SUBG_CUDA(cudaMemsetAsync(bad, 0, sizeof(uint32_t), st));
     if (nseg > 0) {
         const unsigned blocks = (unsigned)std::min<int64_t>((nseg + 255) / 256, 4 * (int64_t)s->num_sms);
-        join_sizes_kernel<<<blocks, 256, 0, st>>>((const long long *)s->indptr, s->n, edge, B, arity, sizes, bad);
+        join_sizes_kernel<<<blocks, 256, 0, st>>>((const long long *)s->rowbeg, s->indptr ? nullptr : s->nsize, s->n, edge, B,
+                                                  arity, sizes, bad);
     }
     SUBG_CUDA(exclusive_scan_i32_i64(sizes, (long long *)indptr_dev, nseg, 0, scratch, st));
     count_launch(4);
@@ -352,7 +358,7 @@ int spjoin_run_impl(const SpG *s, const int64_t *edge_dev, int64_t B, int arity,
     if (enc_table_dev && (s->value_kind != 0 || k < 1)) return fail(SUBG_ERR_ARG, "table lookup needs an int SpG and k >= 1");
     DeviceGuard guard(s->device);
     JoinArgs p{};
-    p.indptr = (const long long *)s->indptr; p.indices = s->indices; p.data = s->data; p.n_rows = s->n;
+    p.rowbeg = (const long long *)s->rowbeg; p.nsize = s->indptr ? nullptr : s->nsize; p.indices = s->indices; p.data = s->data; p.n_rows = s->n;
     p.edge = (const long long *)edge_dev; p.B = B; p.arity = arity; p.seg_ptr = (const long long *)indptr_dev;
     p.enc = enc_table_dev; p.k = k; p.out = out_dev; p.segid = (long long *)segid_dev;
     p.ntask = arity == 2 ? B : 2 * B;

@@ -160,8 +160,8 @@ def sharded_sample(graph, query, num_walks=100, num_steps=3, bucket=-1, seed=111
     h = C.c_void_p()
     mode = _capi.SUBG_RNG_PHILOX if rng_mode is None else rng_mode
     _capi.check(lib.subg_gset_sample_shard(graph._h, _ptr(q), n, lo, hi, int(num_walks), int(num_steps), int(bucket),
-                                           int(seed) & 0xFFFFFFFFFFFFFFFF, int(mode), None, _stream(graph.device),
-                                           C.byref(h)))
+                                           int(seed) & 0xFFFFFFFFFFFFFFFF, int(mode), None, _capi.SAMPLE_NO_RANKS,
+                                           _stream(graph.device), C.byref(h)))
     shard = SpG(h, graph.device, n_nodes=graph.N, num_walks=num_walks)
     v = shard.views()
 

@@ -21,7 +21,7 @@ def subg_matrix(G, train_idx, num_walks=200, num_steps=4, device="cuda", seed=11
     if own:
         graph = DeviceGraph.from_scipy(G, device)
     z = SpG.sample(graph, idx, num_walks=num_walks, num_steps=num_steps - 1, seed=seed,
-                   rng_mode=_capi.SUBG_RNG_PHILOX if rng_mode is None else rng_mode)
+                   rng_mode=_capi.SUBG_RNG_PHILOX if rng_mode is None else rng_mode, first_visit_ranks=False)
     if own:
         graph.close()
     return z, z.enc_table()

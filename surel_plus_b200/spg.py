@@ -117,9 +117,11 @@ class SpG:
     # ---- construction -------------------------------------------------------
     @classmethod
     def sample(cls, graph: DeviceGraph, query, num_walks=100, num_steps=3, bucket=-1, seed=111413,
-               rng_mode=_capi.SUBG_RNG_PHILOX, walks=None) -> "SpG":
+               rng_mode=_capi.SUBG_RNG_PHILOX, walks=None, first_visit_ranks=True) -> "SpG":
         """Walk-based set sampling + LP encoding + SpG build on the device
-        (subg_acc.c:649-1034 and random_walks.py:79).  `num_steps` is the walk length m."""
+        (subg_acc.c:649-1034 and random_walks.py:79).  `num_steps` is the walk length m.
+        first_visit_ranks=False skips the per-entry first-visit rank that only export_reference()
+        (the reference's `remap` order) needs; the SpG itself is identical."""
         lib = _capi.load()
         if isinstance(query, torch.Tensor):
             q = query.to(torch.int32).contiguous()
@@ -137,7 +139,8 @@ class SpG:
         h = C.c_void_p()
         _capi.check(lib.subg_gset_sample(graph._h, _ptr(q), n, int(num_walks), int(num_steps), int(bucket),
                                          int(seed) & 0xFFFFFFFFFFFFFFFF, int(rng_mode), _ptr(w) if w is not None else None,
-                                         _stream(graph.device), C.byref(h)))
+                                         0 if first_visit_ranks else _capi.SAMPLE_NO_RANKS, _stream(graph.device),
+                                         C.byref(h)))
         return cls(h, graph.device, n_nodes=graph.N, num_walks=num_walks)
 
     @classmethod
@@ -183,9 +186,10 @@ class SpG:
 
     # ---- views / export -----------------------------------------------------
     def views(self) -> dict:
-        """Zero-copy torch views of the device arrays (valid while this object lives)."""
+        """Zero-copy torch views of the device arrays in the CSR layout (valid while this object
+        lives).  A sampler-built SpG is compacted into that layout on the first call."""
         p = [C.c_void_p() for _ in range(6)]
-        _capi.check(self._lib.subg_spg_views(self._h, *[C.byref(x) for x in p]))
+        _capi.check(self._lib.subg_spg_views(self._h, _stream(self.device), *[C.byref(x) for x in p]))
         d = self.device
         out = {
             "indptr": _view(p[0].value, (self.n + 1,), "<i8", d, self),
@@ -200,6 +204,16 @@ class SpG:
             if p[5].value:
                 out["nsize"] = _view(p[5].value, (self.n,), "<i4", d, self)
         return out
+
+    def set_sizes(self) -> torch.Tensor:
+        """int32 [n] set sizes without forcing the CSR layout."""
+        p = [C.c_void_p() for _ in range(4)]
+        ext = C.c_int64()
+        _capi.check(self._lib.subg_spg_rows(self._h, *[C.byref(x) for x in p], C.byref(ext)))
+        if p[1].value:
+            return _view(p[1].value, (self.n,), "<i4", self.device, self).clone()
+        rb = _view(p[0].value, (self.n + 1,), "<i8", self.device, self)
+        return (rb[1:] - rb[:-1]).to(torch.int32)
 
     def export_reference(self, want_raw: bool = False):
         """[nsize, remap, enc(, raw_enc)] exactly as gset_sampler returns them

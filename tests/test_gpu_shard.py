@@ -23,7 +23,7 @@ def _shard(graph, q, lo, hi, M, m, seed, mode):
     from surel_plus_b200.spg import _ptr, _stream
     h = C.c_void_p()
     _capi.check(_capi.load().subg_gset_sample_shard(graph._h, _ptr(q), q.size, lo, hi, M, m, -1, seed, mode, None,
-                                                     _stream(graph.device), C.byref(h)))
+                                                     0, _stream(graph.device), C.byref(h)))
     return SpG(h, graph.device, n_nodes=graph.N, num_walks=M)
 
 
