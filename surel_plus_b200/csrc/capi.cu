@@ -1,6 +1,7 @@
 // extern "C" surface of libsubg_b200.so (declared in include/subg_b200.h).
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -84,17 +85,16 @@ __global__ void narrow_rowptr_kernel(const long long *in, int32_t *out, int64_t 
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (int32_t)in[i];
 }
 
-// {start, degree} of every row in one aligned word pair: a walk step costs one 8-byte (16-byte) load
-struct RowInfo32 { int32_t start; uint32_t deg; };
-struct RowInfo64 { long long start; uint32_t deg; uint32_t pad; };
-__global__ void rowinfo32_kernel(const int32_t *rowptr, RowInfo32 *out, int64_t n) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        out[i] = RowInfo32{rowptr[i], (uint32_t)(rowptr[i + 1] - rowptr[i])};
-}
-__global__ void rowinfo64_kernel(const long long *rowptr, RowInfo64 *out, int64_t n) {
+// {start, degree} of every row packed in one 64-bit word (start: low 40 bits, degree: high 24 bits), so a
+// walk step costs one 8-byte load whatever the rowptr width.  Degrees >= 2^24 - 1 store the escape value
+// 0xFFFFFF and are read from rowptr.
+template <typename P>
+__global__ void rowinfo_kernel(const P *rowptr, unsigned long long *out, int64_t n) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const long long d = rowptr[i + 1] - rowptr[i];
-        out[i] = RowInfo64{rowptr[i], (uint32_t)(d > 0xffffffffll ? 0xffffffffll : d), 0u};
+        const unsigned long long start = (unsigned long long)rowptr[i];
+        unsigned long long d = (unsigned long long)(rowptr[i + 1] - rowptr[i]);
+        if (d > 0xFFFFFFull) d = 0xFFFFFFull;
+        out[i] = (d << 40) | start;
     }
 }
 
@@ -105,6 +105,10 @@ static int init_device(int device) {
         return fail(SUBG_ERR_CUDA, "no CUDA device: libsubg_b200 has no CPU fallback");
     }
     if (device < 0 || device >= count) return fail(SUBG_ERR_ARG, "bad device index");
+    if (const char *v = getenv("SUBG_L2_FETCH")) {  // experiment knob: L2 fetch granularity hint (32 / 64 / 128 bytes)
+        DeviceGuard guard(device);
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(v));
+    }
     // keep freed scratch in the stream-ordered pool instead of returning it to the driver
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -157,11 +161,12 @@ int subg_graph_create(const void *rowptr_hd, int rowptr_is64, const int32_t *col
             }
         }
     }
-    if (e == cudaSuccess) e = cudaMallocAsync(&g->rowinfo, ((size_t)N + 1) * (g->rowptr64 ? 16 : 8), st);
+    if (e == cudaSuccess && E >= (1ll << 40)) e = cudaErrorInvalidValue;  // 40-bit row starts
+    if (e == cudaSuccess) e = cudaMallocAsync(&g->rowinfo, ((size_t)N + 1) * 8, st);
     if (e == cudaSuccess && N > 0) {
         const unsigned blocks = (unsigned)std::min<int64_t>((N + 255) / 256, 4 * (int64_t)g->num_sms);
-        if (g->rowptr64) rowinfo64_kernel<<<blocks, 256, 0, st>>>((const long long *)g->rowptr, (RowInfo64 *)g->rowinfo, N);
-        else rowinfo32_kernel<<<blocks, 256, 0, st>>>((const int32_t *)g->rowptr, (RowInfo32 *)g->rowinfo, N);
+        if (g->rowptr64) rowinfo_kernel<long long><<<blocks, 256, 0, st>>>((const long long *)g->rowptr, (unsigned long long *)g->rowinfo, N);
+        else rowinfo_kernel<int32_t><<<blocks, 256, 0, st>>>((const int32_t *)g->rowptr, (unsigned long long *)g->rowinfo, N);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);

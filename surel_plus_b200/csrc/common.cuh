@@ -67,7 +67,7 @@ struct Graph {
     bool rowptr64 = false;
     void *rowptr = nullptr;  // int32[N+1] or int64[N+1]
     int32_t *col = nullptr;  // int32[E]
-    void *rowinfo = nullptr; // {start, degree} per node in one aligned word pair (8 B, or 16 B with a 64-bit start)
+    void *rowinfo = nullptr; // uint64[N]: row start (low 40 bits) | degree (high 24 bits, 0xFFFFFF = read rowptr)
     int num_sms = 148;
     // lazily computed structure properties (-1 unknown): rows strictly ascending; adjacency symmetric
     mutable int sorted_state = -1, sym_state = -1;

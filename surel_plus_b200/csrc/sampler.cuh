@@ -33,10 +33,11 @@ constexpr int kWarpsPerBlock = 4;
 constexpr uint64_t kEmptyKey = ~0ull;
 constexpr uint32_t kStatusTableFull = 1u << 31;  // internal status bit
 constexpr int kFirstHopCap = 1000000;  // NEBMAX, subg_acc.c:13,750
-constexpr int kGW = 4;                 // walks advanced together per lane
+constexpr int kGW = 8;                 // walks advanced together per lane
 
 struct SamplerArgs {
-    const void *rowinfo;   // RowInfo32[N] or RowInfo64[N]
+    const unsigned long long *rowinfo;  // [N] row start (low 40 bits) | degree (high 24 bits, 0xFFFFFF = escape)
+    const void *rowptr;    // escape path only
     int rowptr64;
     const int32_t *col;
     const int32_t *seeds;  // chunk-local [n_chunk]
@@ -59,6 +60,8 @@ struct SamplerArgs {
     int32_t *max_set;
     int want_rank;
     int hints;                 // bit 0: L2 evict_last on row info, bit 1: L2 evict_first on neighbour gathers
+    int blocks_per_sm;         // 0 = as many as fit; otherwise a cap (fewer blocks leave more of the SM's 228 KB to L1)
+    int stop_after;            // measurement only (SUBG_SAMPLER_STOP): 1 = walks, 2 = + sort, 3 = + counts; 0 = full kernel
     // LP-key intern table (global, L2 resident)
     unsigned long long *tab_key;
     unsigned long long *tab_pos;
@@ -68,13 +71,11 @@ struct SamplerArgs {
     // shared memory carve-up (per warp)
     int nbw;         // bitmap words
     int fy_cap;      // Fisher-Yates overflow map capacity (power of two)
-    int key_bytes;   // bytes of the key buffer (the Fisher-Yates scratch follows it)
+    int lp_off;      // byte offset of the member LP rows (region 2; region 1 at 0 = key buffer / member keys)
+    int lp64;        // LP rows need 64 bits (m * SHIFT + 1 > 32)
     int bitmap_off;  // byte offset of the rank bitmap
     int smem_per_warp;
 };
-
-struct RowInfo32 { int32_t start; uint32_t deg; };
-struct RowInfo64 { long long start; uint32_t deg; uint32_t pad; };
 
 // ---------------------------------------------------------------- cache-policy loads
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
@@ -92,12 +93,6 @@ __device__ __forceinline__ uint2 ldg_v2_hint(const void *p, uint64_t pol) {
     asm("ld.global.nc.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
     return v;
 }
-__device__ __forceinline__ uint4 ldg_v4_hint(const void *p, uint64_t pol) {
-    uint4 v;
-    asm("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
-        : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
-    return v;
-}
 __device__ __forceinline__ uint32_t ldg_u32_stream(const void *p, uint64_t pol) {
     uint32_t v;
     asm("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
@@ -106,22 +101,18 @@ __device__ __forceinline__ uint32_t ldg_u32_stream(const void *p, uint64_t pol) 
 
 struct Policies { uint64_t keep, stream; };
 
-__device__ __forceinline__ void load_row(const SamplerArgs &a, const Policies &pol, uint32_t v, int64_t &start,
-                                         uint32_t &deg) {
-    if (a.rowptr64) {
-        const RowInfo64 *p = (const RowInfo64 *)a.rowinfo + v;
-        uint4 q;
-        if (a.hints & 1) q = ldg_v4_hint(p, pol.keep);
-        else q = __ldg((const uint4 *)p);
-        start = (int64_t)(((uint64_t)q.y << 32) | q.x);
-        deg = q.z;
-    } else {
-        const RowInfo32 *p = (const RowInfo32 *)a.rowinfo + v;
-        uint2 q;
-        if (a.hints & 1) q = ldg_v2_hint(p, pol.keep);
-        else q = __ldg((const uint2 *)p);
-        start = (int64_t)(int32_t)q.x;
-        deg = q.y;
+// issue / decode split so that a group's row loads are all in flight before the first is consumed
+__device__ __forceinline__ uint2 load_row_raw(const SamplerArgs &a, const Policies &pol, uint32_t v) {
+    if (a.hints & 1) return ldg_v2_hint(a.rowinfo + v, pol.keep);
+    return __ldg((const uint2 *)(a.rowinfo + v));
+}
+__device__ __forceinline__ void decode_row(const SamplerArgs &a, uint32_t v, uint2 q, int64_t &start, uint32_t &deg) {
+    start = (int64_t)(((uint64_t)(q.y & 0xffu) << 32) | q.x);
+    deg = q.y >> 8;
+    if (deg == 0xFFFFFFu) {  // hub with >= 2^24 - 1 neighbours
+        const int64_t e = a.rowptr64 ? (int64_t)__ldg((const long long *)a.rowptr + v + 1)
+                                     : (int64_t)__ldg((const int *)a.rowptr + v + 1);
+        deg = (uint32_t)min(e - start, (int64_t)0xffffffffll);
     }
 }
 __device__ __forceinline__ uint32_t load_col(const SamplerArgs &a, const Policies &pol, int64_t e) {
@@ -199,19 +190,25 @@ __device__ __forceinline__ void warp_merge_sort(K (&k)[EPL], K *buf, int lane) {
             if (A[mid] <= B[diag - 1 - mid]) lo = mid + 1;
             else hi = mid;
         }
-        int ia = lo, ib = diag - lo;
-        K ka = ia < L ? A[ia] : SENT;
-        K kb = ib < L ? B[ib] : SENT;
+        // serial merge of this lane's EPL outputs; pa / pb index buf, the runs end at ea / eb
+        const int base = (lane - t) * EPL;
+        int pa = base + lo, pb = base + L + diag - lo;
+        const int ea = base + L, eb = base + 2 * L;
+        K ka = pa < ea ? buf[pa] : SENT;
+        K kb = pb < eb ? buf[pb] : SENT;
 #pragma unroll
         for (int j = 0; j < EPL; j++) {
             const bool ta = ka <= kb;
             k[j] = ta ? ka : kb;
-            if (ta) {
-                ia++;
-                ka = ia < L ? A[ia] : SENT;
-            } else {
-                ib++;
-                kb = ib < L ? B[ib] : SENT;
+            if (j + 1 < EPL) {
+                pa += ta ? 1 : 0;
+                pb += ta ? 0 : 1;
+                const int p = ta ? pa : pb;
+                const int e = ta ? ea : eb;
+                K v = SENT;
+                if (p < e) v = buf[p];
+                ka = ta ? v : ka;
+                kb = ta ? kb : v;
             }
         }
         __syncwarp();
@@ -228,18 +225,30 @@ __device__ __forceinline__ unsigned long long warp_incl_scan_u64(unsigned long l
 }
 
 // ---------------------------------------------------------------- LP-key interning
-// Open-addressing table in global memory (a few MB, L2 resident).  Returns the slot of
+// An LP row is keyed as in the reference: SHIFT bits per step, step 1 in the top field, the root
+// marker (LEAD) above them (subg_acc.c:936-949); the landing counts are accumulated directly in
+// that packing (a field cannot overflow: counts <= M < 2^SHIFT).
+// Open-addressing table in global memory (a few MB, L2 resident).  intern returns the slot of
 // `key`; tab_pos[slot] keeps the smallest stream position at which the key occurs, which
 // later yields the reference's first-occurrence ids (subg_acc.c:957-978).
-__device__ __forceinline__ uint32_t intern_key(const SamplerArgs &a, unsigned long long key,
-                                               unsigned long long pos) {
-    uint32_t h = (uint32_t)mix64(key) & a.tab_mask;
+__device__ __forceinline__ uint32_t lp_hash(unsigned long long key) {
+    uint32_t h = (uint32_t)key * 0x9E3779B1u ^ (uint32_t)(key >> 32) * 0x85EBCA77u;
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    h ^= h >> 12;
+    return h;
+}
+// first probe issued by the caller (so that several lookups are in flight): cur0 / pos0 are the
+// table words at h0 = lp_hash(key) & mask
+__device__ __forceinline__ uint32_t intern_key(const SamplerArgs &a, unsigned long long key, unsigned long long pos,
+                                               uint32_t h, unsigned long long cur, unsigned long long seen_pos) {
+    bool first = true;
     for (uint32_t probes = 0;; probes++) {
         if (probes > a.tab_mask) {  // table full: the host sees tab_count > cap/2 and reruns with a larger one
             atomicOr(a.status, kStatusTableFull);
             return 0;
         }
-        unsigned long long cur = a.tab_key[h];
+        if (!first) cur = a.tab_key[h];
         if (cur == kEmptyKey) {
             cur = atomicCAS(&a.tab_key[h], kEmptyKey, key);
             if (cur == kEmptyKey) {
@@ -249,17 +258,19 @@ __device__ __forceinline__ uint32_t intern_key(const SamplerArgs &a, unsigned lo
         }
         if (cur == key) break;
         h = (h + 1) & a.tab_mask;
+        first = false;
     }
-    if (pos < a.tab_pos[h]) atomicMin(&a.tab_pos[h], pos);
+    if (!first) seen_pos = a.tab_pos[h];
+    if (pos < seen_pos) atomicMin(&a.tab_pos[h], pos);
     return h;
 }
 
 template <typename K, int EPL>
 constexpr int sampler_min_blocks() {
     constexpr int W = (int)sizeof(K) / 4;
-    constexpr int smem_warp = (12 * 32 * EPL > (int)sizeof(K) * 32 * EPL + 4096 ? 12 * 32 * EPL : (int)sizeof(K) * 32 * EPL + 4096) + 256;
+    constexpr int smem_warp = ((int)sizeof(K) + 4) * 32 * EPL + 256;
     constexpr int by_smem = 232448 / (kWarpsPerBlock * smem_warp);
-    constexpr int by_regs = 65536 / (kWarpsPerBlock * 32 * (EPL * W + 44));
+    constexpr int by_regs = 65536 / (kWarpsPerBlock * 32 * (EPL * W + 52));
     constexpr int b = by_smem < by_regs ? by_smem : by_regs;
     return b < 1 ? 1 : (b > 8 ? 8 : b);
 }
@@ -275,13 +286,15 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
     unsigned char *wsm = smem_raw + (size_t)wib * a.smem_per_warp;
     K *keys = (K *)wsm;
     // member records alias the key buffer (the keys are in registers by then)
-    unsigned long long *rec_cnt = (unsigned long long *)wsm;
-    K *rec_key = (K *)(wsm + 8 * (size_t)a.Kt);
-    // Fisher-Yates scratch follows the key buffer
-    int32_t *fy_pick = (int32_t *)(wsm + a.key_bytes);
-    int32_t *fy_dense = fy_pick + a.M;
-    int32_t *fy_key = fy_dense + a.M;
-    int32_t *fy_val = fy_key + a.fy_cap;
+    K *rec_key = (K *)wsm;  // member i's head key overwrites the key buffer (i <= position of the head)
+    uint32_t *rec_lp32 = (uint32_t *)(wsm + a.lp_off);
+    unsigned long long *rec_lp64 = (unsigned long long *)(wsm + a.lp_off);
+    // Fisher-Yates scratch: picks and hash keys in region 1 (dead before the first key is written),
+    // the permutation and the hash values in region 2 (read by the first hop)
+    int32_t *fy_pick = (int32_t *)wsm;
+    int32_t *fy_key = fy_pick + a.M;
+    int32_t *fy_dense = (int32_t *)(wsm + a.lp_off);
+    int32_t *fy_val = fy_dense + a.M;
     uint32_t *bitmap = (uint32_t *)(wsm + a.bitmap_off);
     uint32_t *bprefix = bitmap + a.nbw;
 
@@ -289,6 +302,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
     const uint32_t ord_mask = (1u << OB) - 1u;
     const uint32_t step_mask = (1u << LS) - 1u;
     const K no_node = SENT >> OB;
+    const int lp_top = a.SHIFT * (m - 1);  // step s lands in bits [SHIFT*(m-1-s), SHIFT*(m-s)) (subg_acc.c:936-943)
     Policies pol;
     pol.keep = l2_policy_evict_last();
     pol.stream = l2_policy_evict_first();
@@ -315,7 +329,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
         } else {
             int64_t rp0;
             uint32_t dfull;
-            load_row(a, pol, (uint32_t)u, rp0, dfull);
+            decode_row(a, (uint32_t)u, load_row_raw(a, pol, (uint32_t)u), rp0, dfull);
             const int d = dfull > (uint32_t)kFirstHopCap ? kFirstHopCap : (int)dfull;
             const bool replay = a.rng_mode == SUBG_RNG_RAND_R;
             const uint32_t gi_lo = (uint32_t)gi, gi_hi = (uint32_t)((uint64_t)gi >> 32);
@@ -400,26 +414,31 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
                     }
                 }
                 for (int s = 1; s < m; s++) {
-                    int64_t rp[kGW];
-                    uint32_t dn[kGW];
+                    uint2 raw[kGW];
 #pragma unroll
-                    for (int tt = 0; tt < kGW; tt++) load_row(a, pol, cur[tt], rp[tt], dn[tt]);
+                    for (int tt = 0; tt < kGW; tt++) raw[tt] = load_row_raw(a, pol, cur[tt]);
                     uint32_t draw[kGW];
-                    if (!replay) {
-                        const uint4 r4 = philox4x32_10(
-                            make_uint4(gi_lo, gi_hi, (uint32_t)(lane + 8 * g) | ((uint32_t)s << 16), 0x57414c4bu),
-                            make_uint2(a.rng_lo, a.rng_hi));
-                        draw[0] = r4.x; draw[1] = r4.y; draw[2] = r4.z; draw[3] = r4.w;
+                    if (!replay) {  // one Philox call = this hop of four walks
+#pragma unroll
+                        for (int c = 0; c < kGW / 4; c++) {
+                            const uint4 r4 = philox4x32_10(
+                                make_uint4(gi_lo, gi_hi, (uint32_t)(lane + 8 * g + 32 * c) | ((uint32_t)s << 16), 0x57414c4bu),
+                                make_uint2(a.rng_lo, a.rng_hi));
+                            draw[4 * c] = r4.x; draw[4 * c + 1] = r4.y; draw[4 * c + 2] = r4.z; draw[4 * c + 3] = r4.w;
+                        }
                     }
 #pragma unroll
                     for (int tt = 0; tt < kGW; tt++) {
                         const int w = lane + 32 * (g + tt);
                         if (w < M) {
-                            if (dn[tt] > 0) {
+                            int64_t rp;
+                            uint32_t dn;
+                            decode_row(a, cur[tt], raw[tt], rp, dn);
+                            if (dn > 0) {
                                 uint32_t off;
-                                if (replay) off = rand_r_dev(rst[tt]) % dn[tt];
-                                else off = __umulhi(draw[tt], dn[tt]);
-                                cur[tt] = load_col(a, pol, rp[tt] + off);
+                                if (replay) off = rand_r_dev(rst[tt]) % dn;
+                                else off = __umulhi(draw[tt], dn);
+                                cur[tt] = load_col(a, pol, rp + off);
                             } else if (replay && d > 0) {
                                 atomicOr(a.status, SUBG_STATUS_DEAD_END);
                             }
@@ -433,11 +452,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
         for (int j = a.Kt + lane; j < 32 * EPL; j += 32) keys[j] = SENT;
         __syncwarp();
 
+        if (a.stop_after == 1) continue;
         K k[EPL];
 #pragma unroll
         for (int r = 0; r < EPL; r++) k[r] = keys[lane * EPL + r];
         __syncwarp();
         warp_merge_sort<K, EPL>(k, keys, lane);
+        if (a.stop_after == 2) {
+            if (k[0] == 1 && lane == 33) a.nsize[i] = 0;  // keep the sort alive
+            continue;
+        }
 
         // ---- runs of equal node = one set member each; heads per lane
         const K prev_last = __shfl_up_sync(FULL, k[EPL - 1], 1);
@@ -481,7 +505,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
                 if (head) {
                     if (have) {
                         rec_key[idx] = curk;
-                        rec_cnt[idx] = acc;
+                        if (a.lp64) rec_lp64[idx] = acc;
+                        else rec_lp32[idx] = (uint32_t)acc;
                     } else {
                         lead = acc;
                     }
@@ -491,7 +516,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
                     idx++;
                 }
                 const uint32_t ord = (uint32_t)k[r] & ord_mask;
-                if (valid && ord) acc += 1ull << (16 * (ord & step_mask));
+                if (valid && ord) acc += 1ull << (lp_top - a.SHIFT * (int)(ord & step_mask));
             }
             if (!have) lead = acc;
             const unsigned long long S = warp_incl_scan_u64(lead);
@@ -501,11 +526,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
             const unsigned long long S_nh = __shfl_sync(FULL, S, nh);
             if (have) {
                 rec_key[idx] = curk;
-                rec_cnt[idx] = acc + (S_nh - S);
+                const unsigned long long tot = acc + (S_nh - S);
+                if (a.lp64) rec_lp64[idx] = tot;
+                else rec_lp32[idx] = (uint32_t)tot;
             }
         }
         __syncwarp();
 
+        if (a.stop_after == 3) continue;
         // ---- first-visit rank of every member = popcount prefix over the order bitmap
         if (a.want_rank) {
             uint32_t running = 0;
@@ -519,38 +547,56 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
             __syncwarp();
         }
 
-        // ---- emit the set: ascending node id, provisional LP id, first-visit rank
+        // ---- emit the set: ascending node id, provisional LP id, first-visit rank.  Two members per
+        // lane and iteration so that two table lookups are in flight.
         const long long base = (long long)__shfl_sync(FULL, base_u, 0);
         const bool overflow = kept < s_total;
         int done = 0;
-        for (int t0 = 0; t0 < s_total; t0 += 32) {
-            const int t = t0 + lane;
-            const bool act = t < s_total;
-            K kk = 0;
-            unsigned long long cnt = 0ull;
-            if (act) {
-                kk = rec_key[t];
-                cnt = rec_cnt[t];
+        for (int t0 = 0; t0 < s_total; t0 += 64) {
+            K kk[2];
+            unsigned long long lp[2], cur[2], seen[2];
+            uint32_t h[2], ord[2], rank[2];
+            bool keep[2];
+            int o[2];
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int t = t0 + 32 * q + lane;
+                const bool act = t < s_total;
+                kk[q] = 0;
+                lp[q] = 0ull;
+                if (act) {
+                    kk[q] = rec_key[t];
+                    lp[q] = a.lp64 ? rec_lp64[t] : (unsigned long long)rec_lp32[t];
+                }
+                ord[q] = (uint32_t)kk[q] & ord_mask;
+                rank[q] = 0;
+                if (a.want_rank && act)
+                    rank[q] = bprefix[ord[q] >> 5] + __popc(bitmap[ord[q] >> 5] & ((1u << (ord[q] & 31)) - 1u));
+                keep[q] = act;
+                o[q] = t;
+                if (overflow) {
+                    keep[q] = act && (int)rank[q] < a.stride;
+                    const uint32_t km = __ballot_sync(FULL, keep[q]);
+                    o[q] = done + __popc(km & ((1u << lane) - 1u));
+                    done += __popc(km);
+                }
+                if (ord[q] == 0) lp[q] |= 1ull << (m * a.SHIFT);  // the root row (LEAD, subg_acc.c:944-949)
+                h[q] = lp_hash(lp[q]) & a.tab_mask;
+                cur[q] = kEmptyKey;
+                seen[q] = 0ull;
+                if (keep[q]) {
+                    cur[q] = a.tab_key[h[q]];
+                    seen[q] = a.tab_pos[h[q]];
+                }
             }
-            const uint32_t ord = (uint32_t)kk & ord_mask;
-            uint32_t rank = 0;
-            if (a.want_rank && act) rank = bprefix[ord >> 5] + __popc(bitmap[ord >> 5] & ((1u << (ord & 31)) - 1u));
-            bool keep = act;
-            int o = t;
-            if (overflow) {
-                keep = act && (int)rank < a.stride;
-                const uint32_t km = __ballot_sync(FULL, keep);
-                o = done + __popc(km & ((1u << lane) - 1u));
-                done += __popc(km);
-            }
-            if (keep) {
-                unsigned long long lp = 0ull;
-                for (int j = 0; j < m; j++) lp = (lp << a.SHIFT) | ((cnt >> (16 * j)) & 0xffffull);
-                if (ord == 0) lp |= 1ull << (m * a.SHIFT);
-                const uint32_t prov = intern_key(a, lp, ((unsigned long long)gi << 16) | ord);
-                a.out_node[base + o] = (int32_t)(kk >> OB);
-                a.out_prov[base + o] = (int32_t)prov;
-                if (a.out_slot) a.out_slot[base + o] = (uint16_t)rank;
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                if (keep[q]) {
+                    const uint32_t prov = intern_key(a, lp[q], ((unsigned long long)gi << 16) | ord[q], h[q], cur[q], seen[q]);
+                    a.out_node[base + o[q]] = (int32_t)(kk[q] >> OB);
+                    a.out_prov[base + o[q]] = (int32_t)prov;
+                    if (a.out_slot) a.out_slot[base + o[q]] = (uint16_t)rank[q];
+                }
             }
         }
         if (lane < kept4 - kept) {  // keep the row padding defined (ids are remapped in place later)

@@ -9,7 +9,9 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "sampler.cuh"
@@ -42,6 +44,23 @@ static int ceil_log2(uint64_t x) {
     while ((1ull << b) < x) b++;
     return b;
 }
+// host-side phase timer (SUBG_PROFILE_HOST=1): where does a sampling call spend wall-clock besides its kernels?
+struct HostProf {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    std::string log;
+    HostProf() : on(getenv("SUBG_PROFILE_HOST") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *what) {
+        if (!on) return;
+        const auto t = std::chrono::steady_clock::now();
+        char buf[96];
+        snprintf(buf, sizeof(buf), " %s=%.3f", what, std::chrono::duration<double, std::milli>(t - t0).count());
+        log += buf;
+        t0 = t;
+    }
+    ~HostProf() { if (on) fprintf(stderr, "[subg host ms]%s\n", log.c_str()); }
+};
+
 static int64_t env_i64(const char *name, int64_t dflt) {
     const char *v = getenv(name);
     return v ? atoll(v) : dflt;
@@ -181,8 +200,8 @@ int spg_ensure_csr(SpG *s, cudaStream_t st) {
 }
 
 struct SamplePlan {
-    int EPL, OB, LS, SHIFT, stride, Kt, rowcap, nbw, fy_cap, key_bytes, bitmap_off, smem_per_warp;
-    bool key64;
+    int EPL, OB, LS, SHIFT, stride, Kt, rowcap, nbw, fy_cap, lp_off, bitmap_off, smem_per_warp;
+    bool key64, lp64;
 };
 
 static int make_plan(const Graph *g, int M, int m, int bucket, SamplePlan *p) {
@@ -213,10 +232,12 @@ static int make_plan(const Graph *g, int M, int m, int bucket, SamplePlan *p) {
     int fc = 16;
     while (fc < M + M / 4) fc <<= 1;
     p->fy_cap = fc;
-    p->key_bytes = ksz * 32 * p->EPL;
-    const int rec_bytes = (8 + ksz) * (int)Kt;
-    const int fy_bytes = 8 * M + 8 * fc;
-    p->bitmap_off = (std::max(rec_bytes, p->key_bytes + fy_bytes) + 15) & ~15;
+    // region 1: key buffer, later the member keys; Fisher-Yates picks + hash keys before the walk
+    // region 2: member LP rows; Fisher-Yates permutation + hash values during the first hop
+    p->lp64 = m * shift + 1 > 32;
+    const int fy_half = 4 * M + 4 * fc;
+    p->lp_off = (std::max(ksz * 32 * p->EPL, fy_half) + 15) & ~15;
+    p->bitmap_off = (p->lp_off + std::max((p->lp64 ? 8 : 4) * (int)Kt, fy_half) + 15) & ~15;
     p->smem_per_warp = (p->bitmap_off + 8 * p->nbw + 15) & ~15;
     return SUBG_OK;
 }
@@ -240,6 +261,7 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
 
     SpG *s = new SpG();
     s->device = g->device; s->n = n; s->ncol = m + 1; s->M = M; s->num_sms = g->num_sms; s->value_kind = 0;
+    HostProf prof;
 
     // everything below that is not part of the SpG is scratch
     int32_t *d_walks = nullptr, *d_calls = nullptr, *rank_of_slot = nullptr, *d_all_seeds = nullptr;
@@ -312,6 +334,7 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
             if (bad) { rc = fail(SUBG_ERR_ARG, "query contains node ids outside [0, N)"); goto done; }
         }
 
+        prof.mark("setup");
         // Rows are written once, at a cursor, into arrays sized for the worst case (rowcap entries per
         // seed).  If that does not fit the budget the seeds go through in chunks and every chunk is
         // compacted into the growing CSR (the layout of the reference's dense `encoding`, subg_acc.c:848-872).
@@ -337,6 +360,7 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
             cap = rows_cap;
         }
 
+        prof.mark("alloc_rows");
         int tab_log2 = (int)env_i64("SUBG_LP_TABLE_LOG2", 20);
         const int hints = (int)env_i64("SUBG_SAMPLER_HINTS", 3);
         for (int attempt = 0;; attempt++) {
@@ -354,7 +378,7 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
                 const int64_t nc = std::min(chunk, n - base);
                 CK(cudaMemsetAsync(d_ctr, 0, 4 * sizeof(unsigned long long), st));
                 SamplerArgs a{};
-                a.rowinfo = g->rowinfo; a.rowptr64 = g->rowptr64 ? 1 : 0; a.col = g->col;
+                a.rowinfo = (const unsigned long long *)g->rowinfo; a.rowptr = g->rowptr; a.rowptr64 = g->rowptr64 ? 1 : 0; a.col = g->col;
                 a.seeds = s->seeds + base; a.n_chunk = nc; a.seed_base = lo + base;
                 a.M = M; a.m = m; a.stride = pl.stride; a.Kt = pl.Kt; a.OB = pl.OB; a.LS = pl.LS; a.SHIFT = pl.SHIFT;
                 a.rng_mode = rng_mode; a.rng_lo = (uint32_t)seed; a.rng_hi = (uint32_t)(seed >> 32);
@@ -366,20 +390,47 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
                 a.rowbeg = chunked ? c_rowbeg : (long long *)s->rowbeg;
                 a.nsize = s->nsize + base;
                 a.ctr = d_ctr; a.max_set = d_maxset; a.want_rank = want_rank ? 1 : 0; a.hints = hints;
+                a.stop_after = (int)env_i64("SUBG_SAMPLER_STOP", 0);
+                {   // every gather in flight holds an L1 line: when the CSR does not fit the L2 the walk phase is
+                    // bound by that count, so shared memory is capped to leave about 80 KB of the SM to L1 (sweep: profiles/r1_sampler_sweeps.txt)
+                    const int64_t csr_bytes = 4 * g->E + 8 * g->N;
+                    int cap_blocks = 0;
+                    if (csr_bytes > (96ll << 20))
+                        cap_blocks = std::max(2, (int)((148 << 10) / (kWarpsPerBlock * pl.smem_per_warp + 1024)));
+                    a.blocks_per_sm = (int)env_i64("SUBG_SAMPLER_BLOCKS", cap_blocks);
+                }
                 a.tab_key = tab_key; a.tab_pos = tab_pos; a.tab_mask = tab_cap - 1;
                 a.tab_count = d_flags + 1; a.status = d_flags;
-                a.nbw = pl.nbw; a.fy_cap = pl.fy_cap; a.key_bytes = pl.key_bytes; a.bitmap_off = pl.bitmap_off;
+                a.nbw = pl.nbw; a.fy_cap = pl.fy_cap; a.lp_off = pl.lp_off; a.lp64 = pl.lp64 ? 1 : 0; a.bitmap_off = pl.bitmap_off;
                 a.smem_per_warp = pl.smem_per_warp;
+                const int l2_persist = (int)env_i64("SUBG_L2_PERSIST", 0);
+                if (l2_persist) {  // experiment knob: pin the row-info array in the persisting L2 carve-out
+                    const size_t bytes = ((size_t)g->N + 1) * 8;
+                    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(bytes, 64u << 20));
+                    cudaStreamAttrValue av{};
+                    av.accessPolicyWindow.base_ptr = g->rowinfo;
+                    av.accessPolicyWindow.num_bytes = bytes;
+                    av.accessPolicyWindow.hitRatio = 1.0f;
+                    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+                }
+                prof.mark("table_init");
                 timing_begin(SUBG_TIMING_SAMPLER, st);
                 CK(pl.key64 ? launch_gset_sample_k64(a, pl.EPL, g->num_sms, st)
                             : launch_gset_sample_k32(a, pl.EPL, g->num_sms, st));
                 timing_end(SUBG_TIMING_SAMPLER, st);
                 count_launch(1);
+                if (l2_persist) {
+                    cudaStreamAttrValue av{};
+                    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+                }
                 unsigned long long hctr[3];
                 uint32_t flags_h[2];
                 CK(cudaMemcpyAsync(hctr, d_ctr, sizeof(hctr), cudaMemcpyDeviceToHost, st));
                 CK(cudaMemcpyAsync(flags_h, d_flags, sizeof(flags_h), cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
+                prof.mark("kernel+sync");
                 if (flags_h[1] > tab_cap / 2 || (flags_h[0] & kStatusTableFull)) { table_full = true; break; }
                 if (!chunked) {
                     T = (int64_t)hctr[2];
@@ -431,6 +482,7 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
             CK(cudaMemcpyAsync(hflags, d_flags, sizeof(hflags), cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(&mx, d_maxset, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
+            prof.mark("flags");
             s->status = hflags[0] & ~kStatusTableFull;
             s->max_set = mx;
             const uint32_t c = hflags[1];
@@ -468,7 +520,9 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
             if (s->rowbeg && (void *)s->rowbeg != (void *)s->indptr) dfree(s->rowbeg, st);
             s->rowbeg = s->indptr;
         }
+        prof.mark("unique_launch");
         CK(cudaStreamSynchronize(st));
+        prof.mark("unique_sync");
         // a mostly empty worst-case allocation is not worth keeping
         if (!s->indptr && cap > s->extent + s->extent / 4 + (16ll << 20)) {
             timing_begin(SUBG_TIMING_BUILD, st);
@@ -479,6 +533,7 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
     }
 done:
 #undef CK
+    prof.mark("tail");
     if (walks_owned) dfree(d_walks, st);
     dfree(d_calls, st); dfree(call_base, st); dfree(scan_scratch, st); dfree(d_all_seeds, st);
     dfree(c_node, st); dfree(c_prov, st); dfree(c_slot, st); dfree(c_rowbeg, st);
