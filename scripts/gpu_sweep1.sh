@@ -1,7 +1,7 @@
 cd ${GRAFT_REPO_ROOT:-.}
 mkdir -p gpurun_out
 {
-for h in 0 1 2 3; do SUBG_SAMPLER_HINTS=$h python scripts/sampler_bench.py ppa 5; done
+for h in 0 1 2 3; do python scripts/sampler_bench.py ppa 5; done
 RANKS=1 python scripts/sampler_bench.py ppa 5
 python scripts/sampler_bench.py collab 5
 python scripts/sampler_bench.py dblp 5

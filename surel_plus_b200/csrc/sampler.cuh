@@ -59,7 +59,6 @@ struct SamplerArgs {
     unsigned long long *ctr;   // [0] seed ticket  [1] row cursor (entries, rows padded to 4)  [2] sum of set sizes
     int32_t *max_set;
     int want_rank;
-    int hints;                 // bit 0: L2 evict_last on row info, bit 1: L2 evict_first on neighbour gathers
     int blocks_per_sm;         // 0 = as many as fit; otherwise a cap (fewer blocks leave more of the SM's 228 KB to L1)
     int stop_after;            // measurement only (SUBG_SAMPLER_STOP): 1 = walks, 2 = + sort, 3 = + counts; 0 = full kernel
     // LP-key intern table (global, L2 resident)
@@ -83,28 +82,16 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-    uint64_t p;
-    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
 __device__ __forceinline__ uint2 ldg_v2_hint(const void *p, uint64_t pol) {
     uint2 v;
     asm("ld.global.nc.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
     return v;
 }
-__device__ __forceinline__ uint32_t ldg_u32_stream(const void *p, uint64_t pol) {
-    uint32_t v;
-    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
-    return v;
-}
-
-struct Policies { uint64_t keep, stream; };
+struct Policies { uint64_t keep; };
 
 // issue / decode split so that a group's row loads are all in flight before the first is consumed
 __device__ __forceinline__ uint2 load_row_raw(const SamplerArgs &a, const Policies &pol, uint32_t v) {
-    if (a.hints & 1) return ldg_v2_hint(a.rowinfo + v, pol.keep);
-    return __ldg((const uint2 *)(a.rowinfo + v));
+    return ldg_v2_hint(a.rowinfo + v, pol.keep);  // the row info (8 B per node) is what the L2 should keep
 }
 __device__ __forceinline__ void decode_row(const SamplerArgs &a, uint32_t v, uint2 q, int64_t &start, uint32_t &deg) {
     start = (int64_t)(((uint64_t)(q.y & 0xffu) << 32) | q.x);
@@ -116,8 +103,7 @@ __device__ __forceinline__ void decode_row(const SamplerArgs &a, uint32_t v, uin
     }
 }
 __device__ __forceinline__ uint32_t load_col(const SamplerArgs &a, const Policies &pol, int64_t e) {
-    if (a.hints & 2) return ldg_u32_stream(a.col + e, pol.stream);
-    return (uint32_t)__ldg(a.col + e);
+    return (uint32_t)__ldg(a.col + e);  // cache hints on these make no difference (profiles/r1_gather_micro.txt)
 }
 
 // ---------------------------------------------------------------- warp merge sort
@@ -276,7 +262,9 @@ constexpr int sampler_min_blocks() {
 }
 
 // ---------------------------------------------------------------- the sampler kernel
-template <typename K, int EPL>
+// PARITY = false: Philox draws only (the fast path); true: rand_r replay and supplied traces (kept out
+// of the fast kernel: its code has to stay inside the instruction cache).
+template <typename K, int EPL, bool PARITY>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL>()) gset_sample_kernel(const SamplerArgs a) {
     constexpr K SENT = ~(K)0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -287,8 +275,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
     K *keys = (K *)wsm;
     // member records alias the key buffer (the keys are in registers by then)
     K *rec_key = (K *)wsm;  // member i's head key overwrites the key buffer (i <= position of the head)
-    uint32_t *rec_lp32 = (uint32_t *)(wsm + a.lp_off);
-    unsigned long long *rec_lp64 = (unsigned long long *)(wsm + a.lp_off);
+    uint32_t *rec_lp32 = (uint32_t *)(wsm + a.lp_off);   // low words of the member LP rows
+    uint32_t *rec_lphi = rec_lp32 + a.Kt;                // high words (lp64 only)
     // Fisher-Yates scratch: picks and hash keys in region 1 (dead before the first key is written),
     // the permutation and the hash values in region 2 (read by the first hop)
     int32_t *fy_pick = (int32_t *)wsm;
@@ -297,7 +285,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
     int32_t *fy_val = fy_dense + a.M;
     uint32_t *bitmap = (uint32_t *)(wsm + a.bitmap_off);
     uint32_t *bprefix = bitmap + a.nbw;
-
     const int M = a.M, m = a.m, OB = a.OB, LS = a.LS;
     const uint32_t ord_mask = (1u << OB) - 1u;
     const uint32_t step_mask = (1u << LS) - 1u;
@@ -305,7 +292,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
     const int lp_top = a.SHIFT * (m - 1);  // step s lands in bits [SHIFT*(m-1-s), SHIFT*(m-s)) (subg_acc.c:936-943)
     Policies pol;
     pol.keep = l2_policy_evict_last();
-    pol.stream = l2_policy_evict_first();
     int mx = 0;
 
     for (;;) {
@@ -319,7 +305,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
         if (a.want_rank)
             for (int b = lane; b < a.nbw; b += 32) bitmap[b] = 0u;
 
-        if (a.rng_mode == SUBG_RNG_TRACE) {
+        if (PARITY && a.rng_mode == SUBG_RNG_TRACE) {
             const int32_t *wk = a.walks + i * (int64_t)M * m;
             for (int j = lane; j < M * m; j += 32) {
                 const uint32_t v = (uint32_t)__ldg(wk + j);
@@ -331,7 +317,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
             uint32_t dfull;
             decode_row(a, (uint32_t)u, load_row_raw(a, pol, (uint32_t)u), rp0, dfull);
             const int d = dfull > (uint32_t)kFirstHopCap ? kFirstHopCap : (int)dfull;
-            const bool replay = a.rng_mode == SUBG_RNG_RAND_R;
+            const bool replay = PARITY && a.rng_mode == SUBG_RNG_RAND_R;
             const uint32_t gi_lo = (uint32_t)gi, gi_hi = (uint32_t)((uint64_t)gi >> 32);
             int64_t calls0 = 0;
             if (replay) calls0 = __ldg((const long long *)a.call_base + gi);
@@ -472,10 +458,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
             const K pn = r ? (k[r - 1] >> OB) : pn0;
             const bool head = k[r] != SENT && (k[r] >> OB) != pn;
             nhead += head ? 1u : 0u;
-            if (a.want_rank && head) {
-                const uint32_t ord = (uint32_t)k[r] & ord_mask;
-                atomicOr(&bitmap[ord >> 5], 1u << (ord & 31));
-            }
         }
         const uint32_t incl = warp_incl_scan(nhead);
         const int s_total = (int)__shfl_sync(FULL, incl, 31);
@@ -502,11 +484,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
                 const K pn = r ? (k[r - 1] >> OB) : pn0;
                 const bool valid = k[r] != SENT;
                 const bool head = valid && (k[r] >> OB) != pn;
+                const uint32_t ord = (uint32_t)k[r] & ord_mask;
                 if (head) {
                     if (have) {
                         rec_key[idx] = curk;
-                        if (a.lp64) rec_lp64[idx] = acc;
-                        else rec_lp32[idx] = (uint32_t)acc;
+                        rec_lp32[idx] = (uint32_t)acc;
+                        if (a.lp64) rec_lphi[idx] = (uint32_t)(acc >> 32);
                     } else {
                         lead = acc;
                     }
@@ -514,8 +497,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
                     curk = k[r];
                     acc = 0ull;
                     idx++;
+                    if (a.want_rank) atomicOr(&bitmap[ord >> 5], 1u << (ord & 31));
                 }
-                const uint32_t ord = (uint32_t)k[r] & ord_mask;
                 if (valid && ord) acc += 1ull << (lp_top - a.SHIFT * (int)(ord & step_mask));
             }
             if (!have) lead = acc;
@@ -527,8 +510,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
             if (have) {
                 rec_key[idx] = curk;
                 const unsigned long long tot = acc + (S_nh - S);
-                if (a.lp64) rec_lp64[idx] = tot;
-                else rec_lp32[idx] = (uint32_t)tot;
+                rec_lp32[idx] = (uint32_t)tot;
+                if (a.lp64) rec_lphi[idx] = (uint32_t)(tot >> 32);
             }
         }
         __syncwarp();
@@ -566,7 +549,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
                 lp[q] = 0ull;
                 if (act) {
                     kk[q] = rec_key[t];
-                    lp[q] = a.lp64 ? rec_lp64[t] : (unsigned long long)rec_lp32[t];
+                    lp[q] = rec_lp32[t];
+                    if (a.lp64) lp[q] |= (unsigned long long)rec_lphi[t] << 32;
                 }
                 ord[q] = (uint32_t)kk[q] & ord_mask;
                 rank[q] = 0;

@@ -362,7 +362,6 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
 
         prof.mark("alloc_rows");
         int tab_log2 = (int)env_i64("SUBG_LP_TABLE_LOG2", 20);
-        const int hints = (int)env_i64("SUBG_SAMPLER_HINTS", 3);
         for (int attempt = 0;; attempt++) {
             const uint32_t tab_cap = 1u << tab_log2;
             CK(dmalloc(&tab_key, (size_t)tab_cap, st));
@@ -389,7 +388,7 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
                 a.out_slot = chunked ? c_slot : s->slot;
                 a.rowbeg = chunked ? c_rowbeg : (long long *)s->rowbeg;
                 a.nsize = s->nsize + base;
-                a.ctr = d_ctr; a.max_set = d_maxset; a.want_rank = want_rank ? 1 : 0; a.hints = hints;
+                a.ctr = d_ctr; a.max_set = d_maxset; a.want_rank = want_rank ? 1 : 0;
                 a.stop_after = (int)env_i64("SUBG_SAMPLER_STOP", 0);
                 {   // every gather in flight holds an L1 line: when the CSR does not fit the L2 the walk phase is
                     // bound by that count, so shared memory is capped to leave about 80 KB of the SM to L1 (sweep: profiles/r1_sampler_sweeps.txt)
