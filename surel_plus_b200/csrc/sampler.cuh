@@ -34,6 +34,8 @@ constexpr uint64_t kEmptyKey = ~0ull;
 constexpr uint32_t kStatusTableFull = 1u << 31;  // internal status bit
 constexpr int kFirstHopCap = 1000000;  // NEBMAX, subg_acc.c:13,750
 constexpr int kGW = 8;                 // walks advanced together per lane
+constexpr int kTicketBatch = 1;        // consecutive seeds a warp takes per ticket atomic
+constexpr int kCtrCursor = 16, kCtrTotal = 32, kCtrWords = 48;
 
 struct SamplerArgs {
     const unsigned long long *rowinfo;  // [N] row start (low 40 bits) | degree (high 24 bits, 0xFFFFFF = escape)
@@ -56,7 +58,8 @@ struct SamplerArgs {
     uint16_t *out_slot;        // nullable: first-visit ranks are not wanted
     long long *rowbeg;         // chunk-local
     int32_t *nsize;            // chunk-local
-    unsigned long long *ctr;   // [0] seed ticket  [1] row cursor (entries, rows padded to 4)  [2] sum of set sizes
+    unsigned long long *ctr;   // [0] seed ticket  [16] row cursor (entries, rows padded to 4)  [32] sum of set sizes
+                               // (one 128-byte line each: same-address atomics serialise in their L2 slice)
     int32_t *max_set;
     int want_rank;
     int blocks_per_sm;         // 0 = as many as fit; otherwise a cap (fewer blocks leave more of the SM's 228 KB to L1)
@@ -294,10 +297,17 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
     pol.keep = l2_policy_evict_last();
     int mx = 0;
 
+    int64_t next_i = 0;
+    int batch_left = 0;
     for (;;) {
-        unsigned long long ticket = 0;
-        if (lane == 0) ticket = atomicAdd(&a.ctr[0], 1ull);
-        const int64_t i = (int64_t)__shfl_sync(FULL, ticket, 0);
+        if (batch_left == 0) {
+            unsigned long long ticket = 0;
+            if (lane == 0) ticket = atomicAdd(&a.ctr[0], (unsigned long long)kTicketBatch);
+            next_i = (int64_t)__shfl_sync(FULL, ticket, 0);
+            batch_left = kTicketBatch;
+        }
+        const int64_t i = next_i++;
+        batch_left--;
         if (i >= a.n_chunk) break;
         const int64_t gi = a.seed_base + i;
         const int32_t u = __ldg(a.seeds + i);
@@ -465,8 +475,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
         const int kept4 = (kept + 3) & ~3;
         unsigned long long base_u = 0;
         if (lane == 0) {
-            base_u = atomicAdd(&a.ctr[1], (unsigned long long)kept4);
-            atomicAdd(&a.ctr[2], (unsigned long long)kept);
+            base_u = atomicAdd(&a.ctr[kCtrCursor], (unsigned long long)kept4);
+            atomicAdd(&a.ctr[kCtrTotal], (unsigned long long)kept);
             a.rowbeg[i] = (long long)base_u;
             a.nsize[i] = kept;
             if (kept < s_total) atomicOr(a.status, SUBG_STATUS_BUCKET_OVERFLOW);

@@ -291,7 +291,7 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
         CK(dmalloc(&s->nsize, (size_t)n, st));
         CK(dmalloc(&d_flags, 4, st));
         CK(dmalloc(&d_maxset, 1, st));
-        CK(dmalloc(&d_ctr, 4, st));
+        CK(dmalloc(&d_ctr, kCtrWords, st));
         CK(cudaMemsetAsync(d_flags, 0, 4 * sizeof(uint32_t), st));
         if (n > 0) {
             CK(cudaMemcpyAsync(s->seeds, seeds_hd + lo, (size_t)n * sizeof(int32_t), cudaMemcpyDefault, st));
@@ -375,7 +375,7 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
             bool table_full = false;
             for (int64_t base = 0; base < n; base += chunk) {
                 const int64_t nc = std::min(chunk, n - base);
-                CK(cudaMemsetAsync(d_ctr, 0, 4 * sizeof(unsigned long long), st));
+                CK(cudaMemsetAsync(d_ctr, 0, kCtrWords * sizeof(unsigned long long), st));
                 SamplerArgs a{};
                 a.rowinfo = (const unsigned long long *)g->rowinfo; a.rowptr = g->rowptr; a.rowptr64 = g->rowptr64 ? 1 : 0; a.col = g->col;
                 a.seeds = s->seeds + base; a.n_chunk = nc; a.seed_base = lo + base;
@@ -424,7 +424,7 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
                     cudaStreamAttrValue av{};
                     cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
                 }
-                unsigned long long hctr[3];
+                unsigned long long hctr[kCtrWords];
                 uint32_t flags_h[2];
                 CK(cudaMemcpyAsync(hctr, d_ctr, sizeof(hctr), cudaMemcpyDeviceToHost, st));
                 CK(cudaMemcpyAsync(flags_h, d_flags, sizeof(flags_h), cudaMemcpyDeviceToHost, st));
@@ -432,15 +432,15 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
                 prof.mark("kernel+sync");
                 if (flags_h[1] > tab_cap / 2 || (flags_h[0] & kStatusTableFull)) { table_full = true; break; }
                 if (!chunked) {
-                    T = (int64_t)hctr[2];
-                    extent = (int64_t)hctr[1];
+                    T = (int64_t)hctr[kCtrTotal];
+                    extent = (int64_t)hctr[kCtrCursor];
                     break;
                 }
                 // ---- chunked mode: append the chunk's rows to the CSR
                 timing_begin(SUBG_TIMING_BUILD, st);
                 CK(exclusive_scan_i32_i64(s->nsize + base, (long long *)s->indptr + base, nc, T, scan_scratch, st));
                 count_launch(3);
-                const int64_t T_new = T + (int64_t)hctr[2];
+                const int64_t T_new = T + (int64_t)hctr[kCtrTotal];
                 if (T_new > cap) {
                     int64_t want = T_new;
                     if (base + nc < n) want = std::max<int64_t>(T_new, (int64_t)((double)T_new * n / (base + nc) * 1.05) + 1024);
