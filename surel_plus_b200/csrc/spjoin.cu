@@ -130,8 +130,29 @@ struct TaskDesc {
 };
 
 // ------------------------------------------------------------------ the join kernel
+// one thread per (row, side): copies the KK floats of LP row `ptr` to their place in the [N,2,KK] output
+template <int KK>
+__device__ __forceinline__ void put_lp_row(float *out, long long row, int side, const float *enc, int ptr) {
+    float *dst = out + (row * 2 + side) * KK;
+    const float *src = enc + (int64_t)ptr * KK;
+    if (KK > 0 && KK % 4 == 0) {
+#pragma unroll
+        for (int c = 0; c < KK / 4; c++) ((float4 *)dst)[c] = __ldg((const float4 *)src + c);
+    } else if (KK % 2 == 0) {
+#pragma unroll
+        for (int c = 0; c < KK / 2; c++) ((float2 *)dst)[c] = __ldg((const float2 *)src + c);
+    } else {
+        float v[KK > 0 ? KK : 1];
+#pragma unroll
+        for (int c = 0; c < KK; c++) v[c] = __ldg(src + c);
+#pragma unroll
+        for (int c = 0; c < KK; c++) dst[c] = v[c];
+    }
+}
+
 // MODE 0: int32 [N,2] pointers   MODE 1: float32 [N,2,k] fused table lookup   MODE 2: float32 [N,2] values
-template <typename V, int MODE>
+// KK: compile-time k of MODE 1 (0 = any k, element-wise copy)
+template <typename V, int MODE, int KK>
 __global__ void __launch_bounds__(kJoinThreads) spjoin_kernel(const JoinArgs p) {
     extern __shared__ __align__(128) unsigned char sm[];
     const int cap = p.cap;
@@ -213,7 +234,19 @@ __global__ void __launch_bounds__(kJoinThreads) spjoin_kernel(const JoinArgs p) 
         }
         __syncthreads();
         // ---- S_b side: the match (if any) was dropped at its position
-        if (MODE == 1) {
+        if (MODE == 1 && KK > 0) {
+            float *out = (float *)p.out;
+            for (int e = threadIdx.x; e < 2 * d.sa; e += kJoinThreads) {
+                const int r = e >> 1, side = e & 1;
+                put_lp_row<KK>(out, d.offA + r, side, p.enc, side ? (int)mat[r] : (int)VA[r]);
+            }
+            for (int e = threadIdx.x; e < 2 * d.sb; e += kJoinThreads) {
+                const int r = e >> 1, side = e & 1;
+                put_lp_row<KK>(out, d.offB + r, side, p.enc, side ? (int)rev[r] : (int)VB[r]);
+            }
+            if (p.segid)
+                for (int j = threadIdx.x; j < d.sb; j += kJoinThreads) p.segid[d.offB + j] = d.segB;
+        } else if (MODE == 1) {
             const int k = p.k, k2 = 2 * p.k;
             float *out = (float *)p.out;
             for (int e = threadIdx.x; e < d.sa * k2; e += kJoinThreads) {
@@ -327,7 +360,7 @@ int spjoin_plan_impl(const SpG *s, const int64_t *edge_hd, int64_t B, int arity,
     return SUBG_OK;
 }
 
-template <typename V, int MODE>
+template <typename V, int MODE, int KK = 0>
 static cudaError_t launch_join(const SpG *s, JoinArgs &p, cudaStream_t st) {
     if (p.ntask <= 0) return cudaSuccess;
     int dev_smem = 0;
@@ -336,7 +369,7 @@ static cudaError_t launch_join(const SpG *s, JoinArgs &p, cudaStream_t st) {
     const size_t smem = (size_t)cap * (8 + 4 * sizeof(V)) + 128;
     if ((int64_t)smem <= std::min<int64_t>(dev_smem - 1024, 96 * 1024)) {
         p.cap = cap;
-        auto kern = spjoin_kernel<V, MODE>;
+        auto kern = spjoin_kernel<V, MODE, KK>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int per_sm = 0;
@@ -365,7 +398,17 @@ int spjoin_run_impl(const SpG *s, const int64_t *edge_dev, int64_t B, int arity,
     cudaError_t e;
     timing_begin(SUBG_TIMING_SPJOIN, st);
     if (s->value_kind == 1) e = launch_join<double, 2>(s, p, st);
-    else if (enc_table_dev) e = launch_join<int32_t, 1>(s, p, st);
+    else if (enc_table_dev) {
+        // the LP table must allow vector loads of a row (torch allocations are 512-byte aligned)
+        const bool al = ((uintptr_t)enc_table_dev & 15) == 0;
+        switch (al ? k : 0) {
+            case 2: e = launch_join<int32_t, 1, 2>(s, p, st); break;
+            case 3: e = launch_join<int32_t, 1, 3>(s, p, st); break;
+            case 4: e = launch_join<int32_t, 1, 4>(s, p, st); break;
+            case 5: e = launch_join<int32_t, 1, 5>(s, p, st); break;
+            default: e = launch_join<int32_t, 1, 0>(s, p, st);
+        }
+    }
     else e = launch_join<int32_t, 0>(s, p, st);
     timing_end(SUBG_TIMING_SPJOIN, st);
     count_launch(1);
