@@ -218,15 +218,10 @@ class SpG:
     def export_reference(self, want_raw: bool = False):
         """[nsize, remap, enc(, raw_enc)] exactly as gset_sampler returns them
         (subg_acc.c:1017-1024).  Host numpy arrays (filled through pinned memory)."""
-        import os
-        import time
-        t0 = time.perf_counter()
         nsize = torch.empty(self.n, dtype=torch.int32, pin_memory=True)
         remap = torch.empty((2, self.T), dtype=torch.int32, pin_memory=True)
         enc = torch.empty((self.c, self.ncol), dtype=torch.int16, pin_memory=True)
         raw = torch.empty((self.T, self.ncol), dtype=torch.int16, pin_memory=True) if want_raw else None
-        if os.environ.get("SUBG_PROFILE_HOST"):
-            print(f"[subg host ms] export: pinned alloc={1e3 * (time.perf_counter() - t0):.1f}", flush=True)
         _capi.check(self._lib.subg_spg_export(self._h, nsize.data_ptr(), remap.data_ptr(), enc.data_ptr(),
                                               raw.data_ptr() if want_raw else None, _stream(self.device)))
         out = [nsize.numpy(), remap.numpy(), enc.numpy()]

@@ -14,6 +14,7 @@ RNG: the reference draws from glibc rand_r on one word shared by all OpenMP thre
 from __future__ import annotations
 
 import os
+import sys
 import time
 
 import numpy as np
@@ -70,7 +71,7 @@ def gset_sampler(indptr, indices, query, num_walks=100, num_steps=3, bucket=-1, 
     out = spg.export_reference(want_raw=debug > 0)
     t2 = time.perf_counter()
     if os.environ.get("SUBG_PROFILE_HOST"):
-        print(f"[subg host ms] gset_sampler: graph+sample={1e3 * (t1 - t0):.1f} export={1e3 * (t2 - t1):.1f}", flush=True)
+        print(f"[subg host ms] gset_sampler: graph+sample={1e3 * (t1 - t0):.1f} export={1e3 * (t2 - t1):.1f}", file=sys.stderr, flush=True)
     _say(f"#SubGAcc: #enc_unique {spg.c}; compression ratio {spg.T / max(spg.c, 1):.2f}, dT_e {t2 - t1:.2f}s")
     spg.close()
     graph.close()
