@@ -57,7 +57,7 @@ class ClockSampler:
             self.nv = None
 
     def start(self):
-        if self.nv is None:
+        if self.nv is None or os.environ.get("BENCH_NO_CLOCKS"):
             return
         self.th = threading.Thread(target=self._pump, daemon=True)
         self.th.start()

@@ -31,7 +31,8 @@ namespace subg {
 
 constexpr int kWarpsPerBlock = 4;
 constexpr uint64_t kEmptyKey = ~0ull;
-constexpr uint32_t kStatusTableFull = 1u << 31;  // internal status bit
+constexpr uint32_t kStatusTableFull = 1u << 31;  // internal status bits
+constexpr uint32_t kStatusBadSeed = 1u << 30;
 constexpr int kFirstHopCap = 1000000;  // NEBMAX, subg_acc.c:13,750
 constexpr int kGW = 8;                 // walks advanced together per lane
 constexpr int kTicketBatch = 1;        // consecutive seeds a warp takes per ticket atomic
@@ -45,6 +46,7 @@ struct SamplerArgs {
     const int32_t *seeds;  // chunk-local [n_chunk]
     int64_t n_chunk;
     int64_t seed_base;     // global index of seeds[0]
+    int64_t N;             // nodes of the graph
     int M, m, stride, Kt;  // stride = reference's bucket stride (cap on set size); Kt = M*m+1 keys per seed
     int OB, LS;            // bits of the order field; log2 of the step slots per walk
     int SHIFT;             // 32 - clz(M), bits per LP column in the key
@@ -311,6 +313,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
         if (i >= a.n_chunk) break;
         const int64_t gi = a.seed_base + i;
         const int32_t u = __ldg(a.seeds + i);
+        if ((uint64_t)(int64_t)u >= (uint64_t)a.N) {  // the host turns this into the reference's TypeError
+            if (lane == 0) {
+                atomicOr(a.status, kStatusBadSeed);
+                a.nsize[i] = 0;
+                a.rowbeg[i] = 0;
+            }
+            continue;
+        }
 
         if (a.want_rank)
             for (int b = lane; b < a.nbw; b += 32) bitmap[b] = 0u;
@@ -606,9 +616,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
 // rand_r calls consumed per seed in the reference's single stream:
 // M for the Fisher-Yates draw if deg > M, plus M*(m-1) later hops if deg > 0.
 static __global__ void rand_r_calls_kernel(const void *rowptr, int rowptr64, const int32_t *seeds, int64_t n,
-                                    int M, int m, int32_t *calls) {
+                                    int64_t N, int M, int m, int32_t *calls) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t u = seeds[i];
+        if (u < 0 || u >= N) { calls[i] = 0; continue; }  // reported by check_seeds_kernel
         int64_t d = rowptr64 ? ((const long long *)rowptr)[u + 1] - ((const long long *)rowptr)[u]
                              : (int64_t)((const int *)rowptr)[u + 1] - ((const int *)rowptr)[u];
         if (d > kFirstHopCap) d = kFirstHopCap;

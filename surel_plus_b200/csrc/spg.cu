@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <mutex>
 #include <cstdlib>
 #include <string>
 #include <vector>
@@ -199,6 +200,23 @@ int spg_ensure_csr(SpG *s, cudaStream_t st) {
     return SUBG_OK;
 }
 
+// free device memory as of the first request (refresh = ask the driver again)
+static int64_t free_memory_estimate(int device, bool refresh) {
+    static std::mutex mu;
+    static std::vector<int64_t> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    if ((int)cache.size() <= device) cache.resize(device + 1, -1);
+    if (cache[device] < 0 || refresh) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+            cudaGetLastError();
+            free_b = (size_t)8 << 30;
+        }
+        cache[device] = (int64_t)free_b;
+    }
+    return cache[device];
+}
+
 struct SamplePlan {
     int EPL, OB, LS, SHIFT, stride, Kt, rowcap, nbw, fy_cap, lp_off, bitmap_off, smem_per_warp;
     bool key64, lp64;
@@ -289,10 +307,10 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
     {
         CK(dmalloc(&s->seeds, (size_t)n, st));
         CK(dmalloc(&s->nsize, (size_t)n, st));
-        CK(dmalloc(&d_flags, 4, st));
-        CK(dmalloc(&d_maxset, 1, st));
+        CK(dmalloc(&d_flags, 8, st));  // [0] status [1] tab_count [2] bad seeds [3] unique cnt [4] max set size
+        d_maxset = (int32_t *)(d_flags + 4);
         CK(dmalloc(&d_ctr, kCtrWords, st));
-        CK(cudaMemsetAsync(d_flags, 0, 4 * sizeof(uint32_t), st));
+        CK(cudaMemsetAsync(d_flags, 0, 8 * sizeof(uint32_t), st));
         if (n > 0) {
             CK(cudaMemcpyAsync(s->seeds, seeds_hd + lo, (size_t)n * sizeof(int32_t), cudaMemcpyDefault, st));
             check_seeds_kernel<<<std::min<int64_t>((n + 255) / 256, 4 * g->num_sms), 256, 0, st>>>(s->seeds, n, g->N, d_flags + 2);
@@ -314,7 +332,7 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
             CK(dmalloc(&call_base, (size_t)n_all + 1, st));
             CK(dmalloc(&scratch_all, (size_t)std::max(1, scan_num_blocks(n_all)), st));
             rand_r_calls_kernel<<<std::min<int64_t>((n_all + 255) / 256, 4 * g->num_sms), 256, 0, st>>>(
-                g->rowptr, g->rowptr64 ? 1 : 0, all_seeds, n_all, M, m, d_calls);
+                g->rowptr, g->rowptr64 ? 1 : 0, all_seeds, n_all, g->N, M, m, d_calls);
             CK(exclusive_scan_i32_i64(d_calls, call_base, n_all, 0, scratch_all, st));
             dfree(scratch_all, st);
         }
@@ -327,7 +345,9 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
                 CK(cudaMemcpyAsync(d_walks, walks_hd, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, st));
             }
         }
-        {   // the bad-seed flag must be known before any kernel indexes the graph with a seed
+        if (rng_mode == SUBG_RNG_RAND_R && n > 0) {
+            // rand_r_calls_kernel indexes the row pointer with every seed: the range check has to be known first
+            // (the sampler kernel itself skips out-of-range seeds and reports them through the status word)
             uint32_t bad = 0;
             CK(cudaMemcpyAsync(&bad, d_flags + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
@@ -339,25 +359,41 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
         // seed).  If that does not fit the budget the seeds go through in chunks and every chunk is
         // compacted into the growing CSR (the layout of the reference's dense `encoding`, subg_acc.c:848-872).
         const int entry_bytes = want_slot ? 10 : 8;
-        size_t free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
-        const int64_t budget = env_i64("SUBG_STAGING_BYTES", (int64_t)(free_b * 0.45));
-        int64_t chunk = std::max<int64_t>(1, budget / ((int64_t)pl.rowcap * entry_bytes));
-        chunk = std::min<int64_t>(chunk, std::max<int64_t>(n, 1));
-        const bool chunked = chunk < n;
-        const int64_t rows_cap = chunk * pl.rowcap + 16;
-        if (chunked) {
-            CK(dmalloc(&c_node, (size_t)rows_cap, st));
-            CK(dmalloc(&c_prov, (size_t)rows_cap, st));
-            if (want_slot) CK(dmalloc(&c_slot, (size_t)rows_cap, st));
-            CK(dmalloc(&c_rowbeg, (size_t)chunk, st));
-            CK(dmalloc(&s->indptr, (size_t)n + 1, st));
-        } else {
-            CK(dmalloc(&s->indices, (size_t)rows_cap, st));
-            CK(dmalloc((int32_t **)&s->data, (size_t)rows_cap, st));
-            if (want_slot) CK(dmalloc(&s->slot, (size_t)rows_cap, st));
-            CK(dmalloc(&s->rowbeg, (size_t)std::max<int64_t>(n, 1), st));
-            cap = rows_cap;
+        const int64_t worst = std::max<int64_t>(n, 1) * pl.rowcap * entry_bytes;
+        int64_t chunk = 0, rows_cap = 0;
+        bool chunked = false;
+        for (int tries = 0;; tries++) {
+            // cudaMemGetInfo is a driver round trip that can take milliseconds while other processes use
+            // the GPUs: the free-memory figure is cached per device and refreshed only when an allocation fails
+            int64_t free_b = (int64_t)8 << 30;
+            if (worst > (1ll << 30)) free_b = free_memory_estimate(g->device, tries > 0);
+            const int64_t budget = env_i64("SUBG_STAGING_BYTES", (int64_t)(free_b * 0.45));
+            chunk = std::max<int64_t>(1, budget / ((int64_t)pl.rowcap * entry_bytes));
+            chunk = std::min<int64_t>(chunk, std::max<int64_t>(n, 1));
+            chunked = chunk < n;
+            rows_cap = chunk * pl.rowcap + 16;
+            cudaError_t e = cudaSuccess;
+            if (chunked) {
+                e = dmalloc(&c_node, (size_t)rows_cap, st);
+                if (e == cudaSuccess) e = dmalloc(&c_prov, (size_t)rows_cap, st);
+                if (e == cudaSuccess && want_slot) e = dmalloc(&c_slot, (size_t)rows_cap, st);
+                if (e == cudaSuccess) e = dmalloc(&c_rowbeg, (size_t)chunk, st);
+                if (e == cudaSuccess) e = dmalloc(&s->indptr, (size_t)n + 1, st);
+            } else {
+                e = dmalloc(&s->indices, (size_t)rows_cap, st);
+                if (e == cudaSuccess) e = dmalloc((int32_t **)&s->data, (size_t)rows_cap, st);
+                if (e == cudaSuccess && want_slot) e = dmalloc(&s->slot, (size_t)rows_cap, st);
+                if (e == cudaSuccess) e = dmalloc(&s->rowbeg, (size_t)std::max<int64_t>(n, 1), st);
+                cap = rows_cap;
+            }
+            if (e == cudaSuccess) break;
+            if (e != cudaErrorMemoryAllocation || tries >= 1) CK(e);
+            cudaGetLastError();
+            dfree(c_node, st); dfree(c_prov, st); dfree(c_slot, st); dfree(c_rowbeg, st);
+            dfree(s->indptr, st); dfree(s->indices, st); dfree(s->data, st); dfree(s->slot, st); dfree(s->rowbeg, st);
+            c_node = c_prov = nullptr; c_slot = nullptr; c_rowbeg = nullptr;
+            s->indptr = nullptr; s->indices = nullptr; s->data = nullptr; s->slot = nullptr; s->rowbeg = nullptr;
+            cap = 0;
         }
 
         prof.mark("alloc_rows");
@@ -370,16 +406,18 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
             fill_u64_kernel<<<4 * g->num_sms, 256, 0, st>>>(tab_pos, tab_cap, ~0ull);
             CK(cudaMemsetAsync(d_flags, 0, 2 * sizeof(uint32_t), st));
             CK(cudaMemsetAsync(d_maxset, 0, sizeof(int32_t), st));
+            CK(cudaMemsetAsync(d_flags + 3, 0, sizeof(uint32_t), st));
 
             int64_t T = 0, extent = 0;
             bool table_full = false;
+            uint32_t flags_h[5] = {0, 0, 0, 0, 0};
             for (int64_t base = 0; base < n; base += chunk) {
                 const int64_t nc = std::min(chunk, n - base);
                 CK(cudaMemsetAsync(d_ctr, 0, kCtrWords * sizeof(unsigned long long), st));
                 SamplerArgs a{};
                 a.rowinfo = (const unsigned long long *)g->rowinfo; a.rowptr = g->rowptr; a.rowptr64 = g->rowptr64 ? 1 : 0; a.col = g->col;
                 a.seeds = s->seeds + base; a.n_chunk = nc; a.seed_base = lo + base;
-                a.M = M; a.m = m; a.stride = pl.stride; a.Kt = pl.Kt; a.OB = pl.OB; a.LS = pl.LS; a.SHIFT = pl.SHIFT;
+                a.N = g->N; a.M = M; a.m = m; a.stride = pl.stride; a.Kt = pl.Kt; a.OB = pl.OB; a.LS = pl.LS; a.SHIFT = pl.SHIFT;
                 a.rng_mode = rng_mode; a.rng_lo = (uint32_t)seed; a.rng_hi = (uint32_t)(seed >> 32);
                 a.call_base = (const int64_t *)call_base;
                 a.walks = d_walks ? d_walks + base * (int64_t)M * m : nullptr;
@@ -425,11 +463,11 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
                     cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
                 }
                 unsigned long long hctr[kCtrWords];
-                uint32_t flags_h[2];
                 CK(cudaMemcpyAsync(hctr, d_ctr, sizeof(hctr), cudaMemcpyDeviceToHost, st));
                 CK(cudaMemcpyAsync(flags_h, d_flags, sizeof(flags_h), cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
                 prof.mark("kernel+sync");
+                if (flags_h[2] || (flags_h[0] & kStatusBadSeed)) { rc = fail(SUBG_ERR_ARG, "query contains node ids outside [0, N)"); goto done; }
                 if (flags_h[1] > tab_cap / 2 || (flags_h[0] & kStatusTableFull)) { table_full = true; break; }
                 if (!chunked) {
                     T = (int64_t)hctr[kCtrTotal];
@@ -476,15 +514,10 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
             s->T = T; s->extent = extent; s->cap = cap;
 
             // ---- unique LP rows in first-occurrence order
-            uint32_t hflags[2];
-            int32_t mx = 0;
-            CK(cudaMemcpyAsync(hflags, d_flags, sizeof(hflags), cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(&mx, d_maxset, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            prof.mark("flags");
-            s->status = hflags[0] & ~kStatusTableFull;
-            s->max_set = mx;
-            const uint32_t c = hflags[1];
+            // (status, unique count and max set size came back with the last chunk's counters)
+            s->status = flags_h[0] & ~(kStatusTableFull | kStatusBadSeed);
+            s->max_set = (int32_t)flags_h[4];
+            const uint32_t c = flags_h[1];
             s->c = (int32_t)c;
             CK(dmalloc(&s->enc, (size_t)c * (m + 1), st));
             if (c > 0) {
@@ -520,9 +553,9 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
             s->rowbeg = s->indptr;
         }
         prof.mark("unique_launch");
-        CK(cudaStreamSynchronize(st));
-        prof.mark("unique_sync");
-        // a mostly empty worst-case allocation is not worth keeping
+        // No synchronisation here: the id remap is still in flight; everything that touches the SpG later
+        // (SpJoin, export, views, free) is ordered behind it on the stream.
+        // A mostly empty worst-case allocation is not worth keeping
         if (!s->indptr && cap > s->extent + s->extent / 4 + (16ll << 20)) {
             timing_begin(SUBG_TIMING_BUILD, st);
             const int erc = spg_ensure_csr(s, st);
@@ -538,7 +571,7 @@ done:
     dfree(c_node, st); dfree(c_prov, st); dfree(c_slot, st); dfree(c_rowbeg, st);
     dfree(tab_key, st); dfree(tab_pos, st); dfree(u_pos, st); dfree(u_pos2, st);
     dfree(u_slot, st); dfree(u_slot2, st); dfree(rank_of_slot, st);
-    dfree(d_flags, st); dfree(d_maxset, st); dfree(d_ctr, st); dfree(cub_tmp, st);
+    dfree(d_flags, st); dfree(d_ctr, st); dfree(cub_tmp, st);
     if (rc != SUBG_OK) {
         free_spg_arrays(s, st);
         delete s;

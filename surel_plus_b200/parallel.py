@@ -88,8 +88,11 @@ def all_gather_varlen(local: torch.Tensor, counts: np.ndarray, out: torch.Tensor
     offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
     assert local.shape[0] == counts[rank] and out.shape[0] == offs[-1]
     if backend == "nccl":
-        slices = [out[offs[r]:offs[r + 1]] for r in range(world)]
-        dist.all_gather(slices, local.contiguous(), group=group)
+        # bytes on the wire: NCCL has no int16 (the LP table), and a byte view costs nothing
+        ob = out.reshape(out.shape[0], -1).view(torch.uint8) if out.shape[0] else out.reshape(0, 1).view(torch.uint8)
+        lb = local.contiguous().reshape(local.shape[0], -1).view(torch.uint8) if local.shape[0] else ob[:0]
+        slices = [ob[offs[r]:offs[r + 1]] for r in range(world)]
+        dist.all_gather(slices, lb, group=group)
         return out
     # bytes on the wire (gloo has no int16): rows -> uint8 [rows, bytes_per_row]
     per_row = int(np.prod(local.shape[1:], dtype=np.int64))
