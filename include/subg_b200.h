@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SUBG_ABI_VERSION 2
+#define SUBG_ABI_VERSION 3
 
 #define SUBG_OK          0
 #define SUBG_ERR_ARG    -1
@@ -62,6 +62,7 @@ extern "C" {
 
 typedef struct subg_graph subg_graph; /* CSR graph resident in HBM (int64 or int32 rowptr, int32 col) */
 typedef struct subg_spg subg_spg;     /* SpG: CSR-of-sets resident in HBM */
+typedef struct subg_walkset subg_walkset; /* SUREL-v1 walks + relative-position encodings resident in HBM */
 
 int subg_abi_version(void);
 const char *subg_last_error(void);
@@ -189,6 +190,30 @@ int subg_spg_encode(const subg_graph *g, const subg_spg *x, int encoder, void *s
 
 /* forward pushes performed while building a PPR SpG (0 for other SpGs) */
 int subg_spg_pushes(const subg_spg *s, int64_t *pushes);
+
+/* ---- SUREL-v1 walk sampler ---------------------------------------------------------
+ * Replaces walk_sampler (subg_acc/subg_acc.c:316-389): random_walk (:144-181), random_walk_wo
+ * (:183-248) and rpe_encoder (:250-314).  The reference returns [walks, obj]: walks int32
+ * [n, num_walks*(num_steps+1)] (column 0 of every walk = the seed) and an object array whose row i
+ * holds the unique nodes of seed i's walks in first-visit order of the step-major scan (root first)
+ * and their int32 [count, num_steps+1] landing counts (entry [0][0] = num_walks).  Here the ragged
+ * part is one CSR-like triple: off int64[n+1], ids int32[T], rpe int32[T, num_steps+1].
+ *   replacement > 0 selects the first hop WITHOUT replacement, as the reference's flag does
+ *                   (subg_acc.c:359-367); <= 0: every hop uniform with replacement.
+ *   rng_mode        SUBG_RNG_PHILOX, or SUBG_RNG_RAND_R = the reference's nthread=1 stream (bit-exact).
+ * Limits: num_walks*num_steps + 1 <= 16384; num_walks <= 4096 when replacement > 0.
+ * Synchronises the stream (T sizes the allocations). */
+int subg_walk_sample(const subg_graph *g, const int32_t *seeds_hd, int64_t n, int num_walks, int num_steps,
+                     uint64_t seed, int rng_mode, int replacement, void *stream, subg_walkset **out);
+int subg_walkset_info(const subg_walkset *w, int64_t *n, int64_t *T, int32_t *num_walks, int32_t *ncol,
+                      uint32_t *status);
+/* copies to host or device destinations (any may be NULL); synchronises the stream */
+int subg_walkset_export(const subg_walkset *w, int32_t *walks_hd, int64_t *off_hd, int32_t *ids_hd,
+                        int32_t *rpe_hd, void *stream);
+/* device views, valid until subg_walkset_free */
+int subg_walkset_views(const subg_walkset *w, const int32_t **walks, const int64_t **off, const int32_t **ids,
+                       const int32_t **rpe);
+void subg_walkset_free(subg_walkset *w);
 
 /* ---- measurement hooks (bench.py / profiles) -------------------------------------
  * When enabled, the library brackets its dominant kernels with CUDA events on the

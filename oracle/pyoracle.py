@@ -57,6 +57,10 @@ def lib() -> C.CDLL:
     L.orc_ppr_push_many.restype = C.c_int
     L.orc_ppr_push_many.argtypes = [_i64p, _i32p, _i64p, _i32p, C.c_int64, C.c_float, C.c_float, _i32p, _f32p,
                                     C.c_int64, _i64p, _i64p, C.c_int]
+    L.orc_walk_sampler_walks.restype = C.c_uint32
+    L.orc_walk_sampler_walks.argtypes = [_i64p, _i32p, _i32p, C.c_int64, C.c_int, C.c_int, C.c_uint32, C.c_int, _i32p]
+    L.orc_rpe_encode.restype = C.c_int64
+    L.orc_rpe_encode.argtypes = [_i32p, C.c_int64, C.c_int, C.c_int, _i64p, _i32p, _i32p, C.c_int64]
     _lib = L
     return L
 
@@ -121,6 +125,41 @@ def gset_sampler_replay(indptr, indices, query, num_walks=100, num_steps=3, buck
     if debug > 0:
         out.append(r["raw"])
     return out
+
+
+# ------------------------------------------------------- SUREL-v1 walk_sampler
+def walk_sampler(ptr, neighs, query, num_walks=100, num_steps=3, seed=111413, replacement=-1):
+    """== reference walk_sampler(..., nthread=1) [subg_acc.c:144-389]: returns
+    [walks int32[n, M*(m+1)], obj[n,2]] with obj[i,0] = node ids in first-visit order of the
+    step-major scan and obj[i,1] = int32 [count, m+1] relative-position counts.
+    `replacement` truthy selects the first hop WITHOUT replacement (subg_acc.c:359-367; the
+    reference parses it with the 'p' predicate format, default -1 = with replacement)."""
+    q = _c(query, np.int32)
+    n, M, m = len(q), int(num_walks), int(num_steps)
+    without = 1 if (replacement is not None and replacement != -1 and bool(replacement)) else 0
+    walks = np.empty((n, M * (m + 1)), np.int32)
+    lib().orc_walk_sampler_walks(_c(ptr, np.int64), _c(neighs, np.int32), q, n, M, m, seed & 0xFFFFFFFF, without,
+                                 walks.reshape(-1))
+    off, ids, rpe = rpe_encode(walks, M, m)
+    obj = np.empty((n, 2), dtype=object)
+    for i in range(n):
+        obj[i, 0] = ids[off[i]:off[i + 1]]
+        obj[i, 1] = rpe[off[i]:off[i + 1]]
+    return [walks, obj]
+
+
+def rpe_encode(walks, M: int, m: int):
+    """rpe_encoder over every seed (subg_acc.c:250-314) -> (off int64[n+1], ids int32[T], rpe int32[T,m+1])."""
+    walks = _c(walks, np.int32).reshape(-1, M * (m + 1))
+    n = walks.shape[0]
+    cap = max(n * (M * m + 1), 1)
+    off = np.zeros(n + 1, np.int64)
+    ids = np.zeros(cap, np.int32)
+    rpe = np.zeros((cap, m + 1), np.int32)
+    T = lib().orc_rpe_encode(walks.reshape(-1), n, M, m, off, ids, rpe.reshape(-1), cap)
+    if T < 0:
+        raise MemoryError(f"oracle rpe_encode failed rc={T}")
+    return off, ids[:T].copy(), rpe[:T].copy()
 
 
 # -------------------------------------------------------------------- SpG build

@@ -527,3 +527,103 @@ int orc_ppr_push_many(const int64_t *rowptr, const int32_t *col, const int64_t *
     }
     return bad ? -1 : 0;
 }
+
+/* ------------------------------------------------------------------------- */
+/* SUREL-v1 walk_sampler: walks with the root in column 0   */
+/* and the relative-position encoder.  Single rand_r stream == reference with */
+/* nthread=1.                                                                 */
+/*   without <= 0: every hop uniform with replacement   subg_acc.c:144-181    */
+/*   without  > 0: first hop without replacement (round-robin if deg <= M,    */
+/*                 partial Fisher-Yates otherwise; no neighbourhood cap in    */
+/*                 this function)                       subg_acc.c:183-248    */
+/* walks[i][w][0..m], walks[i][w][0] = query[i].  Returns the RNG state.      */
+/* ------------------------------------------------------------------------- */
+uint32_t orc_walk_sampler_walks(const int64_t *rowptr, const int32_t *col,
+                                const int32_t *query, int64_t n, int M, int m,
+                                uint32_t seed, int without, int32_t *walks)
+{
+    uint32_t st = seed;
+    int32_t *perm = NULL;
+    int64_t perm_cap = 0;
+    for (int64_t i = 0; i < n; i++) {
+        const int32_t u = query[i];
+        const int64_t d = rowptr[u + 1] - rowptr[u];
+        if (without > 0 && d > M) {
+            if (d > perm_cap) {
+                perm_cap = d;
+                perm = (int32_t *)realloc(perm, (size_t)perm_cap * sizeof(int32_t));
+            }
+            for (int64_t j = 0; j < d; j++) perm[j] = (int32_t)j;
+            for (int k = 0; k < M; k++) {
+                const int64_t pick = orc_rand_r(&st) % (d - k) + k;
+                const int32_t tmp = perm[k];
+                perm[k] = perm[pick];
+                perm[pick] = tmp;
+            }
+        }
+        for (int w = 0; w < M; w++) {
+            int32_t *out = walks + (i * (int64_t)M + w) * (m + 1);
+            int32_t cur = u;
+            out[0] = cur;
+            for (int s = 0; s < m; s++) {
+                if (without > 0 && s == 0) {
+                    if (d >= 1) cur = col[rowptr[cur] + (d <= M ? (w % d) : perm[w])];
+                } else {
+                    const int64_t dn = rowptr[cur + 1] - rowptr[cur];
+                    if (dn > 0) cur = col[rowptr[cur] + (orc_rand_r(&st) % dn)];
+                }
+                out[s + 1] = cur;
+            }
+        }
+    }
+    free(perm);
+    return st;
+}
+
+/* ------------------------------------------------------------------------- */
+/* rpe_encoder, subg_acc.c:250-314: per seed, unique nodes numbered in        */
+/* first-visit order of the STEP-major, walk-minor scan (root = 0), and       */
+/* rpe[node][step] = number of walks at that node after `step` hops;          */
+/* rpe[root][0] = M.  Output is ragged: seed i owns ids[off[i]..off[i+1]) and */
+/* the matching rows of rpe[., m+1].  Returns the total or -1 if cap is short.*/
+/* ------------------------------------------------------------------------- */
+int64_t orc_rpe_encode(const int32_t *walks, int64_t n, int M, int m,
+                       int64_t *off, int32_t *ids, int32_t *rpe, int64_t cap)
+{
+    slotmap h;
+    if (slotmap_init(&h, (int64_t)M * m + 1)) return -2;
+    int64_t total = 0;
+    const int ncol = m + 1;
+    for (int64_t i = 0; i < n; i++) {
+        const int32_t *wk = walks + i * (int64_t)M * ncol;
+        h.gen++;
+        off[i] = total;
+        int32_t count = 0;
+        uint32_t pos;
+        /* the root first (:256-260) */
+        if (total + 1 > cap) { slotmap_free(&h); return -1; }
+        slotmap_find(&h, wk[0], &pos);
+        h.key[pos] = wk[0]; h.val[pos] = 0; h.stamp[pos] = h.gen;
+        ids[total] = wk[0];
+        memset(rpe + total * ncol, 0, sizeof(int32_t) * ncol);
+        rpe[total * ncol] = M;
+        count = 1;
+        for (int s = 1; s <= m; s++)
+            for (int w = 0; w < M; w++) {
+                const int32_t v = wk[(int64_t)w * ncol + s];
+                int32_t slot = slotmap_find(&h, v, &pos);
+                if (slot < 0) {
+                    if (total + count + 1 > cap) { slotmap_free(&h); return -1; }
+                    slot = count++;
+                    h.key[pos] = v; h.val[pos] = slot; h.stamp[pos] = h.gen;
+                    ids[total + slot] = v;
+                    memset(rpe + (total + slot) * ncol, 0, sizeof(int32_t) * ncol);
+                }
+                rpe[(total + slot) * ncol + s]++;
+            }
+        total += count;
+    }
+    off[n] = total;
+    slotmap_free(&h);
+    return total;
+}

@@ -5,10 +5,10 @@ No CPU fallback: importing works anywhere, calling needs the built library and a
 """
 from . import _capi
 from .spg import DeviceGraph, SpG
-from .sampler import subg_matrix
+from .sampler import subg_matrix, rw_matrix
 from .train import gather, hgather, bgather, pgather
-from .subg_acc import gset_sampler
+from .subg_acc import gset_sampler, walk_sampler
 from .pprgo import topk_ppr_matrix, encoding
 
-__all__ = ["DeviceGraph", "SpG", "subg_matrix", "gather", "hgather", "bgather", "pgather", "gset_sampler", "topk_ppr_matrix",
+__all__ = ["DeviceGraph", "SpG", "subg_matrix", "gather", "hgather", "bgather", "pgather", "gset_sampler", "walk_sampler", "rw_matrix", "topk_ppr_matrix",
            "encoding", "_capi"]

@@ -26,6 +26,7 @@ SYMBOLS = [
     "subg_spg_from_csr", "subg_spg_free",
     "subg_spjoin_plan", "subg_spjoin_run",
     "subg_ppr_topk", "subg_spg_encode", "subg_spg_pushes",
+    "subg_walk_sample", "subg_walkset_info", "subg_walkset_export", "subg_walkset_views", "subg_walkset_free",
     "subg_timing_enable", "subg_timing_read", "subg_launch_count",
     "subg_host_alloc", "subg_host_free",
 ]
@@ -70,6 +71,13 @@ def load() -> C.CDLL:
     L.subg_ppr_topk.argtypes = [vp, vp, i64, C.c_float, C.c_float, i32, i32, vp, i32, vp, C.POINTER(vp)]
     L.subg_spg_encode.argtypes = [vp, vp, i32, vp, C.POINTER(vp)]
     L.subg_spg_pushes.argtypes = [vp, C.POINTER(i64)]
+    L.subg_walk_sample.argtypes = [vp, vp, i64, i32, i32, u64, i32, i32, vp, C.POINTER(vp)]
+    L.subg_walkset_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                    C.POINTER(C.c_uint32)]
+    L.subg_walkset_export.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.subg_walkset_views.argtypes = [vp] + [C.POINTER(vp)] * 4
+    L.subg_walkset_free.argtypes = [vp]
+    L.subg_walkset_free.restype = None
     L.subg_timing_enable.argtypes = [i32]
     L.subg_timing_read.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(i64)]
     L.subg_launch_count.restype = i64

@@ -77,6 +77,13 @@ int spjoin_run_impl(const SpG *s, const int64_t *edge_dev, int64_t B, int arity,
 int ppr_topk_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, float alpha, float eps, int topk,
                   int normalization, const double *norm_deg_hd, cudaStream_t st, SpG **out);
 int spg_encode_impl(const Graph *g, const SpG *x, int encoder, cudaStream_t st, SpG **out);
+struct WalkSet;
+int walk_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, int M, int m, uint64_t seed, int rng_mode,
+                     int without, cudaStream_t st, WalkSet **out);
+int walkset_export_impl(const WalkSet *w, int32_t *walks_hd, int64_t *off_hd, int32_t *ids_hd, int32_t *rpe_hd, cudaStream_t st);
+int walkset_info_impl(const WalkSet *w, int64_t *n, int64_t *T, int32_t *M, int32_t *ncol, uint32_t *status);
+int walkset_views_impl(const WalkSet *w, const int32_t **walks, const int64_t **off, const int32_t **ids, const int32_t **rpe);
+void walkset_free_impl(WalkSet *w);
 
 __global__ void widen_rowptr_kernel(const int32_t *in, long long *out, int64_t n) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = in[i];
@@ -348,6 +355,24 @@ int subg_timing_read(int which, double *ms, int64_t *launches) {
     return SUBG_OK;
 }
 int64_t subg_launch_count(void) { return g_launches.load(); }
+
+int subg_walk_sample(const subg_graph *g, const int32_t *seeds_hd, int64_t n, int num_walks, int num_steps,
+                     uint64_t seed, int rng_mode, int replacement, void *stream, subg_walkset **out) {
+    return walk_sample_impl(reinterpret_cast<const Graph *>(g), seeds_hd, n, num_walks, num_steps, seed, rng_mode,
+                            replacement, (cudaStream_t)stream, reinterpret_cast<WalkSet **>(out));
+}
+int subg_walkset_info(const subg_walkset *w, int64_t *n, int64_t *T, int32_t *num_walks, int32_t *ncol, uint32_t *status) {
+    return walkset_info_impl(reinterpret_cast<const WalkSet *>(w), n, T, num_walks, ncol, status);
+}
+int subg_walkset_export(const subg_walkset *w, int32_t *walks_hd, int64_t *off_hd, int32_t *ids_hd, int32_t *rpe_hd,
+                        void *stream) {
+    return walkset_export_impl(reinterpret_cast<const WalkSet *>(w), walks_hd, off_hd, ids_hd, rpe_hd, (cudaStream_t)stream);
+}
+int subg_walkset_views(const subg_walkset *w, const int32_t **walks, const int64_t **off, const int32_t **ids,
+                       const int32_t **rpe) {
+    return walkset_views_impl(reinterpret_cast<const WalkSet *>(w), walks, off, ids, rpe);
+}
+void subg_walkset_free(subg_walkset *w) { walkset_free_impl(reinterpret_cast<WalkSet *>(w)); }
 
 int subg_host_alloc(void **ptr, int64_t bytes) {
     if (!ptr || bytes < 0) return fail(SUBG_ERR_ARG, "bad host allocation request");

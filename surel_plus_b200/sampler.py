@@ -25,3 +25,50 @@ def subg_matrix(G, train_idx, num_walks=200, num_steps=4, device="cuda", seed=11
     if own:
         graph.close()
     return z, z.enc_table()
+
+
+def gen_batch(iterable, n=1, keep=False):
+    """sampler/random_walks.py:25-33."""
+    length = len(iterable)
+    if keep:
+        for ndx in range(0, length, n):
+            yield iterable[ndx:min(ndx + n, length)]
+    else:
+        for ndx in range(0, length - n, n):
+            yield iterable[ndx:min(ndx + n, length)]
+
+
+def np_sampling(ptr, neighs, bsize, target, num_walks=200, num_steps=4, device="cuda", nthread=-1, seed=111413):
+    """sampler/random_walks.py:36-47: walk_sampler over batches of seeds (first hop without replacement);
+    returns (object array of per-seed node ids, stacked landing counts [T, num_steps+1])."""
+    from .subg_acc import walk_sampler
+    key, freq = [], []
+    for batch in gen_batch(target, bsize, True):
+        _, freqs = walk_sampler(ptr, neighs, batch, num_walks=num_walks, num_steps=num_steps, replacement=True,
+                                nthread=nthread, seed=seed, device=device)
+        key.append(freqs[:, 0])
+        freq.append(freqs[:, 1])
+    return np.concatenate(key), np.vstack(np.hstack(freq))
+
+
+def rw_matrix(G, train_idx, num_walks=200, num_steps=4, batch_size=2000, reduced=True, device="cuda", nthread=-1,
+              seed=111413):
+    """Legacy SUREL-v1 preprocessing (sampler/random_walks.py:58-73): same returns (z scipy CSR of
+    landing-count row pointers + 1, freqs with the all-zero row 0).  `fastremap.unique/remap` of the
+    reference is numpy's unique(return_index/return_inverse): ids follow the sorted projected keys."""
+    import scipy.sparse as sp
+    gsize = G.shape[0]
+    neighbors, freqs = np_sampling(G.indptr, G.indices, batch_size, train_idx, num_walks=num_walks,
+                                   num_steps=num_steps - 1, device=device, nthread=nthread, seed=seed)
+    if reduced:
+        proj = np.array([(num_walks + 1) ** i for i in reversed(range(num_steps))], dtype=np.int64)
+        idy = freqs.astype(np.int64) @ proj
+        _, idx, idy = np.unique(idy, return_index=True, return_inverse=True)
+        freqs = freqs[idx]
+    else:
+        idy = np.arange(len(freqs))
+    i = np.repeat(np.arange(len(neighbors)), np.fromiter(map(len, neighbors), dtype=int))
+    j = np.concatenate(neighbors)
+    z = sp.csr_matrix((idy + 1, (i, j)), (gsize, gsize))
+    freqs = np.insert(freqs, 0, np.zeros((1, num_steps)), axis=0)
+    return z, freqs

@@ -48,6 +48,60 @@ def _view(ptr, shape, typestr, dev, owner):
     return torch.as_tensor(_DevView(ptr, shape, typestr, owner), device=f"cuda:{dev}")
 
 
+class _PinnedPool:
+    """Page-locked host buffers for the arrays handed back to the caller (subg_host_alloc).  Locking
+    pages costs about a second per GB, so blocks are recycled: a block returns to the pool when the
+    numpy array built over it (and every view of it) is garbage collected.  Blocks are 12.5 % larger than
+    asked so that the next call, whose sizes differ slightly, still fits."""
+
+    def __init__(self, keep_bytes: int = 16 << 30):
+        self._free: list[tuple[int, int]] = []  # (capacity, address)
+        self._keep = keep_bytes
+        self._lib = None
+
+    def take(self, nbytes: int) -> tuple[int, int]:
+        fit = [b for b in self._free if b[0] >= nbytes]
+        if fit:
+            b = min(fit)
+            self._free.remove(b)
+            return b
+        self._lib = self._lib or _capi.load()
+        cap = max(4096, ((nbytes + (nbytes >> 3) + (1 << 21) - 1) >> 21) << 21) if nbytes > (1 << 20) else max(nbytes, 64)
+        p = C.c_void_p()
+        _capi.check(self._lib.subg_host_alloc(C.byref(p), cap))
+        return cap, p.value
+
+    def give(self, cap: int, addr: int) -> None:
+        try:
+            self._free.append((cap, addr))
+            while sum(b[0] for b in self._free) > self._keep:
+                c, a = self._free.pop(0)
+                self._lib.subg_host_free(C.c_void_p(a))
+        except Exception:  # interpreter shutdown
+            pass
+
+
+_pinned = _PinnedPool()
+
+
+class _PinnedBlock:
+    """Owner of one pooled block; numpy arrays reference it through __array_interface__."""
+
+    def __init__(self, shape, dtype):
+        self.shape, self.dtype = tuple(int(x) for x in shape), np.dtype(dtype)
+        nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        self.cap, self.addr = _pinned.take(nbytes)
+        self.__array_interface__ = {"shape": self.shape, "typestr": self.dtype.str, "data": (self.addr, False), "version": 3}
+
+    def __del__(self):
+        _pinned.give(self.cap, self.addr)
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """Uninitialised numpy array over pooled page-locked memory (asynchronous D2H target)."""
+    return np.asarray(_PinnedBlock(shape, dtype))
+
+
 class DeviceGraph:
     """CSR adjacency resident in HBM (replaces the `indptr, indices` numpy arguments of
     gset_sampler, subg_acc/subg_acc.c:655-671)."""
@@ -218,15 +272,15 @@ class SpG:
     def export_reference(self, want_raw: bool = False):
         """[nsize, remap, enc(, raw_enc)] exactly as gset_sampler returns them
         (subg_acc.c:1017-1024).  Host numpy arrays (filled through pinned memory)."""
-        nsize = torch.empty(self.n, dtype=torch.int32, pin_memory=True)
-        remap = torch.empty((2, self.T), dtype=torch.int32, pin_memory=True)
-        enc = torch.empty((self.c, self.ncol), dtype=torch.int16, pin_memory=True)
-        raw = torch.empty((self.T, self.ncol), dtype=torch.int16, pin_memory=True) if want_raw else None
-        _capi.check(self._lib.subg_spg_export(self._h, nsize.data_ptr(), remap.data_ptr(), enc.data_ptr(),
-                                              raw.data_ptr() if want_raw else None, _stream(self.device)))
-        out = [nsize.numpy(), remap.numpy(), enc.numpy()]
+        nsize = pinned_empty((self.n,), np.int32)
+        remap = pinned_empty((2, self.T), np.int32)
+        enc = pinned_empty((self.c, self.ncol), np.int16)
+        raw = pinned_empty((self.T, self.ncol), np.int16) if want_raw else None
+        _capi.check(self._lib.subg_spg_export(self._h, nsize.ctypes.data, remap.ctypes.data, enc.ctypes.data,
+                                              raw.ctypes.data if want_raw else None, _stream(self.device)))
+        out = [nsize, remap, enc]
         if want_raw:
-            out.append(raw.numpy())
+            out.append(raw)
         return out
 
     def enc_table(self) -> np.ndarray:

@@ -78,10 +78,58 @@ def gset_sampler(indptr, indices, query, num_walks=100, num_steps=3, bucket=-1, 
     return out
 
 
-def walk_sampler(ptr, neighs, query, num_walks=100, num_steps=3, nthread=-1, seed=111413, replacement=-1):
-    """SUREL-v1 walk + RPE sampler (subg_acc.c:144-389).  Not on the SUREL+ hot path
-    (SURVEY.md section 8f, row 2); the symbol exists because sampler/random_walks.py:18 imports it."""
-    raise NotImplementedError("walk_sampler (SUREL v1) is not part of the B200 hot path yet")
+def walk_sampler(ptr, neighs, query, num_walks=100, num_steps=3, nthread=-1, seed=111413, replacement=-1, device="cuda"):
+    """SUREL-v1 walk sampler + relative-position encoder (subg_acc.c:144-389).
+
+    Returns [walks, obj] as the reference: walks int32 [n, num_walks*(num_steps+1)] (column 0 of every
+    walk is the seed) and obj, an object array [n, 2] with obj[i,0] = the unique nodes of seed i's
+    walks (int32, first-visit order of the step-major scan, root first) and obj[i,1] = their int32
+    [count, num_steps+1] landing counts.  The reference parses `replacement` with the 'p' (predicate)
+    format: truthy selects the first hop WITHOUT replacement (subg_acc.c:359-367), the default -1
+    every hop with replacement.  nthread == 1 replays the reference's rand_r stream bit for bit.
+    The rows of obj are views into two arrays, obj.ids / obj.rpe are not copied per seed."""
+    import ctypes as C
+    from .spg import _dev_index, _stream, pinned_empty
+    try:
+        ptr = np.asarray(ptr)
+        neighs = np.asarray(neighs)
+        query = np.ascontiguousarray(np.asarray(query).astype(np.int32, copy=False))
+        num_walks, num_steps, nthread, seed = int(num_walks), int(num_steps), int(nthread), int(seed)
+        without = 1 if (replacement is not None and replacement != -1 and bool(replacement)) else 0
+    except Exception as e:  # subg_acc.c:323-327
+        raise TypeError("Input parsing error.\n") from e
+    lib = _capi.load()
+    graph = DeviceGraph(ptr, neighs, device)
+    dev = graph.device
+    h = C.c_void_p()
+    n = query.size
+    try:
+        _capi.check(lib.subg_walk_sample(graph._h, query.ctypes.data, n, num_walks, num_steps, seed & 0xFFFFFFFF,
+                                         _rng_mode(nthread), without, _stream(dev), C.byref(h)))
+        T = C.c_int64()
+        st = C.c_uint32()
+        _capi.check(lib.subg_walkset_info(h, None, C.byref(T), None, None, C.byref(st)))
+        T = T.value
+        if st.value & _capi.STATUS_DEAD_END:
+            _say("#SubGAcc: rand_r replay met a node without out-neighbours; output is a valid sample "
+                 "but no longer the reference's nthread=1 stream.")
+        ncol = num_steps + 1
+        walks = pinned_empty((n, num_walks * ncol), np.int32)
+        off = pinned_empty((n + 1,), np.int64)
+        ids = pinned_empty((T,), np.int32)
+        rpe = pinned_empty((T, ncol), np.int32)
+        _capi.check(lib.subg_walkset_export(h, walks.ctypes.data, off.ctypes.data, ids.ctypes.data, rpe.ctypes.data,
+                                            _stream(dev)))
+    finally:
+        if h.value:
+            lib.subg_walkset_free(h)
+        graph.close()
+    obj = np.empty((n, 2), dtype=object)
+    o = off.tolist()
+    for i in range(n):
+        obj[i, 0] = ids[o[i]:o[i + 1]]
+        obj[i, 1] = rpe[o[i]:o[i + 1]]
+    return [walks, obj]
 
 
 def walk_join(*args, **kwargs):

@@ -9,6 +9,7 @@ What is called (nothing is copied; the reference code is executed where it lies)
   * subg_acc.gset_sampler  -- the C extension compiled from /root/reference/subg_acc/subg_acc.c
     (oracle/Makefile target `ref`), nthread=1 so that its shared rand_r word is deterministic
     (subg_acc.c:731-732).
+  * subg_acc.walk_sampler  -- same extension (SUREL-v1 walks + relative-position encoder), nthread=1.
   * train.gather / hgather / pgather+bgather -- imported from /root/reference/train.py, device='cpu',
     numpy edge arrays (scipy >= 1.12 rejects torch row indices).
   * sampler.pprgo.topk_ppr_matrix / calc_ppr_topk_parallel / _calc_ppr_node -- imported from
@@ -173,9 +174,35 @@ def gen_ppr(out):
     out["spd_edge"], out["spd_xz"], out["spd_ptr"] = edge, xz.numpy(), ptr.numpy()
 
 
+def gen_walks(out):
+    """walk_sampler of the compiled reference (subg_acc.c:316-389), nthread=1, both first-hop modes.
+    The object array is flattened to (off, ids, rpe)."""
+    subg = ref.subg_acc()
+    A = small_graph()
+    n = A.shape[0]
+    indptr, indices = A.indptr.astype(np.int32), A.indices.astype(np.int32)
+    q = np.arange(n, dtype=np.int32)
+    qs = np.random.default_rng(4).permutation(n)[:150].astype(np.int32)
+    cases = [(20, 3, 0, 99), (20, 3, 1, 99), (50, 2, 1, 7), (7, 4, 0, 5), (200, 3, 1, 111413), (33, 1, 1, 3), (33, 1, 0, 3)]
+    out["walk_cases"] = np.array(cases, np.int64)
+    out["walk_subset_query"] = qs
+    for ci, (M, m, without, seed) in enumerate(cases):
+        query = qs if ci == 2 else q
+        kw = {"replacement": True} if without else {}
+        walks, obj = subg.walk_sampler(indptr, indices, query, num_walks=M, num_steps=m, nthread=1, seed=seed, **kw)
+        sizes = np.array([len(obj[i, 0]) for i in range(len(query))], np.int64)
+        out[f"walk{ci}_walks"] = walks
+        out[f"walk{ci}_off"] = np.concatenate([[0], np.cumsum(sizes)])
+        out[f"walk{ci}_ids"] = np.concatenate([obj[i, 0] for i in range(len(query))])
+        out[f"walk{ci}_rpe"] = np.vstack([obj[i, 1] for i in range(len(query))])
+
+
 def main():
     assert ref.have_reference_tree(), "needs /root/reference"
-    for name, fn in (("gset", gen_gset), ("spjoin", gen_spjoin), ("ppr", gen_ppr)):
+    only = sys.argv[1:]
+    for name, fn in (("gset", gen_gset), ("spjoin", gen_spjoin), ("ppr", gen_ppr), ("walks", gen_walks)):
+        if only and name not in only:
+            continue
         out = {}
         fn(out)
         path = os.path.join(HERE, f"{name}.npz")

@@ -172,3 +172,32 @@ def test_value_join_equals_reference_gather(ppr, gset):
     xz, sl, sr = po.spjoin_pair(xs, ppr["spd_edge"])
     assert np.array_equal(xz.astype(np.float32)[..., None], ppr["spd_xz"])
     assert np.array_equal(po.pair_index(sl, sr, True), ppr["spd_ptr"])
+
+
+# ------------------------------------------------------------------ SUREL-v1 walk_sampler
+@pytest.fixture(scope="module")
+def walks_gold():
+    return np.load(os.path.join(GOLD, "walks.npz"))
+
+
+def test_walk_sampler_equals_reference_nthread1(gset, walks_gold):
+    """orc_walk_sampler_walks + orc_rpe_encode == reference walk_sampler(nthread=1) (subg_acc.c:144-389)."""
+    indptr, indices = gset["graph_indptr"], gset["graph_indices"]
+    q_all = np.arange(len(indptr) - 1)
+    for ci, (M, m, without, seed) in enumerate(walks_gold["walk_cases"].tolist()):
+        q = walks_gold["walk_subset_query"] if ci == 2 else q_all
+        walks, obj = po.walk_sampler(indptr, indices, q, M, m, seed, True if without else -1)
+        assert walks.dtype == np.int32 and np.array_equal(walks, walks_gold[f"walk{ci}_walks"]), ci
+        off = walks_gold[f"walk{ci}_off"]
+        assert np.array_equal(np.concatenate([obj[i, 0] for i in range(len(q))]), walks_gold[f"walk{ci}_ids"]), ci
+        assert np.array_equal(np.vstack([obj[i, 1] for i in range(len(q))]), walks_gold[f"walk{ci}_rpe"]), ci
+        assert np.array_equal(np.cumsum([len(obj[i, 0]) for i in range(len(q))]), off[1:]), ci
+
+
+def test_rpe_invariants_on_golden(walks_gold):
+    """Column sums: every step column of a seed's rpe sums to M; entry [0][0] = M (subg_acc.c:294-303)."""
+    for ci, (M, m, without, seed) in enumerate(walks_gold["walk_cases"].tolist()):
+        off, rpe = walks_gold[f"walk{ci}_off"], walks_gold[f"walk{ci}_rpe"]
+        seg = np.add.reduceat(rpe, off[:-1], axis=0)
+        assert np.all(seg == M), ci
+        assert np.all(rpe[off[:-1], 0] == M), ci

@@ -116,3 +116,20 @@ def test_topk_ppr_matrix_vs_reference(mid_graph):
         common = exp.multiply(got > 0)
         common2 = got.multiply(exp > 0)
         assert np.array_equal(common.tocsr().data, common2.tocsr().data)
+
+
+@pytest.mark.parametrize("M,m,rep,seed", [(200, 3, True, 111413), (200, 3, -1, 5), (100, 2, True, 1), (1, 1, -1, 2),
+                                          (300, 2, True, 3), (17, 6, -1, 4)])
+def test_walk_sampler_vs_compiled_reference(subg, mid_graph, M, m, rep, seed):
+    """SUREL-v1 walk_sampler (subg_acc.c:144-389): oracle == compiled reference with nthread=1."""
+    A = mid_graph
+    rng = np.random.default_rng(seed)
+    q = rng.permutation(A.shape[0])[:800].astype(np.int32)
+    q[:3] = [A.shape[0] - 1, A.shape[0] - 2, 0]
+    indptr, indices = A.indptr.astype(np.int32), A.indices.astype(np.int32)
+    kw = {} if rep == -1 else {"replacement": rep}
+    walks, obj = subg.walk_sampler(indptr, indices, q, num_walks=M, num_steps=m, nthread=1, seed=seed, **kw)
+    o_walks, o_obj = po.walk_sampler(indptr, indices, q, M, m, seed, rep)
+    assert np.array_equal(walks, o_walks)
+    for i in range(len(q)):
+        assert np.array_equal(obj[i, 0], o_obj[i, 0]) and np.array_equal(obj[i, 1], o_obj[i, 1]), i
