@@ -37,8 +37,6 @@ constexpr int kFirstHopCap = 1000000;  // NEBMAX, subg_acc.c:13,750
 constexpr int kGW = 8;                 // walks advanced together per lane
 constexpr int kTicketBatch = 1;        // consecutive seeds a warp takes per ticket atomic
 constexpr int kCtrCursor = 16, kCtrTotal = 32, kCtrWords = 48;
-constexpr int kLpCacheSlots = 32;      // per-warp direct-mapped cache of interned LP keys
-constexpr int kLpCacheBytes = kLpCacheSlots * 20;
 
 struct SamplerArgs {
     const unsigned long long *rowinfo;  // [N] row start (low 40 bits) | degree (high 24 bits, 0xFFFFFF = escape)
@@ -80,7 +78,6 @@ struct SamplerArgs {
     int lp_off;      // byte offset of the member LP rows (region 2; region 1 at 0 = key buffer / member keys)
     int lp64;        // LP rows need 64 bits (m * SHIFT + 1 > 32)
     int bitmap_off;  // byte offset of the rank bitmap
-    int cache_off;   // byte offset of the warp's LP-key cache (kLpCacheSlots x {key, position, slot})
     int smem_per_warp;
 };
 
@@ -262,7 +259,7 @@ __device__ __forceinline__ uint32_t intern_key(const SamplerArgs &a, unsigned lo
 template <typename K, int EPL>
 constexpr int sampler_min_blocks() {
     constexpr int W = (int)sizeof(K) / 4;
-    constexpr int smem_warp = ((int)sizeof(K) + 4) * 32 * EPL + 256 + kLpCacheBytes;
+    constexpr int smem_warp = ((int)sizeof(K) + 4) * 32 * EPL + 256;
     constexpr int by_smem = 232448 / (kWarpsPerBlock * smem_warp);
     constexpr int by_regs = 65536 / (kWarpsPerBlock * 32 * (EPL * W + 52));
     constexpr int b = by_smem < by_regs ? by_smem : by_regs;
@@ -293,17 +290,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
     int32_t *fy_val = fy_dense + a.M;
     uint32_t *bitmap = (uint32_t *)(wsm + a.bitmap_off);
     uint32_t *bprefix = bitmap + a.nbw;
-    // LP rows repeat heavily (a few hundred distinct rows over hundreds of millions of members): equal rows
-    // of a batch are looked up once (match.any), and a small per-warp cache answers most of those
-    unsigned long long *c_key = (unsigned long long *)(wsm + a.cache_off);
-    unsigned long long *c_pos = c_key + kLpCacheSlots;  // smallest position this warp has reported for the key
-    uint32_t *c_slot = (uint32_t *)(c_pos + kLpCacheSlots);
-    if (lane < kLpCacheSlots) {
-        c_key[lane] = kEmptyKey;
-        c_pos[lane] = 0ull;
-        c_slot[lane] = 0u;
-    }
-    __syncwarp();
     const int M = a.M, m = a.m, OB = a.OB, LS = a.LS;
     const uint32_t ord_mask = (1u << OB) - 1u;
     const uint32_t step_mask = (1u << LS) - 1u;
@@ -571,8 +557,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
         int done = 0;
         for (int t0 = 0; t0 < s_total; t0 += 64) {
             K kk[2];
-            unsigned long long lp[2];
-            uint32_t ord[2], rank[2];
+            unsigned long long lp[2], cur[2], seen[2];
+            uint32_t h[2], ord[2], rank[2];
             bool keep[2];
             int o[2];
 #pragma unroll
@@ -599,47 +585,18 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
                     done += __popc(km);
                 }
                 if (ord[q] == 0) lp[q] |= 1ull << (m * a.SHIFT);  // the root row (LEAD, subg_acc.c:944-949)
+                h[q] = lp_hash(lp[q]) & a.tab_mask;
+                cur[q] = kEmptyKey;
+                seen[q] = 0ull;
+                if (keep[q]) {
+                    cur[q] = a.tab_key[h[q]];
+                    seen[q] = a.tab_pos[h[q]];
+                }
             }
 #pragma unroll
             for (int q = 0; q < 2; q++) {
-                // one lookup per distinct LP row of the batch: the lowest lane of every group of equal rows leads,
-                // with the group's smallest stream position
-                const uint32_t vmask = __ballot_sync(FULL, keep[q]);
-                uint32_t grp = 0, slot = 0;
-                int leader = 0;
-                unsigned long long pos = 0ull;
-                bool lead = false, hit = false;
-                const uint32_t hsh = lp_hash(lp[q]);
-                const uint32_t ci = (hsh >> 22) & (kLpCacheSlots - 1);
                 if (keep[q]) {
-                    grp = __match_any_sync(vmask, lp[q]);
-                    leader = __ffs((int)grp) - 1;
-                    pos = ((unsigned long long)gi << 16) | __reduce_min_sync(grp, ord[q]);
-                    lead = lane == leader;
-                    if (lead && c_key[ci] == lp[q]) {
-                        hit = true;
-                        slot = c_slot[ci];
-                        if (pos < c_pos[ci]) {  // only within the seed that brought the key in
-                            atomicMin(&a.tab_pos[slot], pos);
-                            c_pos[ci] = pos;
-                        }
-                    }
-                }
-                __syncwarp();
-                const uint32_t miss = __ballot_sync(FULL, lead && !hit);
-                if (lead && !hit) {
-                    const uint32_t h = hsh & a.tab_mask;
-                    slot = intern_key(a, lp[q], pos, h, a.tab_key[h], a.tab_pos[h]);
-                    const uint32_t same = __match_any_sync(miss, ci);
-                    if (lane == __ffs((int)same) - 1) {
-                        c_key[ci] = lp[q];
-                        c_pos[ci] = pos;
-                        c_slot[ci] = slot;
-                    }
-                }
-                __syncwarp();
-                if (keep[q]) {
-                    const uint32_t prov = __shfl_sync(grp, slot, leader);
+                    const uint32_t prov = intern_key(a, lp[q], ((unsigned long long)gi << 16) | ord[q], h[q], cur[q], seen[q]);
                     a.out_node[base + o[q]] = (int32_t)(kk[q] >> OB);
                     a.out_prov[base + o[q]] = (int32_t)prov;
                     if (a.out_slot) a.out_slot[base + o[q]] = (uint16_t)rank[q];

@@ -218,7 +218,7 @@ static int64_t free_memory_estimate(int device, bool refresh) {
 }
 
 struct SamplePlan {
-    int EPL, OB, LS, SHIFT, stride, Kt, rowcap, nbw, fy_cap, lp_off, bitmap_off, cache_off, smem_per_warp;
+    int EPL, OB, LS, SHIFT, stride, Kt, rowcap, nbw, fy_cap, lp_off, bitmap_off, smem_per_warp;
     bool key64, lp64;
 };
 
@@ -256,8 +256,7 @@ static int make_plan(const Graph *g, int M, int m, int bucket, SamplePlan *p) {
     const int fy_half = 4 * M + 4 * fc;
     p->lp_off = (std::max(ksz * 32 * p->EPL, fy_half) + 15) & ~15;
     p->bitmap_off = (p->lp_off + std::max((p->lp64 ? 8 : 4) * (int)Kt, fy_half) + 15) & ~15;
-    p->cache_off = (p->bitmap_off + 8 * p->nbw + 15) & ~15;
-    p->smem_per_warp = (p->cache_off + kLpCacheBytes + 15) & ~15;
+    p->smem_per_warp = (p->bitmap_off + 8 * p->nbw + 15) & ~15;
     return SUBG_OK;
 }
 
@@ -439,7 +438,7 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
                 }
                 a.tab_key = tab_key; a.tab_pos = tab_pos; a.tab_mask = tab_cap - 1;
                 a.tab_count = d_flags + 1; a.status = d_flags;
-                a.nbw = pl.nbw; a.fy_cap = pl.fy_cap; a.lp_off = pl.lp_off; a.lp64 = pl.lp64 ? 1 : 0; a.bitmap_off = pl.bitmap_off; a.cache_off = pl.cache_off;
+                a.nbw = pl.nbw; a.fy_cap = pl.fy_cap; a.lp_off = pl.lp_off; a.lp64 = pl.lp64 ? 1 : 0; a.bitmap_off = pl.bitmap_off;
                 a.smem_per_warp = pl.smem_per_warp;
                 const int l2_persist = (int)env_i64("SUBG_L2_PERSIST", 0);
                 if (l2_persist) {  // experiment knob: pin the row-info array in the persisting L2 carve-out
