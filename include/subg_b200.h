@@ -74,6 +74,16 @@ const char *subg_last_error(void);
  * 32-bit rowptr in HBM (8-byte rowptr pair per walk step), larger ones with 64-bit. */
 int subg_graph_create(const void *rowptr_hd, int rowptr_is64, const int32_t *col_hd,
                       int64_t N, int64_t E, int device, void *stream, subg_graph **out);
+/* Edge list -> CSR on the device.  Replaces edge2csr (subg_acc/test/test.py:15-19:
+ * csr_matrix((ones, (row, col)), shape=(nmax+1, nmax+1)): duplicate edges coalesced, columns ascending)
+ * and, with symmetrize != 0, the symmetrisation of dataloader.py:119-129 (every edge stored in both
+ * directions).  row_hd / col_hd: int64[E], host or device.  num_nodes < 0 -> largest id + 1.
+ * drop_self_loops != 0 removes (u, u) entries.  The row pointer is kept 64-bit when the coalesced
+ * graph has >= 2^31 entries.  Synchronises the stream. */
+int subg_graph_from_edges(const int64_t *row_hd, const int64_t *col_hd, int64_t E, int64_t num_nodes,
+                          int symmetrize, int drop_self_loops, int device, void *stream, subg_graph **out);
+/* CSR of a resident graph back to the caller: rowptr int64[N+1], col int32[E] (host or device; either may be NULL) */
+int subg_graph_export(const subg_graph *g, int64_t *rowptr_hd, int32_t *col_hd, void *stream);
 int subg_graph_info(const subg_graph *g, int64_t *N, int64_t *E, int *device);
 void subg_graph_free(subg_graph *g);
 
@@ -163,6 +173,15 @@ int subg_spjoin_plan(const subg_spg *s, const int64_t *edge_hd, int64_t B, int a
 int subg_spjoin_run(const subg_spg *s, const int64_t *edge_dev, int64_t B, int arity,
                     const int64_t *indptr_dev, const float *enc_table_dev, int k,
                     void *out_dev, int64_t *segid_dev, void *stream);
+
+/* plan + run in one call with a single host synchronisation (the per-batch call of the training loop):
+ * the caller passes out_dev (and segid_dev) with room for out_capacity rows, e.g. sized from the previous
+ * batch; sizes, scan and the join kernel are queued back to back and the kernel checks on the device that
+ * the rows fit.  *N_out = total rows; *ran = 1 if out_dev was written, 0 if out_capacity was too small (then
+ * allocate *N_out rows and call subg_spjoin_run: edge_dev and indptr_dev are already filled). */
+int subg_spjoin(const subg_spg *s, const int64_t *edge_hd, int64_t B, int arity, int64_t *edge_dev,
+                int64_t *indptr_dev, const float *enc_table_dev, int k, void *out_dev, int64_t out_capacity,
+                int64_t *segid_dev, int64_t *N_out, int *ran, void *stream);
 
 /* ---- PPR set sampler -----------------------------------------------------------
  * Replaces topk_ppr_matrix (sampler/pprgo.py:83-111): ACL forward push per seed

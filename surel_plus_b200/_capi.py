@@ -21,10 +21,10 @@ TIMING_SAMPLER, TIMING_SPJOIN, TIMING_BUILD, TIMING_PPR = 0, 1, 2, 3
 #: every symbol include/subg_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
     "subg_abi_version", "subg_last_error",
-    "subg_graph_create", "subg_graph_info", "subg_graph_free",
+    "subg_graph_create", "subg_graph_from_edges", "subg_graph_export", "subg_graph_info", "subg_graph_free",
     "subg_gset_sample", "subg_gset_sample_shard", "subg_spg_set_lp_table", "subg_spg_info", "subg_spg_export", "subg_spg_views", "subg_spg_rows",
     "subg_spg_from_csr", "subg_spg_free",
-    "subg_spjoin_plan", "subg_spjoin_run",
+    "subg_spjoin_plan", "subg_spjoin_run", "subg_spjoin",
     "subg_ppr_topk", "subg_spg_encode", "subg_spg_pushes",
     "subg_walk_sample", "subg_walkset_info", "subg_walkset_export", "subg_walkset_views", "subg_walkset_free",
     "subg_timing_enable", "subg_timing_read", "subg_launch_count",
@@ -52,6 +52,8 @@ def load() -> C.CDLL:
     L.subg_abi_version.restype = i32
     L.subg_last_error.restype = C.c_char_p
     L.subg_graph_create.argtypes = [vp, i32, vp, i64, i64, i32, vp, C.POINTER(vp)]
+    L.subg_graph_from_edges.argtypes = [vp, vp, i64, i64, i32, i32, i32, vp, C.POINTER(vp)]
+    L.subg_graph_export.argtypes = [vp, vp, vp, vp]
     L.subg_graph_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
     L.subg_graph_free.argtypes = [vp]
     L.subg_graph_free.restype = None
@@ -68,6 +70,7 @@ def load() -> C.CDLL:
     L.subg_spg_free.restype = None
     L.subg_spjoin_plan.argtypes = [vp, vp, i64, i32, vp, vp, C.POINTER(i64), vp]
     L.subg_spjoin_run.argtypes = [vp, vp, i64, i32, vp, vp, i32, vp, vp, vp]
+    L.subg_spjoin.argtypes = [vp, vp, i64, i32, vp, vp, vp, i32, vp, i64, vp, C.POINTER(i64), C.POINTER(i32), vp]
     L.subg_ppr_topk.argtypes = [vp, vp, i64, C.c_float, C.c_float, i32, i32, vp, i32, vp, C.POINTER(vp)]
     L.subg_spg_encode.argtypes = [vp, vp, i32, vp, C.POINTER(vp)]
     L.subg_spg_pushes.argtypes = [vp, C.POINTER(i64)]

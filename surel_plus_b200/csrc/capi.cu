@@ -74,9 +74,15 @@ int spjoin_plan_impl(const SpG *s, const int64_t *edge_hd, int64_t B, int arity,
                      int64_t *indptr_dev, int64_t *N_out, cudaStream_t st);
 int spjoin_run_impl(const SpG *s, const int64_t *edge_dev, int64_t B, int arity, const int64_t *indptr_dev,
                     const float *enc_table_dev, int k, void *out_dev, int64_t *segid_dev, cudaStream_t st);
+int spjoin_fused_impl(const SpG *s, const int64_t *edge_hd, int64_t B, int arity, int64_t *edge_dev, int64_t *indptr_dev,
+                      const float *enc_table_dev, int k, void *out_dev, int64_t out_capacity, int64_t *segid_dev,
+                      int64_t *N_out, int *ran, cudaStream_t st);
 int ppr_topk_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, float alpha, float eps, int topk,
                   int normalization, const double *norm_deg_hd, cudaStream_t st, SpG **out);
 int spg_encode_impl(const Graph *g, const SpG *x, int encoder, cudaStream_t st, SpG **out);
+int graph_from_edges_impl(const int64_t *row_hd, const int64_t *col_hd, int64_t E, int64_t N_in, int symmetrize,
+                          int drop_self_loops, int device, cudaStream_t st, Graph **out);
+int graph_export_impl(const Graph *g, int64_t *rowptr_hd, int32_t *col_hd, cudaStream_t st);
 struct WalkSet;
 int walk_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, int M, int m, uint64_t seed, int rng_mode,
                      int without, cudaStream_t st, WalkSet **out);
@@ -189,6 +195,16 @@ int subg_graph_create(const void *rowptr_hd, int rowptr_is64, const int32_t *col
     return SUBG_OK;
 }
 
+int subg_graph_from_edges(const int64_t *row_hd, const int64_t *col_hd, int64_t E, int64_t num_nodes, int symmetrize,
+                          int drop_self_loops, int device, void *stream, subg_graph **out) {
+    if (int rc = init_device(device)) return rc;
+    return graph_from_edges_impl(row_hd, col_hd, E, num_nodes, symmetrize, drop_self_loops, device, (cudaStream_t)stream,
+                                 reinterpret_cast<Graph **>(out));
+}
+int subg_graph_export(const subg_graph *g, int64_t *rowptr_hd, int32_t *col_hd, void *stream) {
+    return graph_export_impl(reinterpret_cast<const Graph *>(g), rowptr_hd, col_hd, (cudaStream_t)stream);
+}
+
 int subg_graph_info(const subg_graph *g_, int64_t *N, int64_t *E, int *device) {
     const Graph *g = reinterpret_cast<const Graph *>(g_);
     if (!g) return fail(SUBG_ERR_ARG, "null graph");
@@ -291,6 +307,13 @@ int subg_spjoin_run(const subg_spg *s, const int64_t *edge_dev, int64_t B, int a
                     const float *enc_table_dev, int k, void *out_dev, int64_t *segid_dev, void *stream) {
     return spjoin_run_impl(reinterpret_cast<const SpG *>(s), edge_dev, B, arity, indptr_dev, enc_table_dev, k, out_dev,
                            segid_dev, (cudaStream_t)stream);
+}
+
+int subg_spjoin(const subg_spg *s, const int64_t *edge_hd, int64_t B, int arity, int64_t *edge_dev, int64_t *indptr_dev,
+                const float *enc_table_dev, int k, void *out_dev, int64_t out_capacity, int64_t *segid_dev, int64_t *N_out,
+                int *ran, void *stream) {
+    return spjoin_fused_impl(reinterpret_cast<const SpG *>(s), edge_hd, B, arity, edge_dev, indptr_dev, enc_table_dev, k,
+                             out_dev, out_capacity, segid_dev, N_out, ran, (cudaStream_t)stream);
 }
 
 int subg_ppr_topk(const subg_graph *g, const int32_t *seeds_hd, int64_t n, float alpha, float eps, int topk,

@@ -38,7 +38,17 @@ struct JoinArgs {
     long long *segid;
     int64_t ntask;
     int cap;  // staged elements per row slice
+    // fused plan + run (subg_spjoin): the kernel runs right behind the plan, without the host having seen the row
+    // count; it backs out when the rows do not fit the caller's buffer or a query node is out of range
+    int64_t max_rows;          // < 0: no check
+    const uint32_t *bad;       // nullable
 };
+
+__device__ __forceinline__ bool join_must_skip(const JoinArgs &p) {
+    if (p.max_rows < 0) return false;
+    const int64_t nseg = (p.arity == 2 ? 2 : 4) * p.B;
+    return p.seg_ptr[nseg] > p.max_rows || (p.bad && *p.bad);
+}
 
 __device__ __forceinline__ int row_size(const JoinArgs &p, int64_t u) {
     return p.nsize ? p.nsize[u] : (int)(p.rowbeg[u + 1] - p.rowbeg[u]);
@@ -167,6 +177,7 @@ __global__ void __launch_bounds__(kJoinThreads) spjoin_kernel(const JoinArgs p) 
     const V *gdata = (const V *)p.data;
     constexpr int AE = ValTraits<V>::align_elems;
 
+    if (join_must_skip(p)) return;
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -284,6 +295,7 @@ __global__ void __launch_bounds__(kJoinThreads) spjoin_kernel(const JoinArgs p) 
 template <typename V, int MODE>
 __global__ void __launch_bounds__(kJoinThreads) spjoin_global_kernel(const JoinArgs p) {
     const V *gdata = (const V *)p.data;
+    if (join_must_skip(p)) return;
     for (int64_t t = blockIdx.x; t < p.ntask; t += gridDim.x) {
         int64_t a, b, segA, segB;
         task_nodes(p, t, a, b, segA, segB);
@@ -384,8 +396,9 @@ static cudaError_t launch_join(const SpG *s, JoinArgs &p, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-int spjoin_run_impl(const SpG *s, const int64_t *edge_dev, int64_t B, int arity, const int64_t *indptr_dev,
-                    const float *enc_table_dev, int k, void *out_dev, int64_t *segid_dev, cudaStream_t st) {
+static int join_launch(const SpG *s, const int64_t *edge_dev, int64_t B, int arity, const int64_t *indptr_dev,
+                       const float *enc_table_dev, int k, void *out_dev, int64_t *segid_dev, int64_t max_rows,
+                       const uint32_t *bad, cudaStream_t st) {
     if (!s || !edge_dev || !indptr_dev || B < 0 || (arity != 2 && arity != 3)) return fail(SUBG_ERR_ARG, "Input parsing error.");
     if (B > 0 && !out_dev) return fail(SUBG_ERR_ARG, "null output");
     if (enc_table_dev && (s->value_kind != 0 || k < 1)) return fail(SUBG_ERR_ARG, "table lookup needs an int SpG and k >= 1");
@@ -395,6 +408,7 @@ int spjoin_run_impl(const SpG *s, const int64_t *edge_dev, int64_t B, int arity,
     p.edge = (const long long *)edge_dev; p.B = B; p.arity = arity; p.seg_ptr = (const long long *)indptr_dev;
     p.enc = enc_table_dev; p.k = k; p.out = out_dev; p.segid = (long long *)segid_dev;
     p.ntask = arity == 2 ? B : 2 * B;
+    p.max_rows = max_rows; p.bad = bad;
     cudaError_t e;
     timing_begin(SUBG_TIMING_SPJOIN, st);
     if (s->value_kind == 1) e = launch_join<double, 2>(s, p, st);
@@ -413,6 +427,53 @@ int spjoin_run_impl(const SpG *s, const int64_t *edge_dev, int64_t B, int arity,
     timing_end(SUBG_TIMING_SPJOIN, st);
     count_launch(1);
     if (e != cudaSuccess) return fail(SUBG_ERR_CUDA, cudaGetErrorString(e));
+    return SUBG_OK;
+}
+
+int spjoin_run_impl(const SpG *s, const int64_t *edge_dev, int64_t B, int arity, const int64_t *indptr_dev,
+                    const float *enc_table_dev, int k, void *out_dev, int64_t *segid_dev, cudaStream_t st) {
+    return join_launch(s, edge_dev, B, arity, indptr_dev, enc_table_dev, k, out_dev, segid_dev, -1, nullptr, st);
+}
+
+// plan + run with ONE host synchronisation: sizes, scan and the join kernel are queued back to back; the kernel
+// checks on the device that the rows fit `out_capacity`.  *ran = 0 -> nothing was written (call run with a buffer of
+// *N_out rows; edge_dev / indptr_dev are already filled).
+int spjoin_fused_impl(const SpG *s, const int64_t *edge_hd, int64_t B, int arity, int64_t *edge_dev, int64_t *indptr_dev,
+                      const float *enc_table_dev, int k, void *out_dev, int64_t out_capacity, int64_t *segid_dev,
+                      int64_t *N_out, int *ran, cudaStream_t st) {
+    if (!s || !edge_hd || !edge_dev || !indptr_dev || !N_out || !ran || B < 0 || out_capacity < 0 || (arity != 2 && arity != 3))
+        return fail(SUBG_ERR_ARG, "Input parsing error.");
+    DeviceGuard guard(s->device);
+    const int64_t nseg = (arity == 2 ? 2 : 4) * B;
+    if (edge_dev != edge_hd)
+        SUBG_CUDA(cudaMemcpyAsync(edge_dev, edge_hd, (size_t)arity * B * sizeof(int64_t), cudaMemcpyDefault, st));
+    int32_t *sizes = nullptr;
+    long long *scratch = nullptr;
+    uint32_t *bad = nullptr;
+    SUBG_CUDA(dmalloc(&sizes, (size_t)nseg, st));
+    SUBG_CUDA(dmalloc(&scratch, (size_t)std::max(1, scan_num_blocks(nseg)), st));
+    SUBG_CUDA(dmalloc(&bad, 1, st));
+    SUBG_CUDA(cudaMemsetAsync(bad, 0, sizeof(uint32_t), st));
+    if (nseg > 0) {
+        const unsigned blocks = (unsigned)std::min<int64_t>((nseg + 255) / 256, 4 * (int64_t)s->num_sms);
+        join_sizes_kernel<<<blocks, 256, 0, st>>>((const long long *)s->rowbeg, s->indptr ? nullptr : s->nsize, s->n,
+                                                  (const long long *)edge_dev, B, arity, sizes, bad);
+    }
+    SUBG_CUDA(exclusive_scan_i32_i64(sizes, (long long *)indptr_dev, nseg, 0, scratch, st));
+    count_launch(4);
+    int rc = SUBG_OK;
+    if (B > 0 && out_dev)
+        rc = join_launch(s, edge_dev, B, arity, indptr_dev, enc_table_dev, k, out_dev, segid_dev, out_capacity, bad, st);
+    long long N = 0;
+    uint32_t hbad = 0;
+    SUBG_CUDA(cudaMemcpyAsync(&N, indptr_dev + nseg, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    SUBG_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SUBG_CUDA(cudaStreamSynchronize(st));
+    dfree(sizes, st); dfree(scratch, st); dfree(bad, st);
+    if (rc != SUBG_OK) return rc;
+    if (hbad) return fail(SUBG_ERR_ARG, "query node id outside the SpG");
+    *N_out = N;
+    *ran = (B > 0 && out_dev && N <= out_capacity) || N == 0 ? 1 : 0;
     return SUBG_OK;
 }
 

@@ -137,6 +137,53 @@ class DeviceGraph:
     def from_scipy(cls, G, device="cuda"):
         return cls(G.indptr, G.indices, device)
 
+    @classmethod
+    def from_edges(cls, row, col, num_nodes=None, symmetrize=False, drop_self_loops=False, device="cuda"):
+        """Edge list -> CSR on the device: duplicates coalesced, columns ascending, as scipy's
+        csr_matrix((ones, (row, col))) in edge2csr (subg_acc/test/test.py:15-19); symmetrize=True also
+        stores every edge reversed (dataloader.py:119-129).  row / col: int64 numpy arrays or torch tensors
+        (host or device)."""
+        self = cls.__new__(cls)
+        self._lib = _capi.load()
+        if isinstance(row, torch.Tensor):
+            row, col = row.to(torch.int64).contiguous(), col.to(torch.int64).contiguous()
+            E = row.numel()
+            if row.is_cuda:
+                device = row.device
+        else:
+            row = np.ascontiguousarray(np.asarray(row), dtype=np.int64)
+            col = np.ascontiguousarray(np.asarray(col), dtype=np.int64)
+            E = row.size
+        if (col.numel() if isinstance(col, torch.Tensor) else col.size) != E:
+            raise TypeError("row and col must have the same length")
+        self.device = _dev_index(device)
+        self._h = C.c_void_p()
+        self._keep = None
+        _capi.check(self._lib.subg_graph_from_edges(_ptr(row), _ptr(col), E, -1 if num_nodes is None else int(num_nodes),
+                                                    int(bool(symmetrize)), int(bool(drop_self_loops)), self.device,
+                                                    _stream(self.device), C.byref(self._h)))
+        N, Ecount = C.c_int64(), C.c_int64()
+        _capi.check(self._lib.subg_graph_info(self._h, C.byref(N), C.byref(Ecount), None))
+        self.N, self.E = N.value, Ecount.value
+        return self
+
+    def csr(self, device=None):
+        """(indptr int64[N+1], indices int32[E]) of the resident graph: numpy arrays, or torch tensors
+        on `device` when given."""
+        if device is None:
+            indptr, indices = np.empty(self.N + 1, np.int64), np.empty(self.E, np.int32)
+        else:
+            indptr = torch.empty(self.N + 1, dtype=torch.int64, device=device)
+            indices = torch.empty(self.E, dtype=torch.int32, device=device)
+        _capi.check(self._lib.subg_graph_export(self._h, _ptr(indptr), _ptr(indices), _stream(self.device)))
+        return indptr, indices
+
+    def to_scipy(self):
+        """Boolean scipy CSR of the resident graph (what edge2csr returns, test.py:17-19)."""
+        import scipy.sparse as sp
+        indptr, indices = self.csr()
+        return sp.csr_matrix((np.ones(self.E, dtype=bool), indices, indptr), shape=(self.N, self.N))
+
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
             self._lib.subg_graph_free(self._h)
@@ -268,6 +315,21 @@ class SpG:
             return _view(p[1].value, (self.n,), "<i4", self.device, self).clone()
         rb = _view(p[0].value, (self.n + 1,), "<i8", self.device, self)
         return (rb[1:] - rb[:-1]).to(torch.int32)
+
+    def rows(self) -> dict:
+        """Zero-copy torch views of the layout SpJoin reads, without compaction: row u = entries
+        [rowbeg[u], rowbeg[u] + nsize[u]) of indices / data (sampler-built SpGs are "scattered": rows are
+        16-byte aligned and in completion order).  Invalidated by views() / to_scipy(), which compact."""
+        p = [C.c_void_p() for _ in range(4)]
+        ext = C.c_int64()
+        _capi.check(self._lib.subg_spg_rows(self._h, *[C.byref(x) for x in p], C.byref(ext)))
+        d = self.device
+        compact = not p[1].value
+        rb = _view(p[0].value, (self.n + 1 if compact else self.n,), "<i8", d, self)
+        nsize = (rb[1:] - rb[:-1]).to(torch.int32) if compact else _view(p[1].value, (self.n,), "<i4", d, self)
+        return {"rowbeg": rb[:self.n], "nsize": nsize,
+                "indices": _view(p[2].value, (ext.value,), "<i4", d, self),
+                "data": _view(p[3].value, (ext.value,), "<f8" if self.value_kind else "<i4", d, self)}
 
     def export_reference(self, want_raw: bool = False):
         """[nsize, remap, enc(, raw_enc)] exactly as gset_sampler returns them

@@ -50,6 +50,9 @@ def _edge_arg(edge, arity: int):
 
 
 def _join(edge, x, device, arity, encode=None, want_segid=False, want_ptr=True):
+    """One SpJoin batch.  The output is sized from the rows-per-segment seen on this SpG so far (+25 %), so
+    that sizes, scan and join run back to back with a single host synchronisation (subg_spjoin); the first
+    batch, and a batch that outgrows the estimate, take the two-step plan / run route with an exact buffer."""
     spg = _as_spg(x, device)
     lib = _capi.load()
     dev = spg.device
@@ -58,28 +61,45 @@ def _join(edge, x, device, arity, encode=None, want_segid=False, want_ptr=True):
     nseg = (2 if arity == 2 else 4) * B
     edge_dev = keep if on_dev else torch.empty((arity, B), dtype=torch.int64, device=tdev)
     indptr = torch.empty(nseg + 1, dtype=torch.int64, device=tdev)
-    N = C.c_int64(0)
     st = _stream(dev)
-    _capi.check(lib.subg_spjoin_plan(spg._h, eptr, B, arity, edge_dev.data_ptr(), indptr.data_ptr(), C.byref(N), st))
-    N = N.value
     table = None
     if spg.value_kind == 1:
         if encode is not None:
             raise TypeError("a value SpG (PPR/SPD) is joined without an LP table")
-        out = torch.empty((N, 2), dtype=torch.float32, device=tdev)
-        k = 0
+        shape_tail, dtype, k = (2,), torch.float32, 0
     elif encode is not None:
         table = encode if (isinstance(encode, torch.Tensor) and encode.is_cuda and encode.dtype == torch.float32
                            and encode.is_contiguous()) else torch.as_tensor(encode, dtype=torch.float32, device=tdev).contiguous()
         k = table.shape[1]
-        out = torch.empty((N, 2, k), dtype=torch.float32, device=tdev)
+        shape_tail, dtype = (2, k), torch.float32
     else:
-        out = torch.empty((N, 2), dtype=torch.int32, device=tdev)
-        k = 0
-    segid = torch.empty(N, dtype=torch.int64, device=tdev) if want_segid else None
-    _capi.check(lib.subg_spjoin_run(spg._h, edge_dev.data_ptr(), B, arity, indptr.data_ptr(),
-                                    table.data_ptr() if table is not None else None, k, out.data_ptr(),
-                                    segid.data_ptr() if segid is not None else None, st))
+        shape_tail, dtype, k = (2,), torch.int32, 0
+    tptr = table.data_ptr() if table is not None else None
+    N = C.c_int64(0)
+    rate = getattr(spg, "_rows_per_seg", None)
+    out = segid = None
+    if rate is not None and nseg > 0:
+        cap = int(rate * nseg * 1.25) + 1024
+        out = torch.empty((cap,) + shape_tail, dtype=dtype, device=tdev)
+        segid = torch.empty(cap, dtype=torch.int64, device=tdev) if want_segid else None
+        ran = C.c_int(0)
+        _capi.check(lib.subg_spjoin(spg._h, eptr, B, arity, edge_dev.data_ptr(), indptr.data_ptr(), tptr, k, out.data_ptr(),
+                                    cap, segid.data_ptr() if segid is not None else None, C.byref(N), C.byref(ran), st))
+        if ran.value:
+            out = out[:N.value]
+            segid = segid[:N.value] if segid is not None else None
+        else:
+            out = segid = None
+    else:
+        _capi.check(lib.subg_spjoin_plan(spg._h, eptr, B, arity, edge_dev.data_ptr(), indptr.data_ptr(), C.byref(N), st))
+    N = N.value
+    if nseg > 0:
+        spg._rows_per_seg = max(rate or 0.0, N / nseg)
+    if out is None:
+        out = torch.empty((N,) + shape_tail, dtype=dtype, device=tdev)
+        segid = torch.empty(N, dtype=torch.int64, device=tdev) if want_segid else None
+        _capi.check(lib.subg_spjoin_run(spg._h, edge_dev.data_ptr(), B, arity, indptr.data_ptr(), tptr, k, out.data_ptr(),
+                                        segid.data_ptr() if segid is not None else None, st))
     return out, indptr, segid
 
 
