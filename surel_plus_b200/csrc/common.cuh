@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <chrono>
 #include <string>
 
 #include "../../include/subg_b200.h"
@@ -45,6 +47,24 @@ struct DeviceGuard {
 };
 
 bool is_device_ptr(const void *p);
+
+// host-side phase timer (SUBG_PROFILE_HOST=1): where does a sampling call spend wall-clock besides its kernels?
+struct HostProf {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    std::string log;
+    HostProf() : on(getenv("SUBG_PROFILE_HOST") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *what) {
+        if (!on) return;
+        const auto t = std::chrono::steady_clock::now();
+        char buf[96];
+        snprintf(buf, sizeof(buf), " %s=%.3f", what, std::chrono::duration<double, std::milli>(t - t0).count());
+        log += buf;
+        t0 = t;
+    }
+    ~HostProf() { if (on) fprintf(stderr, "[subg host ms]%s\n", log.c_str()); }
+};
+
 
 // measurement hooks (capi.cu)
 void count_launch(int n = 1);
@@ -99,6 +119,11 @@ struct SpG {
     int32_t *seeds = nullptr;    // [n] node id of each row
     int64_t pushes = 0;          // PPR sampler: forward pushes performed (measurement)
     int num_sms = 148;
+    // per-handle SpJoin scratch, kept between batches (handles are not thread-safe)
+    mutable int32_t *join_sizes = nullptr;   // [join_cap] segment sizes
+    mutable int64_t join_cap = 0;
+    mutable long long *join_tot = nullptr;   // device {total rows, bad-node flag}
+    mutable long long *join_host = nullptr;  // pinned copy of join_tot
 };
 
 void spg_free_impl(SpG *s);

@@ -65,7 +65,8 @@ struct SamplerArgs {
     int32_t *max_set;
     int want_rank;
     int blocks_per_sm;         // 0 = as many as fit; otherwise a cap (fewer blocks leave more of the SM's 228 KB to L1)
-    int stop_after;            // measurement only (SUBG_SAMPLER_STOP): 1 = walks, 2 = + sort, 3 = + counts; 0 = full kernel
+    int stop_after;            // measurement only (SUBG_SAMPLER_STOP): 1 = walks, 2 = + sort, 3 = + counts, 4 = all but the LP-row lookups,
+                               // 5 = all but the row stores; 0 = full kernel
     // LP-key intern table (global, L2 resident)
     unsigned long long *tab_key;
     unsigned long long *tab_pos;
@@ -588,7 +589,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
                 h[q] = lp_hash(lp[q]) & a.tab_mask;
                 cur[q] = kEmptyKey;
                 seen[q] = 0ull;
-                if (keep[q]) {
+                if (keep[q] && a.stop_after != 4) {
                     cur[q] = a.tab_key[h[q]];
                     seen[q] = a.tab_pos[h[q]];
                 }
@@ -596,10 +597,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
 #pragma unroll
             for (int q = 0; q < 2; q++) {
                 if (keep[q]) {
-                    const uint32_t prov = intern_key(a, lp[q], ((unsigned long long)gi << 16) | ord[q], h[q], cur[q], seen[q]);
-                    a.out_node[base + o[q]] = (int32_t)(kk[q] >> OB);
-                    a.out_prov[base + o[q]] = (int32_t)prov;
-                    if (a.out_slot) a.out_slot[base + o[q]] = (uint16_t)rank[q];
+                    // measurement knobs: stop_after 4 = no LP-row lookups, 5 = lookups but no row stores (results invalid)
+                    const uint32_t prov = a.stop_after == 4 ? h[q]
+                                                            : intern_key(a, lp[q], ((unsigned long long)gi << 16) | ord[q], h[q], cur[q], seen[q]);
+                    if (a.stop_after != 5) {
+                        a.out_node[base + o[q]] = (int32_t)(kk[q] >> OB);
+                        a.out_prov[base + o[q]] = (int32_t)prov;
+                        if (a.out_slot) a.out_slot[base + o[q]] = (uint16_t)rank[q];
+                    } else if (prov == 0xffffffffu) {
+                        a.out_prov[base] = 0;  // keeps the lookup alive
+                    }
                 }
             }
         }

@@ -45,23 +45,6 @@ static int ceil_log2(uint64_t x) {
     while ((1ull << b) < x) b++;
     return b;
 }
-// host-side phase timer (SUBG_PROFILE_HOST=1): where does a sampling call spend wall-clock besides its kernels?
-struct HostProf {
-    bool on;
-    std::chrono::steady_clock::time_point t0;
-    std::string log;
-    HostProf() : on(getenv("SUBG_PROFILE_HOST") != nullptr), t0(std::chrono::steady_clock::now()) {}
-    void mark(const char *what) {
-        if (!on) return;
-        const auto t = std::chrono::steady_clock::now();
-        char buf[96];
-        snprintf(buf, sizeof(buf), " %s=%.3f", what, std::chrono::duration<double, std::milli>(t - t0).count());
-        log += buf;
-        t0 = t;
-    }
-    ~HostProf() { if (on) fprintf(stderr, "[subg host ms]%s\n", log.c_str()); }
-};
-
 static int64_t env_i64(const char *name, int64_t dflt) {
     const char *v = getenv(name);
     return v ? atoll(v) : dflt;
@@ -532,7 +515,7 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
                 CK(cudaMallocAsync(&cub_tmp, tmp_bytes ? tmp_bytes : 1, st));
                 CK(cub::DeviceRadixSort::SortPairs(cub_tmp, tmp_bytes, u_pos, u_pos2, u_slot, u_slot2, (int)c, 0, 64, st));
                 finalize_unique_kernel<<<(c + 255) / 256, 256, 0, st>>>(u_slot2, c, tab_key, M, m, pl.SHIFT, rank_of_slot, s->enc);
-                if (extent > 0) {
+                if (extent > 0 && env_i64("SUBG_SAMPLER_STOP", 0) == 0) {  // a truncated measurement run leaves no valid rows
                     const int64_t rb = std::min<int64_t>((extent + 1023) / 1024, 16 * (int64_t)g->num_sms);
                     remap_ids_kernel<<<(unsigned)rb, 256, 0, st>>>((int32_t *)s->data, extent, rank_of_slot);
                 }
@@ -706,6 +689,9 @@ void spg_free_impl(SpG *s) {
     if (!s) return;
     DeviceGuard guard(s->device);
     free_spg_arrays(s, 0);
+    dfree(s->join_sizes, 0);
+    dfree(s->join_tot, 0);
+    if (s->join_host) cudaFreeHost(s->join_host);
     delete s;
 }
 

@@ -41,13 +41,12 @@ struct JoinArgs {
     // fused plan + run (subg_spjoin): the kernel runs right behind the plan, without the host having seen the row
     // count; it backs out when the rows do not fit the caller's buffer or a query node is out of range
     int64_t max_rows;          // < 0: no check
-    const uint32_t *bad;       // nullable
+    const long long *tot;      // {total rows, bad-node flag} written by the plan kernel (fused mode)
 };
 
 __device__ __forceinline__ bool join_must_skip(const JoinArgs &p) {
     if (p.max_rows < 0) return false;
-    const int64_t nseg = (p.arity == 2 ? 2 : 4) * p.B;
-    return p.seg_ptr[nseg] > p.max_rows || (p.bad && *p.bad);
+    return p.tot[0] > p.max_rows || p.tot[1] != 0;
 }
 
 __device__ __forceinline__ int row_size(const JoinArgs &p, int64_t u) {
@@ -90,6 +89,78 @@ __global__ void join_sizes_kernel(const long long *rowbeg, const int32_t *nsize,
             sizes[g] = nsize ? nsize[node] : (int32_t)(rowbeg[node + 1] - rowbeg[node]);
         }
     }
+}
+
+// Plan of a batch in two launches (segments <= kPlanSmallMax = 1024 tiles of 256): (1) sizes of every segment and the
+// tile sums; the last tile to finish scans the tile sums and publishes the total and the bad-node flag; (2) every
+// tile rescans its 256 sizes behind its offset -> segment pointers.
+constexpr int kPlanTile = 256;
+constexpr int kPlanSmallMax = 1024 * kPlanTile;
+__global__ void __launch_bounds__(kPlanTile) join_plan_sizes_kernel(const long long *rowbeg, const int32_t *nsize, int64_t n_rows,
+                                                                   const long long *edge, int64_t B, int arity, int32_t *sizes,
+                                                                   long long *tile_off, unsigned int *done, long long *tot) {
+    __shared__ long long ws[32];
+    __shared__ bool last;
+    const int nseg = (int)(arity == 2 ? 2 * B : 4 * B);
+    const int g = blockIdx.x * kPlanTile + threadIdx.x;
+    int32_t sz = 0;
+    bool bad = false;
+    if (g < nseg) {
+        long long node;
+        if (arity == 2) node = edge[g];
+        else {
+            const int blk = g / (int)B, q = g - blk * (int)B;
+            node = edge[(int64_t)(blk == 0 ? 0 : (blk == 2 ? 1 : 2)) * B + q];  // u, w, v, w
+        }
+        if (node < 0 || node >= n_rows) bad = true;
+        else sz = nsize ? nsize[node] : (int32_t)(rowbeg[node + 1] - rowbeg[node]);
+        sizes[g] = sz;
+    }
+    long long total;
+    block_excl_scan((long long)sz, &total, ws);
+    const int any_bad = __syncthreads_or(bad ? 1 : 0);
+    if (threadIdx.x == 0) {
+        tile_off[blockIdx.x] = total;
+        if (any_bad) atomicExch((unsigned long long *)&tot[1], 1ull);
+        __threadfence();
+        last = atomicAdd(done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    // exclusive scan of the tile sums (<= 1024) by this block: 4 consecutive tiles per thread
+    const int nt = gridDim.x;
+    long long v[4], sum = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int t = threadIdx.x * 4 + q;
+        v[q] = t < nt ? ((volatile long long *)tile_off)[t] : 0;
+        sum += v[q];
+    }
+    long long ex = block_excl_scan(sum, &total, ws);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int t = threadIdx.x * 4 + q;
+        if (t < nt) tile_off[t] = ex;
+        ex += v[q];
+    }
+    if (threadIdx.x == 0) {
+        tot[0] = total;
+        *done = 0u;  // ready for the next batch
+    }
+}
+__global__ void __launch_bounds__(kPlanTile) join_plan_offsets_kernel(const int32_t *sizes, const long long *tile_off, int nseg,
+                                                                     long long *seg_ptr, const long long *tot) {
+    __shared__ long long ws[32];
+    const int g = blockIdx.x * kPlanTile + threadIdx.x;
+    const int32_t sz = g < nseg ? sizes[g] : 0;
+    const long long ex = block_excl_scan((long long)sz, nullptr, ws) + tile_off[blockIdx.x];
+    if (g < nseg) seg_ptr[g] = ex;
+    if (g == nseg - 1) seg_ptr[nseg] = tot[0];
+}
+__global__ void join_tot_kernel(const long long *seg_ptr, int64_t nseg, const uint32_t *bad, long long *tot) {
+    tot[0] = seg_ptr[nseg];
+    tot[1] = *bad;
 }
 
 // ------------------------------------------------------------------ TMA / mbarrier PTX
@@ -375,18 +446,29 @@ int spjoin_plan_impl(const SpG *s, const int64_t *edge_hd, int64_t B, int arity,
 template <typename V, int MODE, int KK = 0>
 static cudaError_t launch_join(const SpG *s, JoinArgs &p, cudaStream_t st) {
     if (p.ntask <= 0) return cudaSuccess;
-    int dev_smem = 0;
-    cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device);
+    static thread_local int c_smem_dev = -1, dev_smem = 0;
+    if (c_smem_dev != s->device) {
+        cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device);
+        c_smem_dev = s->device;
+    }
     const int cap = ((s->max_set + 3) & ~3) + 8;
     const size_t smem = (size_t)cap * (8 + 4 * sizeof(V)) + 128;
     if ((int64_t)smem <= std::min<int64_t>(dev_smem - 1024, 96 * 1024)) {
         p.cap = cap;
         auto kern = spjoin_kernel<V, MODE, KK>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kJoinThreads, smem);
-        if (e != cudaSuccess) return e;
+        // attribute + occupancy query once per (kernel, device, shared-memory size): they cost more than the launch
+        static thread_local int c_dev = -1, c_per_sm = 0;
+        static thread_local size_t c_smem = 0;
+        cudaError_t e;
+        if (c_dev != s->device || c_smem != smem) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c_per_sm, kern, kJoinThreads, smem);
+            if (e != cudaSuccess) return e;
+            c_dev = s->device;
+            c_smem = smem;
+        }
+        const int per_sm = c_per_sm;
         const int64_t blocks = std::min<int64_t>(p.ntask, (int64_t)s->num_sms * std::max(per_sm, 1));
         kern<<<(unsigned)blocks, kJoinThreads, smem, st>>>(p);
     } else {
@@ -398,7 +480,7 @@ static cudaError_t launch_join(const SpG *s, JoinArgs &p, cudaStream_t st) {
 
 static int join_launch(const SpG *s, const int64_t *edge_dev, int64_t B, int arity, const int64_t *indptr_dev,
                        const float *enc_table_dev, int k, void *out_dev, int64_t *segid_dev, int64_t max_rows,
-                       const uint32_t *bad, cudaStream_t st) {
+                       const long long *tot, cudaStream_t st) {
     if (!s || !edge_dev || !indptr_dev || B < 0 || (arity != 2 && arity != 3)) return fail(SUBG_ERR_ARG, "Input parsing error.");
     if (B > 0 && !out_dev) return fail(SUBG_ERR_ARG, "null output");
     if (enc_table_dev && (s->value_kind != 0 || k < 1)) return fail(SUBG_ERR_ARG, "table lookup needs an int SpG and k >= 1");
@@ -408,7 +490,7 @@ static int join_launch(const SpG *s, const int64_t *edge_dev, int64_t B, int ari
     p.edge = (const long long *)edge_dev; p.B = B; p.arity = arity; p.seg_ptr = (const long long *)indptr_dev;
     p.enc = enc_table_dev; p.k = k; p.out = out_dev; p.segid = (long long *)segid_dev;
     p.ntask = arity == 2 ? B : 2 * B;
-    p.max_rows = max_rows; p.bad = bad;
+    p.max_rows = max_rows; p.tot = tot;
     cudaError_t e;
     timing_begin(SUBG_TIMING_SPJOIN, st);
     if (s->value_kind == 1) e = launch_join<double, 2>(s, p, st);
@@ -435,45 +517,73 @@ int spjoin_run_impl(const SpG *s, const int64_t *edge_dev, int64_t B, int arity,
     return join_launch(s, edge_dev, B, arity, indptr_dev, enc_table_dev, k, out_dev, segid_dev, -1, nullptr, st);
 }
 
-// plan + run with ONE host synchronisation: sizes, scan and the join kernel are queued back to back; the kernel
-// checks on the device that the rows fit `out_capacity`.  *ran = 0 -> nothing was written (call run with a buffer of
-// *N_out rows; edge_dev / indptr_dev are already filled).
+// plan + run with ONE host synchronisation: the plan kernel(s) and the join kernel are queued back to back; the join
+// kernel checks on the device that the rows fit `out_capacity`.  *ran = 0 -> nothing was written (call run with a
+// buffer of *N_out rows; edge_dev / indptr_dev are already filled).  Scratch lives on the SpG handle between batches.
 int spjoin_fused_impl(const SpG *s, const int64_t *edge_hd, int64_t B, int arity, int64_t *edge_dev, int64_t *indptr_dev,
                       const float *enc_table_dev, int k, void *out_dev, int64_t out_capacity, int64_t *segid_dev,
                       int64_t *N_out, int *ran, cudaStream_t st) {
     if (!s || !edge_hd || !edge_dev || !indptr_dev || !N_out || !ran || B < 0 || out_capacity < 0 || (arity != 2 && arity != 3))
         return fail(SUBG_ERR_ARG, "Input parsing error.");
     DeviceGuard guard(s->device);
+    HostProf prof;
     const int64_t nseg = (arity == 2 ? 2 : 4) * B;
     if (edge_dev != edge_hd)
         SUBG_CUDA(cudaMemcpyAsync(edge_dev, edge_hd, (size_t)arity * B * sizeof(int64_t), cudaMemcpyDefault, st));
-    int32_t *sizes = nullptr;
-    long long *scratch = nullptr;
-    uint32_t *bad = nullptr;
-    SUBG_CUDA(dmalloc(&sizes, (size_t)nseg, st));
-    SUBG_CUDA(dmalloc(&scratch, (size_t)std::max(1, scan_num_blocks(nseg)), st));
-    SUBG_CUDA(dmalloc(&bad, 1, st));
-    SUBG_CUDA(cudaMemsetAsync(bad, 0, sizeof(uint32_t), st));
-    if (nseg > 0) {
+    if (s->join_cap < nseg + 1 || !s->join_tot) {
+        dfree(s->join_sizes, st);
+        s->join_sizes = nullptr;
+        s->join_cap = 0;
+        SUBG_CUDA(dmalloc(&s->join_sizes, (size_t)nseg + 1, st));
+        s->join_cap = nseg + 1;
+        if (!s->join_tot) {  // [0] total rows  [1] bad-node flag  [2] flag word of the large path  [3] tile counter  [8..] tile sums
+            SUBG_CUDA(dmalloc(&s->join_tot, 8 + 1024, st));
+            SUBG_CUDA(cudaMemsetAsync(s->join_tot, 0, (8 + 1024) * sizeof(long long), st));
+        }
+        if (!s->join_host) SUBG_CUDA(cudaHostAlloc((void **)&s->join_host, 4 * sizeof(long long), cudaHostAllocDefault));
+    }
+    prof.mark("scratch");
+    SUBG_CUDA(cudaMemsetAsync(s->join_tot, 0, 2 * sizeof(long long), st));
+    if (nseg <= kPlanSmallMax) {
+        const int tiles = (int)((nseg + kPlanTile - 1) / kPlanTile);
+        if (tiles > 0) {
+            long long *tile_off = s->join_tot + 8;
+            join_plan_sizes_kernel<<<tiles, kPlanTile, 0, st>>>((const long long *)s->rowbeg, s->indptr ? nullptr : s->nsize, s->n,
+                                                                (const long long *)edge_dev, B, arity, s->join_sizes, tile_off,
+                                                                (unsigned int *)(s->join_tot + 3), s->join_tot);
+            join_plan_offsets_kernel<<<tiles, kPlanTile, 0, st>>>(s->join_sizes, tile_off, (int)nseg, (long long *)indptr_dev,
+                                                                  s->join_tot);
+            count_launch(2);
+        } else {
+            SUBG_CUDA(cudaMemsetAsync(indptr_dev, 0, sizeof(long long), st));
+        }
+    } else {
+        long long *scratch = nullptr;
+        uint32_t *bad = (uint32_t *)(s->join_tot + 2);
+        SUBG_CUDA(dmalloc(&scratch, (size_t)std::max(1, scan_num_blocks(nseg)), st));
+        SUBG_CUDA(cudaMemsetAsync(bad, 0, sizeof(uint32_t), st));
         const unsigned blocks = (unsigned)std::min<int64_t>((nseg + 255) / 256, 4 * (int64_t)s->num_sms);
         join_sizes_kernel<<<blocks, 256, 0, st>>>((const long long *)s->rowbeg, s->indptr ? nullptr : s->nsize, s->n,
-                                                  (const long long *)edge_dev, B, arity, sizes, bad);
+                                                  (const long long *)edge_dev, B, arity, s->join_sizes, bad);
+        SUBG_CUDA(exclusive_scan_i32_i64(s->join_sizes, (long long *)indptr_dev, nseg, 0, scratch, st));
+        join_tot_kernel<<<1, 1, 0, st>>>((const long long *)indptr_dev, nseg, bad, s->join_tot);
+        dfree(scratch, st);
+        count_launch(5);
     }
-    SUBG_CUDA(exclusive_scan_i32_i64(sizes, (long long *)indptr_dev, nseg, 0, scratch, st));
-    count_launch(4);
+    SUBG_CUDA(cudaGetLastError());
+    prof.mark("plan");
     int rc = SUBG_OK;
     if (B > 0 && out_dev)
-        rc = join_launch(s, edge_dev, B, arity, indptr_dev, enc_table_dev, k, out_dev, segid_dev, out_capacity, bad, st);
-    long long N = 0;
-    uint32_t hbad = 0;
-    SUBG_CUDA(cudaMemcpyAsync(&N, indptr_dev + nseg, sizeof(long long), cudaMemcpyDeviceToHost, st));
-    SUBG_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        rc = join_launch(s, edge_dev, B, arity, indptr_dev, enc_table_dev, k, out_dev, segid_dev, out_capacity, s->join_tot, st);
+    prof.mark("join");
+    SUBG_CUDA(cudaMemcpyAsync(s->join_host, s->join_tot, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st));
     SUBG_CUDA(cudaStreamSynchronize(st));
-    dfree(sizes, st); dfree(scratch, st); dfree(bad, st);
+    prof.mark("sync");
     if (rc != SUBG_OK) return rc;
-    if (hbad) return fail(SUBG_ERR_ARG, "query node id outside the SpG");
+    if (s->join_host[1]) return fail(SUBG_ERR_ARG, "query node id outside the SpG");
+    const long long N = s->join_host[0];
     *N_out = N;
-    *ran = (B > 0 && out_dev && N <= out_capacity) || N == 0 ? 1 : 0;
+    *ran = ((B > 0 && out_dev && N <= out_capacity) || N == 0) ? 1 : 0;
     return SUBG_OK;
 }
 

@@ -167,6 +167,8 @@ def sharded_sample(graph, query, num_walks=100, num_steps=3, bucket=-1, seed=111
                                            _stream(graph.device), C.byref(h)))
     shard = SpG(h, graph.device, n_nodes=graph.N, num_walks=num_walks)
     v = shard.views()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
 
     def relabel(id_map: np.ndarray, merged: np.ndarray) -> torch.Tensor:
         m = np.ascontiguousarray(merged, dtype=np.int16)
@@ -182,7 +184,9 @@ def sharded_sample(graph, query, num_walks=100, num_steps=3, bucket=-1, seed=111
     shard.close()
     full = SpG.from_device_csr(parts["indptr"], parts["indices"], parts["data"], n_nodes=graph.N, enc=parts["enc"],
                                num_walks=num_walks, status=status)
+    ev[1].record()
     full.exchange_bytes = parts["bytes_gathered"]
+    full.exchange_events = ev   # elapsed = LP-table merge + all-gathers + CSR assembly (device time)
     return full
 
 
