@@ -309,12 +309,15 @@ def run_ours(args):
     # full SpG.  Reported beside the weak-scaling headline; strong scaling of one sampling pass.
     sharded = None
     if world > 1:
-        from surel_plus_b200.parallel import sharded_sample
+        from surel_plus_b200.parallel import partition_by_work, sharded_sample
+        # contiguous seed ranges balanced by a degree-based estimate of the set size (the synthetic generator puts
+        # the hubs at the low ids; equal-count ranges would leave rank 0 with the largest sets)
+        bounds = partition_by_work(300.0 + 1.5 * np.minimum(deg, M), world)
         spg.close()
         spg = None
         torch.cuda.empty_cache()
         for i in range(2):
-            sharded_sample(graph, query, num_walks=M, num_steps=m, seed=base_seed + i).close()
+            sharded_sample(graph, query, num_walks=M, num_steps=m, seed=base_seed + i, bounds=bounds).close()
         barrier()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = max(2, min(args.steps, 5))
@@ -322,7 +325,7 @@ def run_ours(args):
         for i in range(reps):
             if spg is not None:
                 spg.close()
-            spg = sharded_sample(graph, query, num_walks=M, num_steps=m, seed=111413 + i)
+            spg = sharded_sample(graph, query, num_walks=M, num_steps=m, seed=111413 + i, bounds=bounds)
         s1.record()
         barrier()
         sh_ms = max_over_ranks(s0.elapsed_time(s1)) / reps

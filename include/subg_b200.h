@@ -153,6 +153,12 @@ int subg_spg_rows(const subg_spg *s, const int64_t **rowbeg, const int32_t **nsi
 int subg_spg_from_csr(const int64_t *indptr_hd, const int32_t *indices_hd, const void *data_hd,
                       int value_kind, int64_t n_rows, int64_t nnz, int device, void *stream,
                       subg_spg **out);
+/* Multi-GPU assembly: an empty LP SpG in the CSR layout whose arrays are filled in place -- the
+ * all-gather writes the shards of every rank straight into nsize int32[n], indices int32[T], data int32[T]
+ * (pointers from subg_spg_views; indptr is derived by subg_spg_seal, which also finds the largest set and
+ * checks that the sizes add up to T).  The LP table is attached with subg_spg_set_lp_table(id_map NULL). */
+int subg_spg_alloc(int64_t n, int64_t T, int device, void *stream, subg_spg **out);
+int subg_spg_seal(subg_spg *s, void *stream);
 void subg_spg_free(subg_spg *s);
 
 /* ---- SpJoin -------------------------------------------------------------------

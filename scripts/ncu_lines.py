@@ -38,6 +38,50 @@ def main():
     print("# --- by stall samples")
     for inst, samp, f, ln, src in sorted(lines, key=lambda l: -l[1])[:top]:
         print(f"{100 * inst / ti:5.1f}% inst {100 * samp / ts:5.1f}% samp  {f}:{ln:>4s}  {src[:110]}")
+    phases = sampler_phases()
+    if phases and any(l[2] == "sampler.cuh" for l in lines):
+        print("# --- sampler kernel by phase (source-line ranges of csrc/sampler.cuh, common.cuh = Philox / rand_r)")
+        agg = {}
+        for inst, samp, f, ln, _ in lines:
+            name = "rng (common.cuh)" if f == "common.cuh" else "other"
+            if f == "sampler.cuh":
+                n = int(ln)
+                name = next((ph for ph, lo, hi in phases if lo <= n < hi), "other")
+            a = agg.setdefault(name, [0, 0])
+            a[0] += inst
+            a[1] += samp
+        for name, (inst, samp) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+            print(f"{100 * inst / ti:5.1f}% inst {100 * samp / ts:5.1f}% samp  {name}")
+
+
+def sampler_phases():
+    """[(phase, first line, one past last line)] from anchor strings in csrc/sampler.cuh."""
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "surel_plus_b200", "csrc", "sampler.cuh")
+    try:
+        src = open(path).read().split("\n")
+    except OSError:
+        return []
+    anchors = [("loads / row decode helpers", "// ---------------------------------------------------------------- cache-policy loads"),
+               ("sort (network + merge path)", "// ---------------------------------------------------------------- warp merge sort"),
+               ("LP-row interning", "// ---------------------------------------------------------------- LP-key interning"),
+               ("kernel prologue / seed ticket", "// ---------------------------------------------------------------- the sampler kernel"),
+               ("walk: trace load", "if (PARITY && a.rng_mode == SUBG_RNG_TRACE) {"),
+               ("walk: first hop (incl. Fisher-Yates)", "// ---- first hop without replacement"),
+               ("walk: hops", "// Walks are advanced in groups of kGW per lane"),
+               ("keys -> registers, sort call", "if (lane == 0) keys[0] = (K)(uint32_t)u << OB;"),
+               ("run heads + row allocation", "// ---- runs of equal node = one set member each"),
+               ("landing counts (encode)", "// ---- landing counts per run"),
+               ("first-visit ranks", "// ---- first-visit rank of every member"),
+               ("emit (records, lookups, stores)", "// ---- emit the set"),
+               ("tail", "if (lane == 0 && mx > 0) atomicMax(a.max_set, mx);")]
+    pos = []
+    for name, text in anchors:
+        hit = next((i + 1 for i, line in enumerate(src) if text in line), None)
+        if hit is not None:
+            pos.append((hit, name))
+    pos.sort()
+    return [(name, lo, pos[i + 1][0] if i + 1 < len(pos) else 10 ** 9) for i, (lo, name) in enumerate(pos)]
 
 
 if __name__ == "__main__":

@@ -23,7 +23,7 @@ SYMBOLS = [
     "subg_abi_version", "subg_last_error",
     "subg_graph_create", "subg_graph_from_edges", "subg_graph_export", "subg_graph_info", "subg_graph_free",
     "subg_gset_sample", "subg_gset_sample_shard", "subg_spg_set_lp_table", "subg_spg_info", "subg_spg_export", "subg_spg_views", "subg_spg_rows",
-    "subg_spg_from_csr", "subg_spg_free",
+    "subg_spg_from_csr", "subg_spg_alloc", "subg_spg_seal", "subg_spg_free",
     "subg_spjoin_plan", "subg_spjoin_run", "subg_spjoin",
     "subg_ppr_topk", "subg_spg_encode", "subg_spg_pushes",
     "subg_walk_sample", "subg_walkset_info", "subg_walkset_export", "subg_walkset_views", "subg_walkset_free",
@@ -66,6 +66,8 @@ def load() -> C.CDLL:
     L.subg_spg_views.argtypes = [vp, vp] + [C.POINTER(vp)] * 6
     L.subg_spg_rows.argtypes = [vp] + [C.POINTER(vp)] * 4 + [C.POINTER(i64)]
     L.subg_spg_from_csr.argtypes = [vp, vp, vp, i32, i64, i64, i32, vp, C.POINTER(vp)]
+    L.subg_spg_alloc.argtypes = [i64, i64, i32, vp, C.POINTER(vp)]
+    L.subg_spg_seal.argtypes = [vp, vp]
     L.subg_spg_free.argtypes = [vp]
     L.subg_spg_free.restype = None
     L.subg_spjoin_plan.argtypes = [vp, vp, i64, i32, vp, vp, C.POINTER(i64), vp]

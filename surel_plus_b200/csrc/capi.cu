@@ -70,6 +70,8 @@ int spg_export_impl(const SpG *s, int32_t *nsize_hd, int32_t *remap_hd, int16_t 
                     cudaStream_t st);
 int spg_from_csr_impl(const int64_t *indptr_hd, const int32_t *indices_hd, const void *data_hd, int value_kind,
                       int64_t n_rows, int64_t nnz, int device, cudaStream_t st, SpG **out);
+int spg_alloc_impl(int64_t n, int64_t T, int device, cudaStream_t st, SpG **out);
+int spg_seal_impl(SpG *s, cudaStream_t st);
 int spjoin_plan_impl(const SpG *s, const int64_t *edge_hd, int64_t B, int arity, int64_t *edge_dev,
                      int64_t *indptr_dev, int64_t *N_out, cudaStream_t st);
 int spjoin_run_impl(const SpG *s, const int64_t *edge_dev, int64_t B, int arity, const int64_t *indptr_dev,
@@ -294,6 +296,12 @@ int subg_spg_from_csr(const int64_t *indptr_hd, const int32_t *indices_hd, const
     return spg_from_csr_impl(indptr_hd, indices_hd, data_hd, value_kind, n_rows, nnz, device, (cudaStream_t)stream,
                              reinterpret_cast<SpG **>(out));
 }
+
+int subg_spg_alloc(int64_t n, int64_t T, int device, void *stream, subg_spg **out) {
+    if (int rc = init_device(device)) return rc;
+    return spg_alloc_impl(n, T, device, (cudaStream_t)stream, reinterpret_cast<SpG **>(out));
+}
+int subg_spg_seal(subg_spg *s, void *stream) { return spg_seal_impl(reinterpret_cast<SpG *>(s), (cudaStream_t)stream); }
 
 void subg_spg_free(subg_spg *s) { spg_free_impl(reinterpret_cast<SpG *>(s)); }
 

@@ -101,9 +101,21 @@ __global__ void finalize_unique_kernel(const uint32_t *sorted_slot, uint32_t c, 
     for (int q = 1; q <= m; q++) enc[(int64_t)j * ncol + q] = (int16_t)((key >> (SHIFT * (m - q))) & fm);
 }
 
+// provisional table slot -> LP-row id + 1, in place: one streaming pass (16-byte accesses; the slot -> id map is a few
+// thousand hot entries of an L1/L2-resident array)
 __global__ void remap_ids_kernel(int32_t *data, int64_t T, const int32_t *rank_of_slot) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < T; i += (int64_t)gridDim.x * blockDim.x)
-        data[i] = rank_of_slot[data[i]] + 1;
+    const int64_t T4 = T >> 2;
+    int4 *d4 = (int4 *)data;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < T4; i += (int64_t)gridDim.x * blockDim.x) {
+        int4 v = d4[i];
+        v.x = __ldg(rank_of_slot + v.x) + 1;
+        v.y = __ldg(rank_of_slot + v.y) + 1;
+        v.z = __ldg(rank_of_slot + v.z) + 1;
+        v.w = __ldg(rank_of_slot + v.w) + 1;
+        d4[i] = v;
+    }
+    for (int64_t i = (T4 << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < T; i += (int64_t)gridDim.x * blockDim.x)
+        data[i] = __ldg(rank_of_slot + data[i]) + 1;
 }
 
 __global__ void relabel_ids_kernel(int32_t *data, int64_t T, const int32_t *id_map, int32_t c_old, int32_t c_new) {
@@ -516,7 +528,7 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
                 CK(cub::DeviceRadixSort::SortPairs(cub_tmp, tmp_bytes, u_pos, u_pos2, u_slot, u_slot2, (int)c, 0, 64, st));
                 finalize_unique_kernel<<<(c + 255) / 256, 256, 0, st>>>(u_slot2, c, tab_key, M, m, pl.SHIFT, rank_of_slot, s->enc);
                 if (extent > 0 && env_i64("SUBG_SAMPLER_STOP", 0) == 0) {  // a truncated measurement run leaves no valid rows
-                    const int64_t rb = std::min<int64_t>((extent + 1023) / 1024, 16 * (int64_t)g->num_sms);
+                    const int64_t rb = std::min<int64_t>((extent / 4 + 255) / 256 + 1, 16 * (int64_t)g->num_sms);
                     remap_ids_kernel<<<(unsigned)rb, 256, 0, st>>>((int32_t *)s->data, extent, rank_of_slot);
                 }
                 timing_end(SUBG_TIMING_BUILD, st);
@@ -579,7 +591,7 @@ int spg_set_lp_table_impl(SpG *s, const int32_t *id_map_hd, const int16_t *enc_h
     SUBG_CUDA(dmalloc(&d_enc, (size_t)c_new * s->ncol, st));
     if (s->c > 0) SUBG_CUDA(cudaMemcpyAsync(d_map, id_map_hd, (size_t)s->c * 4, cudaMemcpyDefault, st));
     if (c_new > 0) SUBG_CUDA(cudaMemcpyAsync(d_enc, enc_hd, (size_t)c_new * s->ncol * 2, cudaMemcpyDefault, st));
-    if (s->extent > 0) {
+    if (s->extent > 0 && s->c > 0) {
         const int64_t rb = std::min<int64_t>((s->extent + 255) / 256, 16 * (int64_t)s->num_sms);
         relabel_ids_kernel<<<(unsigned)rb, 256, 0, st>>>((int32_t *)s->data, s->extent, d_map, s->c, c_new);
         SUBG_CUDA(cudaGetLastError());
@@ -590,6 +602,61 @@ int spg_set_lp_table_impl(SpG *s, const int32_t *id_map_hd, const int16_t *enc_h
     dfree(s->enc, st);
     s->enc = d_enc;
     s->c = c_new;
+    return SUBG_OK;
+}
+
+// An empty LP SpG in the compact layout whose arrays the caller fills in place (the multi-GPU exchange lets NCCL
+// write the gathered shards straight into them): nsize int32[n], indices int32[T], data int32[T].  spg_seal_impl then
+// derives the row pointer and the largest set on the device.
+__global__ void max_i32_kernel(const int32_t *v, int64_t n, int32_t *out) {
+    int32_t m = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = max(m, v[i]);
+    for (int d = 16; d; d >>= 1) m = max(m, __shfl_xor_sync(FULL, m, d));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
+int spg_alloc_impl(int64_t n, int64_t T, int device, cudaStream_t st, SpG **out) {
+    if (!out || n < 0 || T < 0) return fail(SUBG_ERR_ARG, "Input parsing error.");
+    DeviceGuard guard(device);
+    SpG *s = new SpG();
+    s->device = device; s->n = n; s->T = T; s->value_kind = 0;
+    cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, device);
+    cudaError_t e = dmalloc(&s->indptr, (size_t)n + 1, st);
+    if (e == cudaSuccess) e = dmalloc(&s->nsize, (size_t)std::max<int64_t>(n, 1), st);
+    if (e == cudaSuccess) e = dmalloc(&s->indices, (size_t)T + 16, st);
+    if (e == cudaSuccess) e = dmalloc((int32_t **)&s->data, (size_t)T + 16, st);
+    if (e != cudaSuccess) {
+        free_spg_arrays(s, st);
+        delete s;
+        return fail(e == cudaErrorMemoryAllocation ? SUBG_ERR_MEM : SUBG_ERR_CUDA, cudaGetErrorString(e));
+    }
+    s->rowbeg = s->indptr; s->extent = T; s->cap = T + 16;
+    *out = s;
+    return SUBG_OK;
+}
+
+int spg_seal_impl(SpG *s, cudaStream_t st) {
+    if (!s || !s->indptr || !s->nsize) return fail(SUBG_ERR_ARG, "seal needs an SpG from subg_spg_alloc");
+    DeviceGuard guard(s->device);
+    long long *scratch = nullptr;
+    int32_t *d_max = nullptr;
+    SUBG_CUDA(dmalloc(&scratch, (size_t)std::max(1, scan_num_blocks(s->n)), st));
+    SUBG_CUDA(dmalloc(&d_max, 1, st));
+    SUBG_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int32_t), st));
+    SUBG_CUDA(exclusive_scan_i32_i64(s->nsize, (long long *)s->indptr, s->n, 0, scratch, st));
+    if (s->n > 0) {
+        const unsigned blocks = (unsigned)std::min<int64_t>((s->n + 255) / 256, 4 * (int64_t)s->num_sms);
+        max_i32_kernel<<<blocks, 256, 0, st>>>(s->nsize, s->n, d_max);
+    }
+    count_launch(4);
+    long long total = 0;
+    int32_t mx = 0;
+    SUBG_CUDA(cudaMemcpyAsync(&total, s->indptr + s->n, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    SUBG_CUDA(cudaMemcpyAsync(&mx, d_max, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SUBG_CUDA(cudaStreamSynchronize(st));
+    dfree(scratch, st); dfree(d_max, st);
+    if (total != s->T) return fail(SUBG_ERR_ARG, "set sizes do not add up to the number of entries");
+    s->max_set = mx;
     return SUBG_OK;
 }
 

@@ -79,7 +79,7 @@ def all_gather_sizes(vals: List[int], device, group=None) -> np.ndarray:
     return out.view(world, len(vals)).cpu().numpy()
 
 
-def all_gather_varlen(local: torch.Tensor, counts: np.ndarray, out: torch.Tensor, group=None) -> torch.Tensor:
+def all_gather_varlen(local: torch.Tensor, counts: np.ndarray, out: torch.Tensor, group=None, async_op: bool = False):
     """Concatenate the ranks' `local` (rank r contributes counts[r] leading-dim rows) into `out`.
     NCCL: the output slices are handed to all_gather directly (uneven sizes become grouped
     ncclBroadcasts that write in place, no staging copy).  Other backends (gloo in the CPU tests):
@@ -88,11 +88,28 @@ def all_gather_varlen(local: torch.Tensor, counts: np.ndarray, out: torch.Tensor
     offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
     assert local.shape[0] == counts[rank] and out.shape[0] == offs[-1]
     if backend == "nccl":
-        # bytes on the wire: NCCL has no int16 (the LP table), and a byte view costs nothing
+        # bytes on the wire: NCCL has no int16 (the LP table), and a byte view costs nothing.  Every rank sends its
+        # shard to every peer and receives the peers' shards straight into their slices of `out` (grouped
+        # ncclSend/ncclRecv over NVLink: 614 GB/s per GPU at world 2 where the uneven list all-gather, which torch
+        # turns into one broadcast per rank, reaches 356 GB/s -- scripts/nccl_probe.py); the own slice is a local copy.
         ob = out.reshape(out.shape[0], -1).view(torch.uint8) if out.shape[0] else out.reshape(0, 1).view(torch.uint8)
         lb = local.contiguous().reshape(local.shape[0], -1).view(torch.uint8) if local.shape[0] else ob[:0]
-        slices = [ob[offs[r]:offs[r + 1]] for r in range(world)]
-        dist.all_gather(slices, lb, group=group)
+        if counts[rank]:
+            ob[offs[rank]:offs[rank + 1]].copy_(lb)
+        ops = []
+        for r in range(world):
+            if r == rank:
+                continue
+            peer = r if group is None else dist.get_global_rank(group, r)
+            if counts[rank]:
+                ops.append(dist.P2POp(dist.isend, lb, peer, group))
+            if counts[r]:
+                ops.append(dist.P2POp(dist.irecv, ob[offs[r]:offs[r + 1]], peer, group))
+        works = dist.batch_isend_irecv(ops) if ops else []
+        if async_op:
+            return works
+        for w in works:
+            w.wait()
         return out
     # bytes on the wire (gloo has no int16): rows -> uint8 [rows, bytes_per_row]
     per_row = int(np.prod(local.shape[1:], dtype=np.int64))
@@ -154,7 +171,7 @@ def sharded_sample(graph, query, num_walks=100, num_steps=3, bucket=-1, seed=111
     """Sample this rank's seed range on its GPU and exchange shards: returns the full SpG (replicated
     on every rank), identical to SpG.sample(graph, query, ...) of a single process (bit for bit in
     RAND_R / TRACE-free modes: seed indices, rand_r offsets and LP ids are global)."""
-    from .spg import SpG, _ptr, _stream
+    from .spg import SpG, _ptr, _stream, _view
     lib = _capi.load()
     world, rank, _ = _group_info(group)
     q = np.ascontiguousarray(np.asarray(query).astype(np.int32, copy=False))
@@ -167,25 +184,73 @@ def sharded_sample(graph, query, num_walks=100, num_steps=3, bucket=-1, seed=111
                                            _stream(graph.device), C.byref(h)))
     shard = SpG(h, graph.device, n_nodes=graph.N, num_walks=num_walks)
     v = shard.views()
+    dev = v["indices"].device
+    st = _stream(graph.device)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     ev[0].record()
+    import os as _os, sys as _sys, time as _time
+    prof = _os.environ.get("SUBG_PROFILE_HOST") is not None
+    marks, t_last = [], _time.perf_counter()
 
-    def relabel(id_map: np.ndarray, merged: np.ndarray) -> torch.Tensor:
-        m = np.ascontiguousarray(merged, dtype=np.int16)
-        _capi.check(lib.subg_spg_set_lp_table(shard._h, _ptr(id_map), _ptr(m), m.shape[0], -1, _stream(graph.device)))
-        return v["data"]
-
-    enc_local = v["enc"] if "enc" in v else torch.zeros((0, num_steps + 1), dtype=torch.int16, device=v["indices"].device)
-    nsize_local = v["nsize"] if "nsize" in v else torch.zeros(0, dtype=torch.int32, device=v["indices"].device)
-    parts = assemble_shards(nsize_local, v["indices"], v["data"], enc_local, relabel=relabel, group=group)
-    status = shard.status
-    if world > 1:
-        status = int(np.bitwise_or.reduce(all_gather_sizes([shard.status], parts["indices"].device, group)[:, 0]))
+    def mark(name):
+        nonlocal t_last
+        if prof:
+            torch.cuda.synchronize()
+            t = _time.perf_counter()
+            marks.append(f"{name}={1e3 * (t - t_last):.2f}")
+            t_last = t
+    ncol = num_steps + 1
+    enc_local = v["enc"] if "enc" in v else torch.zeros((0, ncol), dtype=torch.int16, device=dev)
+    nsize_local = v["nsize"] if "nsize" in v else torch.zeros(0, dtype=torch.int32, device=dev)
+    counts = all_gather_sizes([shard.n, shard.T, shard.c, shard.status], dev, group)
+    n_r, T_r, c_r = counts[:, 0], counts[:, 1], counts[:, 2]
+    n_tot, T_tot = int(n_r.sum()), int(T_r.sum())
+    # the full SpG is allocated once and every rank's shard lands in place (no staging copy)
+    fh = C.c_void_p()
+    mark("sizes")
+    _capi.check(lib.subg_spg_alloc(n_tot, T_tot, graph.device, st, C.byref(fh)))
+    mark("alloc")
+    try:
+        p = [C.c_void_p() for _ in range(6)]
+        _capi.check(lib.subg_spg_views(fh, st, *[C.byref(x) for x in p]))
+        g_indices = _view(p[1].value, (T_tot,), "<i4", graph.device, None)
+        g_data = _view(p[2].value, (T_tot,), "<i4", graph.device, None)
+        g_nsize = _view(p[5].value, (n_tot,), "<i4", graph.device, None)
+        # node ids and set sizes do not depend on the LP relabelling: their all-gathers run on NCCL's stream while
+        # the LP tables are merged on the host and this rank's ids are relabelled
+        works = [all_gather_varlen(nsize_local, n_r, g_nsize, group, async_op=True),
+                 all_gather_varlen(v["indices"], T_r, g_indices, group, async_op=True)]
+        mark("gather nsize+indices")
+        enc_all = torch.empty((int(c_r.sum()), ncol), dtype=torch.int16, device=dev)
+        all_gather_varlen(enc_local.contiguous(), c_r, enc_all, group)
+        enc_np = enc_all.cpu().numpy()
+        offs = np.concatenate([[0], np.cumsum(c_r)])
+        merged, maps = merge_lp_tables([enc_np[offs[r]:offs[r + 1]] for r in range(world)])
+        merged = np.ascontiguousarray(merged, dtype=np.int16)
+        id_map = maps[rank]
+        mark("lp merge")
+        _capi.check(lib.subg_spg_set_lp_table(shard._h, _ptr(id_map), _ptr(merged), merged.shape[0], -1, st))
+        mark("relabel")
+        works.append(all_gather_varlen(v["data"], T_r, g_data, group, async_op=True))
+        for w in works:
+            for one in (w if isinstance(w, (list, tuple)) else [w]):
+                if one is not None and not isinstance(one, torch.Tensor):
+                    one.wait()
+        mark("gather data")
+        _capi.check(lib.subg_spg_seal(fh, st))
+        _capi.check(lib.subg_spg_set_lp_table(fh, None, _ptr(merged), merged.shape[0], ncol, st))
+        mark("seal")
+        if prof and rank == 0:
+            print("[subg host ms] exchange: " + " ".join(marks), file=_sys.stderr, flush=True)
+    except Exception:
+        lib.subg_spg_free(fh)
+        raise
+    status = int(np.bitwise_or.reduce(counts[:, 3]))
     shard.close()
-    full = SpG.from_device_csr(parts["indptr"], parts["indices"], parts["data"], n_nodes=graph.N, enc=parts["enc"],
-                               num_walks=num_walks, status=status)
+    full = SpG(fh, graph.device, n_nodes=graph.N, num_walks=num_walks)
+    full.status = status
     ev[1].record()
-    full.exchange_bytes = parts["bytes_gathered"]
+    full.exchange_bytes = 8 * T_tot + 4 * n_tot + 2 * ncol * int(c_r.sum())
     full.exchange_events = ev   # elapsed = LP-table merge + all-gathers + CSR assembly (device time)
     return full
 
