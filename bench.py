@@ -377,13 +377,13 @@ def bench_spjoin(args, torch, dev, spg, A, M, k, gather, _capi, peaks, barrier, 
     sizes = spg.set_sizes().cpu().numpy()
     rows = [int(sizes[b[0]].sum() + sizes[b[1]].sum()) for b in batches]
     # device-resident edges, fused fp32 feature output [N,2,k]
-    for i in range(3):
+    for i in range(2 * nb):  # every batch shape once: the output-size estimate and torch's block cache settle
         gather(dev_batches[i % nb], spg, dev, True, xpe)
     _capi.timing_enable(True)
     _capi.timing_read(1)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = max(args.steps, 1) * 4
+    reps = max(args.steps, 1) * 8
     e0.record()
     for i in range(reps):
         xz, ptr = gather(dev_batches[i % nb], spg, dev, True, xpe)
@@ -396,7 +396,7 @@ def bench_spjoin(args, torch, dev, spg, A, M, k, gather, _capi, peaks, barrier, 
     alg = 48.0 * B + (8 + 8 * kdim) * rows_avg  # SURVEY 8(d), fused-feature form
     ach = alg / (k_ms / max(k_n, 1) / 1e3) / 1e9
     # e2e: pinned host edges in, checksum scalar back (what a training step does with the loss)
-    for i in range(2):
+    for i in range(nb):
         gather(pin_batches[i], spg, dev, True, xpe)
     barrier()
     t0 = time.perf_counter()

@@ -227,11 +227,11 @@ static int make_plan(const Graph *g, int M, int m, int bucket, SamplePlan *p) {
         return fail(SUBG_ERR_ASSERT, "Longer width of type for hasing key needed > INT64.");
     const int64_t Kt = (int64_t)M * m + 1;
     const int max_epl = kEplList[sizeof(kEplList) / sizeof(int) - 1];
-    if (m > 4 || Kt > 32 * (int64_t)max_epl)
-        return fail(SUBG_ERR_UNSUPPORTED, "this build supports num_steps <= 4 and num_walks * num_steps <= 2015");
+    if (m > 16 || Kt > 32 * (int64_t)max_epl)
+        return fail(SUBG_ERR_UNSUPPORTED, "this build supports num_steps <= 16 and num_walks * num_steps <= 2015");
     p->SHIFT = shift;
     p->Kt = (int)Kt;
-    p->LS = m <= 1 ? 0 : (m <= 2 ? 1 : 2);
+    p->LS = ceil_log2((uint64_t)m);  // step slots per walk: 1, 2, 4, 8, 16
     p->EPL = max_epl;
     for (int e : kEplList)
         if (32 * e >= Kt) { p->EPL = e; break; }

@@ -138,3 +138,53 @@ def test_collab_window_vs_oracle_and_dblp_triplets():
     sizes = torch.cat([p1[1:] - p1[:-1], p2[1:] - p2[:-1]])
     assert torch.equal(ind, torch.repeat_interleave(torch.arange(4 * B, device="cuda:0"), sizes))
     spg.close()
+
+
+def test_citation2_ppr_full_size_window_vs_oracle_and_mrr_queries():
+    """configs[2]: citation2 shape (2.93 M nodes, 61 M directed entries), PPR top-100 alpha 0.1 eps 1e-4 'sym'
+    (main.py:44,111): a window of seeds (hubs, mid ids, the tail) bit-exact against the oracle on the FULL graph,
+    size-independent properties of every row, and MRR-style 1-vs-1000 queries sharing their source joined on the
+    value SpG (float mode of gather, train.py:38-43)."""
+    from oracle import pyoracle as po
+    from surel_plus_b200 import DeviceGraph, gather, topk_ppr_matrix
+    from surel_plus_b200.graphs import named_graph
+    A = named_graph("citation2").astype(np.int64)
+    n, topk = A.shape[0], 100
+    g = DeviceGraph.from_scipy(A, "cuda:0")
+    win = np.concatenate([np.arange(0, 150), np.arange(n // 2, n // 2 + 150), np.arange(n - 150, n)])
+    exp = po.topk_ppr_matrix(A, 0.1, 1e-4, win, topk, "sym").astype(np.float64).tocsr()
+    exp.sort_indices()
+    # the product call: graph resident in HBM, unweighted degree == adj.sum(1) for this 0/1 adjacency
+    got = topk_ppr_matrix(g, 0.1, 1e-4, win, topk, normalization="sym").to_scipy()
+    assert np.array_equal(got.indptr, exp.indptr) and np.array_equal(got.indices, exp.indices)
+    assert np.allclose(got.data, exp.data, rtol=1e-5, atol=0)          # north star: scores within 1e-5 relative
+    assert np.array_equal(got.data, exp.data)                           # and in fact identical
+    # every node a seed
+    x = topk_ppr_matrix(g, 0.1, 1e-4, np.arange(n), topk, normalization="sym")
+    v = x.views()
+    indptr, indices, data = v["indptr"], v["indices"], v["data"]
+    sizes = indptr[1:] - indptr[:-1]
+    assert x.n == n and int(sizes.max()) <= topk and int(sizes.min()) >= 1
+    asc = indices[1:] > indices[:-1]
+    asc[indptr[1:-1] - 1] = True
+    assert bool(asc.all())
+    assert bool(torch.isfinite(data).all()) and float(data.min()) > 0
+    # the seed is always in its own top-k (p[s] >= alpha), found by searching its row
+    rows = torch.repeat_interleave(torch.arange(n, device="cuda:0"), sizes)
+    assert int((indices.long() == rows).sum()) == n
+    del rows, asc
+    # 1 positive + 1000 negatives per source (MRR evaluation pattern), 16 sources per call
+    rng = np.random.default_rng(5)
+    src = rng.integers(0, n, 16)
+    edge = np.stack([np.repeat(src, 1001), rng.integers(0, n, 16 * 1001)])
+    xz, ptr = gather(torch.from_numpy(edge), x, "cuda:0", True, None)
+    assert xz.shape[1:] == (2, 1) and xz.dtype == torch.float32 and ptr.numel() == 2 * edge.shape[1] + 1
+    B = edge.shape[1]
+    ip = ptr.cpu().numpy()
+    S = x.to_scipy()
+    exz, sl, sr = po.spjoin_pair(S, edge[:, :3003])
+    nl = int(sl.sum())
+    assert np.array_equal(np.diff(ip)[:3003], sl) and np.array_equal(np.diff(ip)[B:B + 3003], sr)
+    assert np.array_equal(xz[:nl, :, 0].cpu().numpy(), exz[:nl].astype(np.float32))
+    x.close()
+    g.close()

@@ -21,7 +21,8 @@ def _assert_same(got, exp, tag):
 
 
 @pytest.mark.parametrize("M,m,bucket", [(20, 3, -1), (50, 2, -1), (20, 3, 15), (200, 2, -1), (7, 4, -1),
-                                        (200, 3, -1), (100, 2, -1), (33, 1, -1), (64, 2, -1), (32, 4, -1)])
+                                        (200, 3, -1), (100, 2, -1), (33, 1, -1), (64, 2, -1), (32, 4, -1),
+                                        (20, 6, -1), (100, 5, -1), (12, 9, 40), (250, 7, -1)])
 def test_rand_r_replay_bit_exact(small_graph, M, m, bucket):
     """SUBG_RNG_RAND_R == reference gset_sampler(nthread=1) (via the pinned oracle), whole output."""
     from surel_plus_b200 import DeviceGraph, _capi
