@@ -476,7 +476,7 @@ def main():
     ap.add_argument("--workload", default="ppa", choices=sorted(WORKLOADS))
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (smoke runs only)")
     ap.add_argument("--spjoin-batch", type=int, default=21504, help="queries per SpJoin call (1024 x (1 pos + 20 neg))")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--ref-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

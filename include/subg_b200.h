@@ -240,6 +240,23 @@ int subg_walkset_views(const subg_walkset *w, const int32_t **walks, const int64
                        const int32_t **rpe);
 void subg_walkset_free(subg_walkset *w);
 
+/* Replaces walk_join (subg_acc/subg_acc.c:509-647), the SUREL-v1 join over walk sets.
+ *   walks   int32[n, stride]: row i holds the walks of root walks[i*stride] (walk_sampler's first output)
+ *   key     the node set of every row as a CSR pair: key_off int64[n+1], key_ids int32[T] (the reference takes a
+ *           sequence of n arrays; walk_sampler's obj[:,0] concatenated); ids are unique within a row
+ *   query   int32[Q, 2] node ids
+ *   out     int32[2, Q*2*stride]: for query x = (u, v) and position j, with w1 = walks[row(u)][j], w2 = walks[row(v)][j]:
+ *             out[0][2x*stride + 2j] = idx(u, w1)   out[0][.. + 1] = idx(v, w1)
+ *             out[1][2x*stride + 2j] = idx(u, w2)   out[1][.. + 1] = idx(v, w2)
+ *           idx(r, w) = 1 + position of w in the concatenated key sets if w is in the set of root r, else 0
+ *           (-1 if r is not a root, subg_acc.c:87-100)
+ *   xq      int32[Q, 2] (nullable): row of every query node, -1 if it is not a root (the reference's `return_idx`).
+ * Entries that depend on the walks of an unknown root are -1 (the reference reads out of bounds there).
+ * All pointers host or device.  Synchronises the stream. */
+int subg_walk_join(const int32_t *walks_hd, int64_t n, int64_t stride, const int64_t *key_off_hd,
+                   const int32_t *key_ids_hd, const int32_t *query_hd, int64_t Q, int32_t *out_hd, int32_t *xq_hd,
+                   int device, void *stream);
+
 /* ---- measurement hooks (bench.py / profiles) -------------------------------------
  * When enabled, the library brackets its dominant kernels with CUDA events on the
  * launching stream.  subg_timing_read synchronises those events, returns the summed

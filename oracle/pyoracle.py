@@ -59,6 +59,8 @@ def lib() -> C.CDLL:
                                     C.c_int64, _i64p, _i64p, C.c_int]
     L.orc_walk_sampler_walks.restype = C.c_uint32
     L.orc_walk_sampler_walks.argtypes = [_i64p, _i32p, _i32p, C.c_int64, C.c_int, C.c_int, C.c_uint32, C.c_int, _i32p]
+    L.orc_walk_join.restype = C.c_int
+    L.orc_walk_join.argtypes = [_i32p, C.c_int64, C.c_int64, _i64p, _i32p, _i32p, C.c_int64, _i32p, _i32p]
     L.orc_rpe_encode.restype = C.c_int64
     L.orc_rpe_encode.argtypes = [_i32p, C.c_int64, C.c_int, C.c_int, _i64p, _i32p, _i32p, C.c_int64]
     _lib = L
@@ -146,6 +148,27 @@ def walk_sampler(ptr, neighs, query, num_walks=100, num_steps=3, seed=111413, re
         obj[i, 0] = ids[off[i]:off[i + 1]]
         obj[i, 1] = rpe[off[i]:off[i + 1]]
     return [walks, obj]
+
+
+def walk_join(walk, key, query, return_idx=False):
+    """== reference walk_join(walk, key, query) [subg_acc.c:509-647].  Returns out int32 [2, Q*2*stride]
+    (and xq int32 [Q,2] when return_idx)."""
+    walk = _c(walk, np.int32)
+    n = walk.shape[0]
+    stride = int(np.prod(walk.shape[1:]))
+    keys = [np.asarray(k, dtype=np.int32).ravel() for k in key]
+    assert len(keys) == n, "Dims do not match between num of walks and keys."
+    off = np.zeros(n + 1, np.int64)
+    np.cumsum([len(k) for k in keys], out=off[1:])
+    ids = _c(np.concatenate(keys), np.int32) if n else np.zeros(0, np.int32)
+    q = _c(query, np.int32)
+    Q = q.shape[0]
+    out = np.zeros((2, Q * 2 * stride), np.int32)
+    xq = np.zeros((Q, 2), np.int32)
+    rc = lib().orc_walk_join(walk.reshape(-1), n, stride, off, ids, q.reshape(-1), Q, out.reshape(-1), xq.reshape(-1))
+    if rc != 0:
+        raise MemoryError(f"oracle walk_join failed rc={rc}")
+    return [out, xq] if return_idx else out
 
 
 def rpe_encode(walks, M: int, m: int):

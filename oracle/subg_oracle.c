@@ -627,3 +627,76 @@ int64_t orc_rpe_encode(const int32_t *walks, int64_t n, int M, int m,
     slotmap_free(&h);
     return total;
 }
+
+/* ------------------------------------------------------------------------- */
+/* walk_join (SUREL v1), subg_acc.c:509-647.  Two-level lookup as the         */
+/* reference builds it: root node -> row (:566-575), and per row node ->      */
+/* running index starting at 1 over the concatenated key sets (:577-588).     */
+/* find_idx (:87-100): index, 0 if the node is not in that root's set, -1 if  */
+/* the root is unknown.  out[2][Q*2*stride], xq[Q][2] (:618-633).  Entries    */
+/* that depend on the walks of an unknown root are set to -1 (the reference   */
+/* reads out of bounds there).  Duplicate roots / duplicate ids within a key  */
+/* set are outside the contract (uthash keeps both and finds one of them).    */
+/* ------------------------------------------------------------------------- */
+int orc_walk_join(const int32_t *walks, int64_t n, int64_t stride, const int64_t *key_off,
+                  const int32_t *key_ids, const int32_t *query, int64_t Q, int32_t *out, int32_t *xq)
+{
+    idmap roots, members;
+    uint64_t cap = 64;
+    while (cap < 4 * (uint64_t)(key_off[n] + n + 1)) cap <<= 1;
+    if (idmap_init(&roots, cap) || idmap_init(&members, cap)) return -1;
+    int added;
+    for (int64_t i = 0; i < n; i++) {
+        idmap_get_or_add(&roots, (uint64_t)(uint32_t)walks[i * stride], (int32_t)i, &added);
+        for (int64_t j = key_off[i]; j < key_off[i + 1]; j++)
+            idmap_get_or_add(&members, ((uint64_t)i << 32) | (uint32_t)key_ids[j], (int32_t)(j + 1), &added);
+    }
+    const int64_t half = Q * 2 * stride;
+#define ORC_FIND_ROW(node, dst)                                                            \
+    do {                                                                                   \
+        uint64_t p_ = mix64((uint64_t)(uint32_t)(node)) & (roots.cap - 1);                 \
+        (dst) = -1;                                                                        \
+        while (roots.val[p_] >= 0) {                                                       \
+            if (roots.key[p_] == (uint64_t)(uint32_t)(node)) { (dst) = roots.val[p_]; break; } \
+            p_ = (p_ + 1) & (roots.cap - 1);                                               \
+        }                                                                                  \
+    } while (0)
+#define ORC_FIND_IDX(row, node, dst)                                                       \
+    do {                                                                                   \
+        if ((row) < 0) { (dst) = -1; break; }                                              \
+        const uint64_t k_ = ((uint64_t)(row) << 32) | (uint32_t)(node);                    \
+        uint64_t p_ = mix64(k_) & (members.cap - 1);                                       \
+        (dst) = 0;                                                                         \
+        while (members.val[p_] >= 0) {                                                     \
+            if (members.key[p_] == k_) { (dst) = members.val[p_]; break; }                 \
+            p_ = (p_ + 1) & (members.cap - 1);                                             \
+        }                                                                                  \
+    } while (0)
+    for (int64_t x = 0; x < Q; x++) {
+        int32_t r1, r2;
+        ORC_FIND_ROW(query[2 * x], r1);
+        ORC_FIND_ROW(query[2 * x + 1], r2);
+        xq[2 * x] = r1;
+        xq[2 * x + 1] = r2;
+        for (int64_t j = 0; j < stride; j++) {
+            const int64_t o = 2 * x * stride + 2 * j;
+            int32_t a = -1, b = -1, c = -1, d = -1;
+            if (r1 >= 0) {
+                const int32_t w1 = walks[(int64_t)r1 * stride + j];
+                ORC_FIND_IDX(r1, w1, a);
+                ORC_FIND_IDX(r2, w1, b);
+            }
+            if (r2 >= 0) {
+                const int32_t w2 = walks[(int64_t)r2 * stride + j];
+                ORC_FIND_IDX(r1, w2, c);
+                ORC_FIND_IDX(r2, w2, d);
+            }
+            out[o] = a; out[o + 1] = b; out[half + o] = c; out[half + o + 1] = d;
+        }
+    }
+#undef ORC_FIND_ROW
+#undef ORC_FIND_IDX
+    idmap_free(&roots);
+    idmap_free(&members);
+    return 0;
+}

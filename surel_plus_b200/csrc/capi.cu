@@ -92,6 +92,8 @@ int walkset_export_impl(const WalkSet *w, int32_t *walks_hd, int64_t *off_hd, in
 int walkset_info_impl(const WalkSet *w, int64_t *n, int64_t *T, int32_t *M, int32_t *ncol, uint32_t *status);
 int walkset_views_impl(const WalkSet *w, const int32_t **walks, const int64_t **off, const int32_t **ids, const int32_t **rpe);
 void walkset_free_impl(WalkSet *w);
+int walk_join_impl(const int32_t *walks_hd, int64_t n, int64_t stride, const int64_t *key_off_hd, const int32_t *key_ids_hd,
+                   const int32_t *query_hd, int64_t Q, int32_t *out_hd, int32_t *xq_hd, int device, cudaStream_t st);
 
 __global__ void widen_rowptr_kernel(const int32_t *in, long long *out, int64_t n) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = in[i];
@@ -404,6 +406,11 @@ int subg_walkset_views(const subg_walkset *w, const int32_t **walks, const int64
     return walkset_views_impl(reinterpret_cast<const WalkSet *>(w), walks, off, ids, rpe);
 }
 void subg_walkset_free(subg_walkset *w) { walkset_free_impl(reinterpret_cast<WalkSet *>(w)); }
+int subg_walk_join(const int32_t *walks_hd, int64_t n, int64_t stride, const int64_t *key_off_hd, const int32_t *key_ids_hd,
+                   const int32_t *query_hd, int64_t Q, int32_t *out_hd, int32_t *xq_hd, int device, void *stream) {
+    if (int rc = init_device(device)) return rc;
+    return walk_join_impl(walks_hd, n, stride, key_off_hd, key_ids_hd, query_hd, Q, out_hd, xq_hd, device, (cudaStream_t)stream);
+}
 
 int subg_host_alloc(void **ptr, int64_t bytes) {
     if (!ptr || bytes < 0) return fail(SUBG_ERR_ARG, "bad host allocation request");

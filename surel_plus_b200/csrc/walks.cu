@@ -15,6 +15,7 @@
 // equal nodes become runs, a bitmap over the visit orders of the run heads ranks the nodes in
 // first-visit order, and each head counts its run per step.  It runs twice: sizes, scan, then rows.
 #include <algorithm>
+#include <cub/cub.cuh>
 
 #include "common.cuh"
 #include "scan.cuh"
@@ -424,6 +425,166 @@ int walkset_export_impl(const WalkSet *w, int32_t *walks_hd, int64_t *off_hd, in
     if (rpe_hd && w->T > 0) SUBG_CUDA(cudaMemcpyAsync(rpe_hd, w->rpe, (size_t)w->T * ncol * sizeof(int32_t), cudaMemcpyDefault, st));
     SUBG_CUDA(cudaStreamSynchronize(st));
     return SUBG_OK;
+}
+
+// ---------------------------------------------------------------- walk_join (SUREL v1), subg_acc.c:509-647
+// For every query (u, v) and every position j of the rows of u and v in `walks`: the 1-based position of the visited
+// node in the concatenated key sets, looked up in the set of u and in the set of v (0 = not a member).  The
+// reference builds a two-level hash (root -> row, (row, node) -> running index); here both levels are sorted arrays
+// searched by bisection: (row << 32 | node) -> index for the sets, root node -> row for the roots.
+namespace {
+
+__global__ void join_keys_kernel(const long long *off, const int32_t *ids, int64_t n, unsigned long long *keys, int32_t *vals) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < n; i += nw)
+        for (long long j = off[i] + lane; j < off[i + 1]; j += 32) {
+            keys[j] = ((unsigned long long)i << 32) | (uint32_t)ids[j];
+            vals[j] = (int32_t)(j + 1);  // idx starts at 1 and runs over all rows (subg_acc.c:563,583-586)
+        }
+}
+__global__ void join_roots_kernel(const int32_t *walks, int64_t n, int64_t stride, unsigned long long *keys) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        keys[i] = ((unsigned long long)(uint32_t)walks[i * stride] << 32) | (uint32_t)i;  // root node -> row (subg_acc.c:572-575)
+}
+__device__ __forceinline__ int32_t find_row(const unsigned long long *roots, int64_t n, int32_t node) {
+    int64_t lo = 0, hi = n;
+    const unsigned long long want = (unsigned long long)(uint32_t)node << 32;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (roots[mid] < want) lo = mid + 1;
+        else hi = mid;
+    }
+    return (lo < n && (roots[lo] >> 32) == (uint32_t)node) ? (int32_t)(uint32_t)roots[lo] : -1;
+}
+__global__ void join_query_rows_kernel(const unsigned long long *roots, int64_t n, const int32_t *query, int64_t Q2, int32_t *xq) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < Q2; i += (int64_t)gridDim.x * blockDim.x)
+        xq[i] = find_row(roots, n, query[i]);
+}
+__device__ __forceinline__ int32_t find_member(const unsigned long long *keys, const int32_t *vals, const long long *off,
+                                               int32_t row, int32_t node) {
+    if (row < 0) return -1;  // find_idx: unknown main key (subg_acc.c:96-99)
+    long long lo = off[row], hi = off[row + 1];
+    const long long end = hi;
+    const unsigned long long want = ((unsigned long long)(uint32_t)row << 32) | (uint32_t)node;
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (keys[mid] < want) lo = mid + 1;
+        else hi = mid;
+    }
+    return (lo < end && keys[lo] == want) ? vals[lo] : 0;
+}
+__global__ void walk_join_kernel(const int32_t *walks, int64_t stride, const unsigned long long *keys, const int32_t *vals,
+                                 const long long *off, const int32_t *xq, int64_t Q, int32_t *out) {
+    const int64_t total = Q * stride, half = Q * 2 * stride;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t x = t / stride, j = t - x * stride;
+        const int32_t r1 = xq[2 * x], r2 = xq[2 * x + 1];
+        const int64_t o = 2 * x * stride + 2 * j;
+        // a query node that is no root has no walks: its entries are -1 (the reference reads out of bounds there)
+        const int32_t w1 = r1 >= 0 ? walks[(int64_t)r1 * stride + j] : -1;
+        const int32_t w2 = r2 >= 0 ? walks[(int64_t)r2 * stride + j] : -1;
+        out[o] = r1 >= 0 ? find_member(keys, vals, off, r1, w1) : -1;
+        out[o + 1] = r1 >= 0 ? find_member(keys, vals, off, r2, w1) : -1;
+        out[half + o] = r2 >= 0 ? find_member(keys, vals, off, r1, w2) : -1;
+        out[half + o + 1] = r2 >= 0 ? find_member(keys, vals, off, r2, w2) : -1;
+    }
+}
+
+}  // namespace
+
+int walk_join_impl(const int32_t *walks_hd, int64_t n, int64_t stride, const int64_t *key_off_hd, const int32_t *key_ids_hd,
+                   const int32_t *query_hd, int64_t Q, int32_t *out_hd, int32_t *xq_hd, int device, cudaStream_t st) {
+    if (n < 0 || stride < 1 || Q < 0 || (n > 0 && (!walks_hd || !key_off_hd)) || (Q > 0 && (!query_hd || !out_hd)))
+        return fail(SUBG_ERR_ARG, "Input parsing error.");
+    if (n >= (1ll << 31)) return fail(SUBG_ERR_ARG, "too many rows");
+    DeviceGuard guard(device);
+    int num_sms = 148;
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device);
+    int32_t *d_walks = nullptr, *d_ids = nullptr, *d_query = nullptr, *d_out = nullptr, *d_xq = nullptr, *v_a = nullptr, *v_b = nullptr;
+    long long *d_off = nullptr;
+    unsigned long long *k_a = nullptr, *k_b = nullptr, *r_a = nullptr, *r_b = nullptr;
+    void *tmp = nullptr;
+    int rc = SUBG_OK;
+    cudaError_t e = cudaSuccess;
+#define JK(call)                                                                                   \
+    do {                                                                                           \
+        e = (call);                                                                                \
+        if (e != cudaSuccess) {                                                                    \
+            rc = fail(e == cudaErrorMemoryAllocation ? SUBG_ERR_MEM : SUBG_ERR_CUDA,               \
+                      std::string(#call) + ": " + cudaGetErrorString(e));                          \
+            goto done;                                                                             \
+        }                                                                                          \
+    } while (0)
+    {
+        long long T = 0;
+        const long long *off = (const long long *)key_off_hd;
+        if (n > 0) {
+            if (!is_device_ptr(key_off_hd)) {
+                T = key_off_hd[n];
+                JK(dmalloc(&d_off, (size_t)n + 1, st));
+                JK(cudaMemcpyAsync(d_off, key_off_hd, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
+                off = d_off;
+            } else {
+                JK(cudaMemcpyAsync(&T, key_off_hd + n, 8, cudaMemcpyDeviceToHost, st));
+                JK(cudaStreamSynchronize(st));
+            }
+        }
+        if (T < 0 || (T > 0 && !key_ids_hd)) { rc = fail(SUBG_ERR_ARG, "Input parsing error."); goto done; }
+        const int32_t *walks = walks_hd, *ids = key_ids_hd, *query = query_hd;
+        if (n > 0 && !is_device_ptr(walks_hd)) {
+            JK(dmalloc(&d_walks, (size_t)n * stride, st));
+            JK(cudaMemcpyAsync(d_walks, walks_hd, (size_t)n * stride * 4, cudaMemcpyHostToDevice, st));
+            walks = d_walks;
+        }
+        if (T > 0 && !is_device_ptr(key_ids_hd)) {
+            JK(dmalloc(&d_ids, (size_t)T, st));
+            JK(cudaMemcpyAsync(d_ids, key_ids_hd, (size_t)T * 4, cudaMemcpyHostToDevice, st));
+            ids = d_ids;
+        }
+        if (Q > 0 && !is_device_ptr(query_hd)) {
+            JK(dmalloc(&d_query, (size_t)2 * Q, st));
+            JK(cudaMemcpyAsync(d_query, query_hd, (size_t)2 * Q * 4, cudaMemcpyHostToDevice, st));
+            query = d_query;
+        }
+        int32_t *out = out_hd, *xq = xq_hd;
+        if (Q > 0 && !is_device_ptr(out_hd)) { JK(dmalloc(&d_out, (size_t)4 * Q * stride, st)); out = d_out; }
+        if (Q > 0 && (!xq_hd || !is_device_ptr(xq_hd))) { JK(dmalloc(&d_xq, (size_t)2 * Q, st)); xq = d_xq; }
+        JK(dmalloc(&k_a, (size_t)T + 1, st)); JK(dmalloc(&k_b, (size_t)T + 1, st));
+        JK(dmalloc(&v_a, (size_t)T + 1, st)); JK(dmalloc(&v_b, (size_t)T + 1, st));
+        JK(dmalloc(&r_a, (size_t)n + 1, st)); JK(dmalloc(&r_b, (size_t)n + 1, st));
+        const unsigned gb = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n * 32 + 255) / 256, 8 * (int64_t)num_sms));
+        cub::DoubleBuffer<unsigned long long> dk(k_a, k_b), dr(r_a, r_b);
+        cub::DoubleBuffer<int32_t> dv(v_a, v_b);
+        if (n > 0) {
+            join_keys_kernel<<<gb, 256, 0, st>>>(off, ids, n, k_a, v_a);
+            join_roots_kernel<<<gb, 256, 0, st>>>(walks, n, stride, r_a);
+            int nbits = 1;
+            while ((n >> nbits) != 0) nbits++;
+            size_t b1 = 0, b2 = 0;
+            JK(cub::DeviceRadixSort::SortPairs(nullptr, b1, dk, dv, (int64_t)T, 0, 32 + nbits, st));
+            JK(cub::DeviceRadixSort::SortKeys(nullptr, b2, dr, (int64_t)n, 0, 64, st));
+            JK(cudaMallocAsync(&tmp, std::max<size_t>(std::max(b1, b2), 16), st));
+            if (T > 0) JK(cub::DeviceRadixSort::SortPairs(tmp, b1, dk, dv, (int64_t)T, 0, 32 + nbits, st));
+            JK(cub::DeviceRadixSort::SortKeys(tmp, b2, dr, (int64_t)n, 0, 64, st));
+            count_launch(8);
+        }
+        if (Q > 0) {
+            const unsigned qb = (unsigned)std::max<int64_t>(1, std::min<int64_t>((Q * stride + 255) / 256, 16 * (int64_t)num_sms));
+            join_query_rows_kernel<<<std::max(1u, std::min(qb, (unsigned)((2 * Q + 255) / 256))), 256, 0, st>>>(dr.Current(), n, query, 2 * Q, xq);
+            walk_join_kernel<<<qb, 256, 0, st>>>(walks, stride, dk.Current(), dv.Current(), off, xq, Q, out);
+            count_launch(2);
+            JK(cudaGetLastError());
+            if (out != out_hd) JK(cudaMemcpyAsync(out_hd, out, (size_t)4 * Q * stride * 4, cudaMemcpyDeviceToHost, st));
+            if (xq_hd && xq != xq_hd) JK(cudaMemcpyAsync(xq_hd, xq, (size_t)2 * Q * 4, cudaMemcpyDeviceToHost, st));
+        }
+        JK(cudaStreamSynchronize(st));
+    }
+done:
+#undef JK
+    dfree(d_walks, st); dfree(d_ids, st); dfree(d_query, st); dfree(d_out, st); dfree(d_xq, st); dfree(d_off, st);
+    dfree(k_a, st); dfree(k_b, st); dfree(v_a, st); dfree(v_b, st); dfree(r_a, st); dfree(r_b, st); dfree(tmp, st);
+    return rc;
 }
 
 int walkset_info_impl(const WalkSet *w, int64_t *n, int64_t *T, int32_t *M, int32_t *ncol, uint32_t *status) {

@@ -132,11 +132,41 @@ def walk_sampler(ptr, neighs, query, num_walks=100, num_steps=3, nthread=-1, see
     return [walks, obj]
 
 
-def walk_join(*args, **kwargs):
-    """SUREL-v1 walk joining (subg_acc.c:509-647): no caller in the reference; out of scope."""
-    raise NotImplementedError("walk_join (SUREL v1) is out of scope of the B200 hot path")
+def walk_join(walk, key, query, nthread=-1, return_idx=-1, device="cuda"):
+    """SUREL-v1 walk joining (subg_acc.c:509-647): for every query (u, v) and every walk position, the index of
+    the visited node in the concatenated key sets, looked up in the set of u and in the set of v.
+    walk: int32 [n, stride] (or [n, M, m+1]); key: sequence of n node-id arrays (walk_sampler's obj[:,0]);
+    query: int [Q, 2].  Returns int32 [2, Q*2*stride], and [that, xq int32 [Q,2]] when return_idx is truthy (the
+    reference parses it with the 'p' predicate format; left at its default -1 the index is not returned)."""
+    import ctypes as C
+    from .spg import _dev_index, _stream
+    try:
+        walk = np.ascontiguousarray(np.asarray(walk), dtype=np.int32)
+        if walk.ndim < 2:
+            raise ValueError("walk must be at least 2-D")
+        n = walk.shape[0]
+        stride = int(walk.shape[1] * walk.shape[2]) if walk.ndim > 2 else int(walk.shape[1])   # subg_acc.c:529-530
+        keys = [np.asarray(k).astype(np.int32, copy=False).ravel() for k in key]
+        q = np.ascontiguousarray(np.asarray(query), dtype=np.int32)
+    except Exception as e:
+        raise TypeError("Input parsing error.\n") from e
+    if len(keys) != n:
+        raise AssertionError("Dims do not match between num of walks and keys.\n")                # subg_acc.c:536-540
+    off = np.zeros(n + 1, np.int64)
+    np.cumsum([len(k) for k in keys], out=off[1:])
+    ids = np.ascontiguousarray(np.concatenate(keys)) if n else np.zeros(0, np.int32)
+    Q = q.shape[0]
+    out = np.empty((2, Q * 2 * stride), np.int32)
+    xq = np.empty(q.shape, np.int32)
+    dev = _dev_index(device)
+    _capi.check(_capi.load().subg_walk_join(walk.ctypes.data, n, stride, off.ctypes.data, ids.ctypes.data, q.ctypes.data, Q,
+                                            out.ctypes.data, xq.ctypes.data, dev, _stream(dev)))
+    want = bool(return_idx) and not (isinstance(return_idx, (int, np.integer)) and not isinstance(return_idx, bool) and return_idx == -1)
+    return [out, xq] if want else out
 
 
 def batch_sampler(*args, **kwargs):
-    """Serial mini-batch node sampler (subg_acc.c:391-507): no caller in the reference; out of scope."""
+    """Serial mini-batch node sampler (subg_acc.c:391-507): no caller in the reference, every seed's early exit
+    depends on the running size of one shared node set, and the stream is seeded with seed + getpid()
+    (subg_acc.c:423), i.e. not reproducible; out of scope."""
     raise NotImplementedError("batch_sampler is out of scope of the B200 hot path")

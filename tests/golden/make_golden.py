@@ -195,6 +195,12 @@ def gen_walks(out):
         out[f"walk{ci}_off"] = np.concatenate([[0], np.cumsum(sizes)])
         out[f"walk{ci}_ids"] = np.concatenate([obj[i, 0] for i in range(len(query))])
         out[f"walk{ci}_rpe"] = np.vstack([obj[i, 1] for i in range(len(query))])
+        if ci in (1, 2):  # walk_join of the reference on these walks (subg_acc.c:509-647)
+            rng = np.random.default_rng(10 + ci)
+            qq = query[rng.integers(0, len(query), (120, 2))].astype(np.int32)
+            qq[0] = [query[0], query[0]]
+            joined, xq = subg.walk_join(walks, list(obj[:, 0]), qq, return_idx=True)
+            out[f"walk{ci}_join_query"], out[f"walk{ci}_join_out"], out[f"walk{ci}_join_xq"] = qq, joined, xq
 
 
 def main():

@@ -128,3 +128,40 @@ def test_rw_matrix_matches_reference_formulation(small_graph):
     ez = sp.csr_matrix((inv + 1, (rows, np.concatenate([obj[i, 0] for i in range(n)]))), (n, n))
     assert (z != ez).nnz == 0
     assert np.array_equal(freqs, np.insert(fr[first], 0, np.zeros((1, K)), axis=0))
+
+
+def test_walk_join_bit_exact(mid_graph):
+    """SUREL-v1 walk_join (subg_acc.c:509-647) on the device == oracle, incl. u == v, 3-D walk input and a query
+    node that is not a root (-1 row)."""
+    from surel_plus_b200 import subg_acc
+    A = mid_graph
+    rng = np.random.default_rng(2)
+    q = rng.permutation(A.shape[0])[:900].astype(np.int32)
+    M, m = 40, 3
+    walks, obj = subg_acc.walk_sampler(A.indptr, A.indices, q, num_walks=M, num_steps=m, nthread=1, seed=4, replacement=True)
+    qq = q[rng.integers(0, len(q), (500, 2))].astype(np.int32)
+    qq[0] = [q[0], q[0]]
+    out, xq = subg_acc.walk_join(walks, list(obj[:, 0]), qq, return_idx=True)
+    e_out, e_xq = po.walk_join(walks, list(obj[:, 0]), qq, return_idx=True)
+    assert out.dtype == np.int32 and out.shape == (2, 500 * 2 * M * (m + 1))
+    assert np.array_equal(out, e_out) and np.array_equal(xq, e_xq)
+    out3 = subg_acc.walk_join(walks.reshape(len(q), M, m + 1), list(obj[:, 0]), qq)
+    assert isinstance(out3, np.ndarray) and np.array_equal(out3, e_out)
+    # a node that is no root: documented -1 entries, identical in the oracle
+    missing = np.setdiff1d(np.arange(A.shape[0]), q)[:1].astype(np.int32)
+    qm = np.array([[q[1], missing[0]], [missing[0], q[2]]], np.int32)
+    om, xm = subg_acc.walk_join(walks, list(obj[:, 0]), qm, return_idx=True)
+    eo, ex = po.walk_join(walks, list(obj[:, 0]), qm, return_idx=True)
+    assert np.array_equal(om, eo) and np.array_equal(xm, ex) and xm[0, 1] == -1 and xm[1, 0] == -1
+    with pytest.raises(AssertionError):
+        subg_acc.walk_join(walks, list(obj[:-1, 0]), qq)
+
+
+def test_walk_join_matches_reference_fixture(small_graph):
+    from surel_plus_b200 import subg_acc
+    gold = np.load(os.path.join(GOLD, "walks.npz"))
+    for ci in (1, 2):
+        walks, off, ids = gold[f"walk{ci}_walks"], gold[f"walk{ci}_off"], gold[f"walk{ci}_ids"]
+        keys = [ids[off[i]:off[i + 1]] for i in range(len(off) - 1)]
+        out, xq = subg_acc.walk_join(walks, keys, gold[f"walk{ci}_join_query"], return_idx=True)
+        assert np.array_equal(out, gold[f"walk{ci}_join_out"]) and np.array_equal(xq, gold[f"walk{ci}_join_xq"])

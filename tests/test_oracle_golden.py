@@ -201,3 +201,13 @@ def test_rpe_invariants_on_golden(walks_gold):
         seg = np.add.reduceat(rpe, off[:-1], axis=0)
         assert np.all(seg == M), ci
         assert np.all(rpe[off[:-1], 0] == M), ci
+
+
+def test_walk_join_equals_reference(walks_gold):
+    """orc_walk_join == reference walk_join (subg_acc.c:509-647) on the reference's own walks and key sets."""
+    for ci in (1, 2):
+        walks, off, ids = walks_gold[f"walk{ci}_walks"], walks_gold[f"walk{ci}_off"], walks_gold[f"walk{ci}_ids"]
+        keys = [ids[off[i]:off[i + 1]] for i in range(len(off) - 1)]
+        out, xq = po.walk_join(walks, keys, walks_gold[f"walk{ci}_join_query"], return_idx=True)
+        assert out.dtype == np.int32 and np.array_equal(out, walks_gold[f"walk{ci}_join_out"]), ci
+        assert np.array_equal(xq, walks_gold[f"walk{ci}_join_xq"]), ci

@@ -133,3 +133,17 @@ def test_walk_sampler_vs_compiled_reference(subg, mid_graph, M, m, rep, seed):
     assert np.array_equal(walks, o_walks)
     for i in range(len(q)):
         assert np.array_equal(obj[i, 0], o_obj[i, 0]) and np.array_equal(obj[i, 1], o_obj[i, 1]), i
+
+
+@pytest.mark.parametrize("M,m,rep", [(50, 3, True), (20, 2, -1)])
+def test_walk_join_vs_compiled_reference(subg, mid_graph, M, m, rep):
+    A = mid_graph
+    rng = np.random.default_rng(M)
+    q = rng.permutation(A.shape[0])[:700].astype(np.int32)
+    indptr, indices = A.indptr.astype(np.int32), A.indices.astype(np.int32)
+    kw = {} if rep == -1 else {"replacement": rep}
+    walks, obj = subg.walk_sampler(indptr, indices, q, num_walks=M, num_steps=m, nthread=1, seed=1, **kw)
+    qq = q[rng.integers(0, len(q), (400, 2))].astype(np.int32)
+    out, xq = subg.walk_join(walks, list(obj[:, 0]), qq, return_idx=True)
+    o_out, o_xq = po.walk_join(walks, list(obj[:, 0]), qq, return_idx=True)
+    assert np.array_equal(out, o_out) and np.array_equal(xq, o_xq)
