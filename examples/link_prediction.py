@@ -79,11 +79,42 @@ def hits_at_k(pos, neg, k=50):
     return float((pos > kth).float().mean())
 
 
-def run(G_obs, pos_tr, pos_te, neg_te, rng_mode, args, model_seed):
+def numpy_walks(G, M, m, seed):
+    """The reference's sampling law (subg_acc.c:763-809) written independently with numpy's PCG64: first hop without
+    replacement (w % d if d <= M, else M distinct neighbours), later hops uniform; walks[n, M, m]."""
+    rng = np.random.default_rng(seed)
+    indptr, indices = G.indptr.astype(np.int64), G.indices
+    n = G.shape[0]
+    deg = np.diff(indptr)
+    off = np.arange(M)[None, :] % np.maximum(deg, 1)[:, None]
+    for u in np.where(deg > M)[0]:
+        off[u] = rng.choice(deg[u], M, replace=False)
+    cur = np.where(deg[:, None] > 0, indices[np.minimum(indptr[:-1, None] + off, len(indices) - 1)], np.arange(n)[:, None])
+    walks = np.empty((n, M, m), np.int32)
+    walks[:, :, 0] = cur
+    for s in range(1, m):
+        d = deg[cur]
+        pick = np.minimum((rng.random(cur.shape) * d).astype(np.int64), np.maximum(d - 1, 0))
+        nxt = indices[np.minimum(indptr[cur] + pick, len(indices) - 1)]
+        cur = np.where(d > 0, nxt, cur)
+        walks[:, :, s] = cur
+    return walks
+
+
+def run(G_obs, pos_tr, pos_te, neg_te, rng_mode, args, model_seed, sample_seed):
     dev = "cuda:0"
     t0 = time.perf_counter()
-    z, enc = subg_matrix(G_obs, np.arange(G_obs.shape[0]), num_walks=args.num_walks, num_steps=args.num_steps,
-                         device=dev, seed=111413, rng_mode=rng_mode)
+    if rng_mode == _capi.SUBG_RNG_TRACE:
+        from surel_plus_b200 import DeviceGraph, SpG
+        g = DeviceGraph.from_scipy(G_obs, dev)
+        z = SpG.sample(g, np.arange(G_obs.shape[0]), num_walks=args.num_walks, num_steps=args.num_steps - 1,
+                       rng_mode=rng_mode, walks=numpy_walks(G_obs, args.num_walks, args.num_steps - 1, sample_seed),
+                       first_visit_ranks=False)
+        enc = z.enc_table()
+        g.close()
+    else:
+        z, enc = subg_matrix(G_obs, np.arange(G_obs.shape[0]), num_walks=args.num_walks, num_steps=args.num_steps,
+                             device=dev, seed=sample_seed, rng_mode=rng_mode)
     xpe = torch.from_numpy(enc).to(dev).float() / args.num_walks                  # main.py:174
     t_prep = time.perf_counter() - t0
     torch.manual_seed(model_seed)
@@ -128,6 +159,7 @@ def main():
     ap.add_argument("--aggr", default="mean", choices=["mean", "attn"])
     ap.add_argument("--communities", type=int, default=400)
     ap.add_argument("--model-seeds", type=int, default=3)
+    ap.add_argument("--sample-seeds", type=int, default=4)
     args = ap.parse_args()
     # heavy-tailed background (30 % of the edges) + planted communities (70 %): held-out edges are then predictable
     # from the structure around their endpoints, which is what the LP features encode
@@ -155,16 +187,25 @@ def main():
           f"num_steps={args.num_steps}; Net hidden={args.hidden} aggr={args.aggr}; {args.steps} steps of {args.batch}+{args.batch}")
     res = {}
     for name, mode in (("rand_r replay (the reference's nthread=1 stream, bit-identical arrays)", _capi.SUBG_RNG_RAND_R),
-                       ("philox (fast path)", _capi.SUBG_RNG_PHILOX)):
+                       ("philox (fast path)", _capi.SUBG_RNG_PHILOX),
+                       ("numpy PCG64 walks fed as traces (independent statement of the sampling law)", _capi.SUBG_RNG_TRACE)):
         hs = []
-        for ms in range(args.model_seeds):
-            h50, loss, t_prep = run(G_obs, pos_tr, pos_te, neg_te, mode, args, ms)
-            hs.append(h50)
-            print(f"  {name}: model seed {ms}: Hits@50 = {h50:.4f}  final loss {loss:.4f}  prep {t_prep * 1e3:.0f} ms", flush=True)
+        for ss in range(args.sample_seeds):          # one sampled SpG per sampling seed ...
+            for ms in range(args.model_seeds):       # ... and several model initialisations / batch orders on it
+                h50, loss, t_prep = run(G_obs, pos_tr, pos_te, neg_te, mode, args, ms, 111413 + ss)
+                hs.append(h50)
+                print(f"  {name}: sampling seed {111413 + ss} model seed {ms}: Hits@50 = {h50:.4f}  final loss {loss:.4f}  "
+                      f"prep {t_prep * 1e3:.0f} ms", flush=True)
         res[name] = hs
-    (a, ha), (b, hb) = res.items()
-    print(f"Hits@50 mean +- std over model seeds: reference stream {np.mean(ha):.4f} +- {np.std(ha):.4f}, "
-          f"philox {np.mean(hb):.4f} +- {np.std(hb):.4f}, difference {abs(np.mean(ha) - np.mean(hb)):.4f}")
+    names = list(res)
+    print(f"Hits@50 over {len(res[names[0]])} runs each (sampling seeds x model seeds):")
+    for nm in names:
+        print(f"  {np.mean(res[nm]):.4f} +- {np.std(res[nm], ddof=1):.4f}  {nm}")
+    for i in range(len(names)):
+        for j in range(i + 1, len(names)):
+            ha, hb = res[names[i]], res[names[j]]
+            se = float(np.sqrt(np.var(ha, ddof=1) / len(ha) + np.var(hb, ddof=1) / len(hb)))
+            print(f"  difference of the means [{j}] - [{i}]: {np.mean(hb) - np.mean(ha):+.4f} (standard error {se:.4f})")
 
 
 if __name__ == "__main__":

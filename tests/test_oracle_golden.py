@@ -211,3 +211,20 @@ def test_walk_join_equals_reference(walks_gold):
         out, xq = po.walk_join(walks, keys, walks_gold[f"walk{ci}_join_query"], return_idx=True)
         assert out.dtype == np.int32 and np.array_equal(out, walks_gold[f"walk{ci}_join_out"]), ci
         assert np.array_equal(xq, walks_gold[f"walk{ci}_join_xq"]), ci
+
+
+def test_rand_r_low_bits_cycle():
+    """Documents why the Philox path is checked against the sampling LAW and not against the reference stream
+    alone ('Parity of the fast path'): glibc rand_r is a 32-bit LCG whose output modulo a power of two is
+    state bits 16..18 of every third step -- short cycles, so consecutive draws are far MORE evenly spread than
+    independent draws would be (chi-square of the pair histogram ~ 0 instead of ~ its degrees of freedom)."""
+    from scipy.stats import chi2
+    x = po.rand_r_stream(111413, 300_000)
+    for a in (4, 8, 16):
+        cnt = np.bincount((x[:-1] % a) * a + (x[1:] % a), minlength=a * a).astype(float)
+        exp = (len(x) - 1) / (a * a)
+        stat = ((cnt - exp) ** 2 / exp).sum()
+        assert chi2.cdf(stat, a * a - 1) < 2e-3, (a, stat)      # under-dispersed: an independent stream fails this
+    cnt = np.bincount((x[:-1] % 11) * 13 + (x[1:] % 13), minlength=143).astype(float)   # other moduli look fine
+    stat = ((cnt - (len(x) - 1) / 143) ** 2 / ((len(x) - 1) / 143)).sum()
+    assert 0.001 < chi2.cdf(stat, 142) < 0.999
