@@ -26,7 +26,7 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    per = 142_000_000  # int32 entries per rank (ppa shard at world 2)
+    per = 284_000_000 // world  # int32 entries per rank (ppa shard)
     mine = per + 1000 * rank
     counts = [per + 1000 * r for r in range(world)]
     local_t = torch.full((mine,), rank, dtype=torch.int32, device="cuda")
@@ -51,7 +51,7 @@ def main():
     t_p2p = timeit(p2p)
     if rank == 0:
         gb = per * 4 * (world - 1) / 1e9
-        print(f"[nccl probe] world={world} {gb:.2f} GB received per GPU: all_gather(list, uneven)={t_uneven:.2f} ms ({gb / t_uneven * 1e3:.0f} GB/s), "
+        print(f"[nccl probe] world={world} env={ {k: v for k, v in os.environ.items() if k.startswith('NCCL_') and 'FILE' not in k} } {gb:.2f} GB received per GPU: all_gather(list, uneven)={t_uneven:.2f} ms ({gb / t_uneven * 1e3:.0f} GB/s), "
               f"all_gather_into_tensor={t_equal:.2f} ms ({gb / t_equal * 1e3:.0f} GB/s), all_gather(list, equal)={t_list_equal:.2f} ms, "
               f"send/recv={t_p2p:.2f} ms ({gb / t_p2p * 1e3:.0f} GB/s)", flush=True)
     dist.destroy_process_group()
