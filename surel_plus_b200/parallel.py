@@ -3,14 +3,15 @@ HBM, seeds range-partitioned, SpG shards all-gathered once (NCCL over NVLink/NVS
 then joined locally on the replicated SpG.  The reference has no
 distributed code at all; this is the B200 scaling path of the same operators.
 
-Exchange step (the only collectives on the path):
-  1. all-gather of the shard sizes (n_r, T_r, c_r);
-  2. all-gather of the per-shard unique LP tables (c_r x ncol int16, KBs) -> every rank merges
-     them in rank order, which reproduces the first-occurrence order of the single-process scan
-     (subg_acc.c:957-978) because shards are contiguous seed ranges; local LP ids are re-labelled
-     on the device (subg_spg_set_lp_table);
-  3. variable-size all-gather of nsize / indices / data (8 B per set entry) straight into the
-     slices of the final arrays.
+Exchange step (the only collectives on the path; `sharded_sample`):
+  1. one small equal-size all-gather with every rank's sizes (n_r, T_r, c_r, status) and its unique LP table
+     (c_r x ncol int16, KBs) -> every rank merges the tables in rank order, which reproduces the
+     first-occurrence order of the single-process scan (subg_acc.c:957-978) because shards are contiguous seed
+     ranges; local LP ids are re-labelled on the device (subg_spg_set_lp_table);
+  2. the full SpG is allocated once (subg_spg_alloc) and nsize / indices / data of every peer (8 B per set entry)
+     are received straight into their slices in ONE NCCL group of sends and receives; subg_spg_seal derives the
+     row pointer on the device.
+`assemble_shards` is the same exchange on plain tensors with staged all-gathers (any backend).
 The host-side logic below is device-agnostic (it is exercised with gloo on CPU tensors in
 tests/test_parallel_gloo.py); the sampling itself is CUDA only.
 """
@@ -128,6 +129,30 @@ def all_gather_varlen(local: torch.Tensor, counts: np.ndarray, out: torch.Tensor
     return out
 
 
+_LP_INLINE_ROWS = 4096  # unique LP rows of a shard that travel with the sizes in the first (small) all-gather
+
+
+def _p2p_ops(local: torch.Tensor, counts: np.ndarray, out: torch.Tensor, group=None) -> list:
+    """Send / recv operations that put every rank's `local` rows into its slice of `out` (byte views; the own slice
+    is copied locally).  The caller batches the operations of several arrays into ONE NCCL group."""
+    world, rank, _ = _group_info(group)
+    offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    ob = out.reshape(out.shape[0], -1).view(torch.uint8) if out.shape[0] else out.reshape(0, 1).view(torch.uint8)
+    lb = local.contiguous().reshape(local.shape[0], -1).view(torch.uint8) if local.shape[0] else ob[:0]
+    if counts[rank]:
+        ob[offs[rank]:offs[rank + 1]].copy_(lb)
+    ops = []
+    for r in range(world):
+        if r == rank:
+            continue
+        peer = r if group is None else dist.get_global_rank(group, r)
+        if counts[rank]:
+            ops.append(dist.P2POp(dist.isend, lb, peer, group))
+        if counts[r]:
+            ops.append(dist.P2POp(dist.irecv, ob[offs[r]:offs[r + 1]], peer, group))
+    return ops
+
+
 def assemble_shards(nsize: torch.Tensor, indices: torch.Tensor, data: torch.Tensor, enc: torch.Tensor,
                     relabel: Optional[Callable[[np.ndarray, np.ndarray], torch.Tensor]] = None, group=None) -> dict:
     """The exchange step on plain tensors.  Inputs are this rank's shard: nsize int32 [n_r],
@@ -202,41 +227,50 @@ def sharded_sample(graph, query, num_walks=100, num_steps=3, bucket=-1, seed=111
     ncol = num_steps + 1
     enc_local = v["enc"] if "enc" in v else torch.zeros((0, ncol), dtype=torch.int16, device=dev)
     nsize_local = v["nsize"] if "nsize" in v else torch.zeros(0, dtype=torch.int32, device=dev)
-    counts = all_gather_sizes([shard.n, shard.T, shard.c, shard.status], dev, group)
+    # (1) ONE small equal-size all-gather carries every rank's sizes AND its unique LP table (a few hundred to a few
+    # thousand int16 rows; _LP_INLINE_ROWS of them ride along, a larger table falls back to a second exchange)
+    row_b = 2 * ncol
+    blob = torch.zeros(32 + _LP_INLINE_ROWS * row_b, dtype=torch.uint8, device=dev)
+    blob[:32] = torch.tensor([shard.n, shard.T, shard.c, shard.status], dtype=torch.int64).view(torch.uint8).to(dev)
+    c_in = min(shard.c, _LP_INLINE_ROWS)
+    if c_in:
+        blob[32:32 + c_in * row_b] = enc_local[:c_in].contiguous().view(torch.uint8).reshape(-1)
+    blobs = torch.empty((world, blob.numel()), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(blobs, blob, group=group)
+    hb = blobs.cpu().numpy()
+    counts = hb[:, :32].copy().view(np.int64).reshape(world, 4)
     n_r, T_r, c_r = counts[:, 0], counts[:, 1], counts[:, 2]
     n_tot, T_tot = int(n_r.sum()), int(T_r.sum())
-    # the full SpG is allocated once and every rank's shard lands in place (no staging copy)
+    mark("sizes + LP tables")
+    if int(c_r.max()) <= _LP_INLINE_ROWS:
+        tables = [hb[r, 32:32 + int(c_r[r]) * row_b].copy().view(np.int16).reshape(int(c_r[r]), ncol) for r in range(world)]
+    else:
+        enc_all = torch.empty((int(c_r.sum()), ncol), dtype=torch.int16, device=dev)
+        all_gather_varlen(enc_local.contiguous(), c_r, enc_all, group)
+        enc_np = enc_all.cpu().numpy()
+        offs = np.concatenate([[0], np.cumsum(c_r)])
+        tables = [enc_np[offs[r]:offs[r + 1]] for r in range(world)]
+    merged, maps = merge_lp_tables(tables)
+    merged = np.ascontiguousarray(merged, dtype=np.int16)
+    mark("lp merge")
+    # (2) this rank's ids become global ids, the full SpG is allocated once and every shard lands in place
+    _capi.check(lib.subg_spg_set_lp_table(shard._h, _ptr(maps[rank]), _ptr(merged), merged.shape[0], -1, st))
+    mark("relabel")
     fh = C.c_void_p()
-    mark("sizes")
     _capi.check(lib.subg_spg_alloc(n_tot, T_tot, graph.device, st, C.byref(fh)))
-    mark("alloc")
     try:
         p = [C.c_void_p() for _ in range(6)]
         _capi.check(lib.subg_spg_views(fh, st, *[C.byref(x) for x in p]))
         g_indices = _view(p[1].value, (T_tot,), "<i4", graph.device, None)
         g_data = _view(p[2].value, (T_tot,), "<i4", graph.device, None)
         g_nsize = _view(p[5].value, (n_tot,), "<i4", graph.device, None)
-        # node ids and set sizes do not depend on the LP relabelling: their all-gathers run on NCCL's stream while
-        # the LP tables are merged on the host and this rank's ids are relabelled
-        works = [all_gather_varlen(nsize_local, n_r, g_nsize, group, async_op=True),
-                 all_gather_varlen(v["indices"], T_r, g_indices, group, async_op=True)]
-        mark("gather nsize+indices")
-        enc_all = torch.empty((int(c_r.sum()), ncol), dtype=torch.int16, device=dev)
-        all_gather_varlen(enc_local.contiguous(), c_r, enc_all, group)
-        enc_np = enc_all.cpu().numpy()
-        offs = np.concatenate([[0], np.cumsum(c_r)])
-        merged, maps = merge_lp_tables([enc_np[offs[r]:offs[r + 1]] for r in range(world)])
-        merged = np.ascontiguousarray(merged, dtype=np.int16)
-        id_map = maps[rank]
-        mark("lp merge")
-        _capi.check(lib.subg_spg_set_lp_table(shard._h, _ptr(id_map), _ptr(merged), merged.shape[0], -1, st))
-        mark("relabel")
-        works.append(all_gather_varlen(v["data"], T_r, g_data, group, async_op=True))
-        for w in works:
-            for one in (w if isinstance(w, (list, tuple)) else [w]):
-                if one is not None and not isinstance(one, torch.Tensor):
-                    one.wait()
-        mark("gather data")
+        # (3) one NCCL group: set sizes, node ids and LP ids of every peer (grouped send / recv over NVLink)
+        ops = []
+        for local, cnt, out in ((nsize_local, n_r, g_nsize), (v["indices"], T_r, g_indices), (v["data"], T_r, g_data)):
+            ops += _p2p_ops(local, cnt, out, group)
+        for w in (dist.batch_isend_irecv(ops) if ops else []):
+            w.wait()
+        mark("shards")
         _capi.check(lib.subg_spg_seal(fh, st))
         _capi.check(lib.subg_spg_set_lp_table(fh, None, _ptr(merged), merged.shape[0], ncol, st))
         mark("seal")
