@@ -384,10 +384,13 @@ def bench_spjoin(args, torch, dev, spg, A, M, k, gather, _capi, peaks, barrier, 
     _capi.timing_read(1)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = max(args.steps, 1) * 8
+    reps = max(args.steps, 1) * 40     # ~50 ms of work: one scheduling hiccup of the host must not decide the number
+    per_call = []
     e0.record()
     for i in range(reps):
-        xz, ptr = gather(dev_batches[i % nb], spg, dev, True, xpe)
+        t_call = time.perf_counter()
+        xz, ptr = gather(dev_batches[i % nb], spg, dev, True, xpe)     # returns after its one stream synchronisation
+        per_call.append(time.perf_counter() - t_call)
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
@@ -409,6 +412,7 @@ def bench_spjoin(args, torch, dev, spg, A, M, k, gather, _capi, peaks, barrier, 
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     return {"value": world * B * reps / (ms / 1e3), "unit": "queries/s", "batch": B, "output": f"float32 [N,2,{kdim}] fused LP lookup",
             "avg_rows_per_batch": rows_avg, "avg_set_size": rows_avg / (2 * B), "ms_per_batch": ms / reps,
+            "ms_per_batch_median": float(np.median(per_call)) * 1e3, "ms_per_batch_max": float(np.max(per_call)) * 1e3, "calls": reps,
             "e2e": {"value": world * B * reps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": 16 * B, "d2h_bytes_per_step": 12},
             "roofline": {"bound": "hbm", "kernel": "spjoin_kernel", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": ach / peaks["hbm_gbs"], "traffic": load_traffic("spjoin", args),

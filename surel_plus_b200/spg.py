@@ -8,6 +8,7 @@ in place (surel_plus_b200/train.py).
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -54,7 +55,7 @@ class _PinnedPool:
     numpy array built over it (and every view of it) is garbage collected.  Blocks are 12.5 % larger than
     asked so that the next call, whose sizes differ slightly, still fits."""
 
-    def __init__(self, keep_bytes: int = 16 << 30):
+    def __init__(self, keep_bytes: int = int(os.environ.get("SUBG_PINNED_POOL_BYTES", 6 << 30))):
         self._free: list[tuple[int, int]] = []  # (capacity, address)
         self._keep = keep_bytes
         self._lib = None
