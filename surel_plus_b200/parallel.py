@@ -18,6 +18,9 @@ tests/test_parallel_gloo.py); the sampling itself is CUDA only.
 from __future__ import annotations
 
 import ctypes as C
+import os
+import sys
+import time
 from typing import Callable, List, Optional, Tuple
 
 import numpy as np
@@ -213,15 +216,14 @@ def sharded_sample(graph, query, num_walks=100, num_steps=3, bucket=-1, seed=111
     st = _stream(graph.device)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     ev[0].record()
-    import os as _os, sys as _sys, time as _time
-    prof = _os.environ.get("SUBG_PROFILE_HOST") is not None
-    marks, t_last = [], _time.perf_counter()
+    prof = os.environ.get("SUBG_PROFILE_HOST") is not None   # per-phase host times (adds a device sync per phase)
+    marks, t_last = [], time.perf_counter()
 
     def mark(name):
         nonlocal t_last
         if prof:
             torch.cuda.synchronize()
-            t = _time.perf_counter()
+            t = time.perf_counter()
             marks.append(f"{name}={1e3 * (t - t_last):.2f}")
             t_last = t
     ncol = num_steps + 1
@@ -275,7 +277,7 @@ def sharded_sample(graph, query, num_walks=100, num_steps=3, bucket=-1, seed=111
         _capi.check(lib.subg_spg_set_lp_table(fh, None, _ptr(merged), merged.shape[0], ncol, st))
         mark("seal")
         if prof and rank == 0:
-            print("[subg host ms] exchange: " + " ".join(marks), file=_sys.stderr, flush=True)
+            print("[subg host ms] exchange: " + " ".join(marks), file=sys.stderr, flush=True)
     except Exception:
         lib.subg_spg_free(fh)
         raise
