@@ -75,6 +75,10 @@ def _join(edge, x, device, arity, encode=None, want_segid=False, want_ptr=True):
     else:
         shape_tail, dtype, k = (2,), torch.int32, 0
     tptr = table.data_ptr() if table is not None else None
+    if B == 0:  # nothing to join: empty rows, a single segment pointer
+        indptr.zero_()
+        return (torch.empty((0,) + shape_tail, dtype=dtype, device=tdev), indptr,
+                torch.empty(0, dtype=torch.int64, device=tdev) if want_segid else None)
     N = C.c_int64(0)
     rate = getattr(spg, "_rows_per_seg", None)
     out = segid = None

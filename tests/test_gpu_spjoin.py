@@ -114,3 +114,36 @@ def test_bad_query_raises(lp_spg):
     spg, z, xpe = lp_spg
     with pytest.raises(TypeError):
         gather(np.array([[0], [z.shape[0] + 5]]), spg, "cuda", True, xpe)
+
+
+def test_fused_call_falls_back_when_the_estimate_is_too_small(mid_graph):
+    """subg_spjoin sizes the output from the rows per segment seen so far; a batch that outgrows it must take the
+    exact two-step route and give the same rows (first: isolated nodes, sets of size 1; then the hubs)."""
+    from surel_plus_b200 import DeviceGraph, SpG, gather
+    A = mid_graph
+    n = A.shape[0]
+    g = DeviceGraph.from_scipy(A)
+    spg = SpG.sample(g, np.arange(n), 60, 2, seed=3, first_visit_ranks=False)
+    z = spg.to_scipy()
+    xpe = torch.from_numpy(spg.enc_table()).float().cuda() / 60
+    tiny = np.full((2, 2048), n - 1)                       # isolated node: one row per segment
+    gather(tiny, spg, "cuda", True, xpe)
+    gather(tiny, spg, "cuda", True, xpe)                   # second call runs fused with a capacity of ~1.25 rows / segment
+    assert spg._rows_per_seg == 1.0
+    hubs = np.stack([np.arange(2048) % 50, (np.arange(2048) * 7) % 50])   # the largest sets
+    exz, sl, sr = po.spjoin_pair(z, hubs)
+    xz, ptr = gather(hubs, spg, "cuda", True, xpe)
+    assert xz.shape[0] == len(exz) > 10 * 4096
+    assert torch.equal(xz.cpu(), xpe.cpu()[torch.from_numpy(exz).long()])
+    assert np.array_equal(ptr.cpu().numpy(), po.pair_index(sl, sr, True))
+    xz2, ptr2 = gather(hubs, spg, "cuda", True, xpe)       # now the estimate fits: fused route, same result
+    assert torch.equal(xz2, xz) and torch.equal(ptr2, ptr)
+
+
+def test_empty_batch(lp_spg):
+    from surel_plus_b200 import gather, hgather
+    spg, z, xpe = lp_spg
+    xz, ptr = gather(np.zeros((2, 0), np.int64), spg, "cuda", True, xpe)
+    assert tuple(xz.shape) == (0, 2, xpe.shape[1]) and ptr.cpu().tolist() == [0]
+    xz, ind = hgather(np.zeros((3, 0), np.int64), spg, "cuda", xpe)
+    assert xz.shape[0] == 0 and ind.numel() == 0
