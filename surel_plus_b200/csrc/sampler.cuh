@@ -35,7 +35,6 @@ constexpr uint32_t kStatusTableFull = 1u << 31;  // internal status bits
 constexpr uint32_t kStatusBadSeed = 1u << 30;
 constexpr int kFirstHopCap = 1000000;  // NEBMAX, subg_acc.c:13,750
 constexpr int kGW = 8;                 // walks advanced together per lane
-constexpr int kTicketBatch = 1;        // consecutive seeds a warp takes per ticket atomic
 constexpr int kCtrCursor = 16, kCtrTotal = 32, kCtrWords = 48;
 
 struct SamplerArgs {
@@ -159,21 +158,26 @@ __device__ __forceinline__ void lane_sort(K (&k)[EPL]) {
 }
 
 // Sorts the 32*EPL keys of a warp ascending.  In: lane L holds elements [L*EPL, (L+1)*EPL) of any
-// order.  Out: the same blocked layout, globally sorted.  buf: 32*EPL keys of shared memory owned by
-// the warp.  Keys are distinct except for the ~0 padding.
+// order.  Out: the same blocked layout, globally sorted.  buf: 32*EPL + 32 keys of shared memory owned by
+// the warp.  Keys are distinct except for the padding (~0 - 1); ~0 itself never occurs in the data: it is the
+// sentinel that follows every run in shared memory, so the serial merge reads without bounds tests (an exhausted
+// run presents ~0, which loses against every key including the padding).
 template <typename K, int EPL>
 __device__ __forceinline__ void warp_merge_sort(K (&k)[EPL], K *buf, int lane) {
     constexpr K SENT = ~(K)0;
     lane_sort<K, EPL>(k);
 #pragma unroll 1
     for (int r = 0; r < 5; r++) {
+        const int L = EPL << r;                  // run length; run q occupies buf[q * (L + 1) ..] + one sentinel slot
+        const int own = lane * EPL + (lane >> r);
 #pragma unroll
-        for (int j = 0; j < EPL; j++) buf[lane * EPL + j] = k[j];
+        for (int j = 0; j < EPL; j++) buf[own + j] = k[j];
+        if ((lane & ((1 << r) - 1)) == (1 << r) - 1) buf[own + EPL] = SENT;  // last lane of its run
         __syncwarp();
-        const int L = EPL << r;                  // run length
         const int t = lane & ((2 << r) - 1);     // lane index inside the pair of runs
-        const K *A = buf + (lane - t) * EPL;
-        const K *B = A + L;
+        const int a0 = (lane - t) * EPL + ((lane - t) >> r);   // first key of run A; run B starts L + 1 later
+        const K *A = buf + a0;
+        const K *B = A + L + 1;
         const int diag = t * EPL;
         int lo = diag > L ? diag - L : 0;
         int hi = diag < L ? diag : L;
@@ -182,12 +186,10 @@ __device__ __forceinline__ void warp_merge_sort(K (&k)[EPL], K *buf, int lane) {
             if (A[mid] <= B[diag - 1 - mid]) lo = mid + 1;
             else hi = mid;
         }
-        // serial merge of this lane's EPL outputs; pa / pb index buf, the runs end at ea / eb
-        const int base = (lane - t) * EPL;
-        int pa = base + lo, pb = base + L + diag - lo;
-        const int ea = base + L, eb = base + 2 * L;
-        K ka = pa < ea ? buf[pa] : SENT;
-        K kb = pb < eb ? buf[pb] : SENT;
+        // serial merge of this lane's EPL outputs; pa / pb index buf
+        int pa = a0 + lo, pb = a0 + L + 1 + diag - lo;
+        K ka = buf[pa];
+        K kb = buf[pb];
 #pragma unroll
         for (int j = 0; j < EPL; j++) {
             const bool ta = ka <= kb;
@@ -195,10 +197,7 @@ __device__ __forceinline__ void warp_merge_sort(K (&k)[EPL], K *buf, int lane) {
             if (j + 1 < EPL) {
                 pa += ta ? 1 : 0;
                 pb += ta ? 0 : 1;
-                const int p = ta ? pa : pb;
-                const int e = ta ? ea : eb;
-                K v = SENT;
-                if (p < e) v = buf[p];
+                const K v = buf[ta ? pa : pb];
                 ka = ta ? v : ka;
                 kb = ta ? kb : v;
             }
@@ -260,7 +259,7 @@ __device__ __forceinline__ uint32_t intern_key(const SamplerArgs &a, unsigned lo
 template <typename K, int EPL>
 constexpr int sampler_min_blocks() {
     constexpr int W = (int)sizeof(K) / 4;
-    constexpr int smem_warp = ((int)sizeof(K) + 4) * 32 * EPL + 256;
+    constexpr int smem_warp = ((int)sizeof(K) + 4) * 32 * EPL + 32 * (int)sizeof(K) + 256;
     constexpr int by_smem = 232448 / (kWarpsPerBlock * smem_warp);
     constexpr int by_regs = 65536 / (kWarpsPerBlock * 32 * (EPL * W + 52));
     constexpr int b = by_smem < by_regs ? by_smem : by_regs;
@@ -273,6 +272,7 @@ constexpr int sampler_min_blocks() {
 template <typename K, int EPL, bool PARITY>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL>()) gset_sample_kernel(const SamplerArgs a) {
     constexpr K SENT = ~(K)0;
+    constexpr K PAD = SENT - 1;  // fills the key slots beyond M*m+1: above every real key, below the merge sentinel
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
     const int lane = threadIdx.x & 31;
@@ -300,18 +300,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
     pol.keep = l2_policy_evict_last();
     int mx = 0;
 
-    int64_t next_i = 0;
-    int batch_left = 0;
+    // seeds are handed out by a ticket counter; the ticket of the NEXT seed is requested before this one is processed
+    unsigned long long ticket = 0;
+    if (lane == 0) ticket = atomicAdd(&a.ctr[0], 1ull);
     for (;;) {
-        if (batch_left == 0) {
-            unsigned long long ticket = 0;
-            if (lane == 0) ticket = atomicAdd(&a.ctr[0], (unsigned long long)kTicketBatch);
-            next_i = (int64_t)__shfl_sync(FULL, ticket, 0);
-            batch_left = kTicketBatch;
-        }
-        const int64_t i = next_i++;
-        batch_left--;
+        const int64_t i = (int64_t)__shfl_sync(FULL, ticket, 0);
         if (i >= a.n_chunk) break;
+        if (lane == 0) ticket = atomicAdd(&a.ctr[0], 1ull);
         const int64_t gi = a.seed_base + i;
         const int32_t u = __ldg(a.seeds + i);
         if ((uint64_t)(int64_t)u >= (uint64_t)a.N) {  // the host turns this into the reference's TypeError
@@ -456,7 +451,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
             }
         }
         if (lane == 0) keys[0] = (K)(uint32_t)u << OB;  // the root: order 0
-        for (int j = a.Kt + lane; j < 32 * EPL; j += 32) keys[j] = SENT;
+        for (int j = a.Kt + lane; j < 32 * EPL; j += 32) keys[j] = PAD;
         __syncwarp();
 
         if (a.stop_after == 1) continue;
@@ -477,7 +472,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
 #pragma unroll
         for (int r = 0; r < EPL; r++) {
             const K pn = r ? (k[r - 1] >> OB) : pn0;
-            const bool head = k[r] != SENT && (k[r] >> OB) != pn;
+            const bool head = k[r] < PAD && (k[r] >> OB) != pn;
             nhead += head ? 1u : 0u;
         }
         const uint32_t incl = warp_incl_scan(nhead);
@@ -503,7 +498,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
 #pragma unroll
             for (int r = 0; r < EPL; r++) {
                 const K pn = r ? (k[r - 1] >> OB) : pn0;
-                const bool valid = k[r] != SENT;
+                const bool valid = k[r] < PAD;
                 const bool head = valid && (k[r] >> OB) != pn;
                 const uint32_t ord = (uint32_t)k[r] & ord_mask;
                 if (head) {

@@ -249,7 +249,7 @@ static int make_plan(const Graph *g, int M, int m, int bucket, SamplePlan *p) {
     // region 2: member LP rows; Fisher-Yates permutation + hash values during the first hop
     p->lp64 = m * shift + 1 > 32;
     const int fy_half = 4 * M + 4 * fc;
-    p->lp_off = (std::max(ksz * 32 * p->EPL, fy_half) + 15) & ~15;
+    p->lp_off = (std::max(ksz * (32 * p->EPL + 32), fy_half) + 15) & ~15;  // keys + one merge sentinel per run
     p->bitmap_off = (p->lp_off + std::max((p->lp64 ? 8 : 4) * (int)Kt, fy_half) + 15) & ~15;
     p->smem_per_warp = (p->bitmap_off + 8 * p->nbw + 15) & ~15;
     return SUBG_OK;
@@ -428,7 +428,7 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
                     const int64_t csr_bytes = 4 * g->E + 8 * g->N;
                     int cap_blocks = 0;
                     if (csr_bytes > (96ll << 20))
-                        cap_blocks = std::max(2, (int)((148 << 10) / (kWarpsPerBlock * pl.smem_per_warp + 1024)));
+                        cap_blocks = std::max(2, (int)((152 << 10) / (kWarpsPerBlock * pl.smem_per_warp + 1024)));
                     a.blocks_per_sm = (int)env_i64("SUBG_SAMPLER_BLOCKS", cap_blocks);
                 }
                 a.tab_key = tab_key; a.tab_pos = tab_pos; a.tab_mask = tab_cap - 1;
