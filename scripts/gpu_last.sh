@@ -1,5 +1,3 @@
 cd ${GRAFT_REPO_ROOT:-.}
 mkdir -p gpurun_out
-timeout 400 python -m pytest tests -x -q -m gpu --timeout 300 2>&1 | tail -4
-python scripts/sampler_bench.py ppa 5 2>&1 | grep -v Warning | tail -1
-python scripts/sampler_bench.py dblp 5 2>&1 | grep -v Warning | tail -1
+python bench.py --scale 0.05 --steps 3 --warmup 3 --e2e-steps 1 --no-cpu-baseline 2>gpurun_out/tiny.err | cut -c1-400; tail -2 gpurun_out/tiny.err | cut -c1-200
