@@ -1,0 +1,90 @@
+"""CPU: host-side logic that needs no GPU -- edge-list parsing (surel_plus_b200.io), seed partitioning and the
+LP-table merge of the multi-GPU exchange under randomised inputs, the pooled host buffers' ownership rules."""
+import gc
+
+import numpy as np
+from hypothesis import given, settings, strategies as st
+
+from surel_plus_b200 import parallel as par
+
+
+def test_read_edgelist_matches_loadtxt(tmp_path):
+    from surel_plus_b200.io import read_edgelist
+    rng = np.random.default_rng(0)
+    e = rng.integers(0, 10_000, (5000, 2))
+    path = tmp_path / "edges.txt"
+    with open(path, "w") as f:
+        f.write("# comment line\n")
+        for i, (a, b) in enumerate(e):
+            f.write(f"{a}\t{b}\n" if i % 2 else f"{a} {b}\n")        # tabs and blanks, as in the twitter / SNAP releases
+    row, col = read_edgelist(str(path))
+    ref_row, ref_col = np.loadtxt(path, dtype=int).T                   # subg_acc/test/test.py:16
+    assert row.dtype == np.int64 and np.array_equal(row, ref_row) and np.array_equal(col, ref_col)
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.lists(st.floats(min_value=0.0, max_value=1e3, allow_nan=False), min_size=0, max_size=200), st.integers(1, 9))
+def test_partition_by_work_is_a_partition(weights, world):
+    b = par.partition_by_work(np.asarray(weights, dtype=np.float64), world)
+    assert len(b) == world + 1 and b[0] == 0 and b[-1] == len(weights)
+    assert np.all(np.diff(b) >= 0)
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.lists(st.lists(st.tuples(st.integers(0, 3), st.integers(0, 3)), min_size=0, max_size=12, unique=True), min_size=1, max_size=5))
+def test_merge_lp_tables_is_the_first_occurrence_scan(shards):
+    """Merging per-shard unique tables in rank order == the reference's serial first-occurrence scan over the
+    concatenated stream (subg_acc.c:957-978)."""
+    tables = [np.array(t, np.int16).reshape(-1, 2) for t in shards]
+    merged, maps = par.merge_lp_tables(tables)
+    seen, order = {}, []
+    for t in tables:
+        for row in map(tuple, t.tolist()):
+            if row not in seen:
+                seen[row] = len(order)
+                order.append(row)
+    assert [tuple(r) for r in merged.tolist()] == order
+    for t, mp in zip(tables, maps):
+        assert mp.tolist() == [seen[tuple(r)] for r in t.tolist()]
+
+
+def test_pinned_blocks_return_to_the_pool_when_the_last_view_dies(monkeypatch):
+    """Arrays handed to the caller own their page-locked block through their base chain; the block goes back to the
+    pool only when the array AND every view of it are gone (no GPU: the allocator is replaced by a counter)."""
+    import ctypes as C
+    from surel_plus_b200 import spg
+
+    class FakeLib:
+        def __init__(self):
+            self.bufs, self.freed = {}, []
+
+        def subg_host_alloc(self, pptr, nbytes):
+            buf = (C.c_char * int(nbytes))()
+            self.bufs[C.addressof(buf)] = buf
+            pptr._obj.value = C.addressof(buf)
+            return 0
+
+        def subg_host_free(self, p):
+            self.freed.append(p.value)
+
+    pool = spg._PinnedPool(keep_bytes=1 << 20)
+    pool._lib = FakeLib()
+    monkeypatch.setattr(spg, "_pinned", pool)
+    a = spg.pinned_empty((1000,), np.int32)
+    a[:] = 7
+    view = a[10:20]
+    addr = a.ctypes.data
+    del a
+    gc.collect()
+    assert pool._free == [] and view.tolist() == [7] * 10           # the view keeps the block alive
+    del view
+    gc.collect()
+    assert len(pool._free) == 1 and pool._free[0][1] == addr
+    b = spg.pinned_empty((900,), np.int32)                          # fits the recycled block (12.5 % slack rule)
+    assert b.ctypes.data == addr and pool._free == []
+    del b
+    gc.collect()
+    big = spg.pinned_empty((1 << 19,), np.int32)                    # 2 MiB > keep_bytes: trimmed when it comes back
+    del big
+    gc.collect()
+    assert sum(c for c, _ in pool._free) <= 1 << 20 and len(pool._lib.freed) >= 1
