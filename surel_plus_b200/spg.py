@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 
 import numpy as np
 import torch
@@ -59,13 +60,15 @@ class _PinnedPool:
         self._free: list[tuple[int, int]] = []  # (capacity, address)
         self._keep = keep_bytes
         self._lib = None
+        self._lock = threading.Lock()  # blocks come back from __del__, i.e. from whichever thread drops the last view
 
     def take(self, nbytes: int) -> tuple[int, int]:
-        fit = [b for b in self._free if b[0] >= nbytes]
-        if fit:
-            b = min(fit)
-            self._free.remove(b)
-            return b
+        with self._lock:
+            fit = [b for b in self._free if b[0] >= nbytes]
+            if fit:
+                b = min(fit)
+                self._free.remove(b)
+                return b
         self._lib = self._lib or _capi.load()
         cap = max(4096, ((nbytes + (nbytes >> 3) + (1 << 21) - 1) >> 21) << 21) if nbytes > (1 << 20) else max(nbytes, 64)
         p = C.c_void_p()
@@ -74,10 +77,11 @@ class _PinnedPool:
 
     def give(self, cap: int, addr: int) -> None:
         try:
-            self._free.append((cap, addr))
-            while sum(b[0] for b in self._free) > self._keep:
-                c, a = self._free.pop(0)
-                self._lib.subg_host_free(C.c_void_p(a))
+            with self._lock:
+                self._free.append((cap, addr))
+                while sum(b[0] for b in self._free) > self._keep:
+                    c, a = self._free.pop(0)
+                    self._lib.subg_host_free(C.c_void_p(a))
         except Exception:  # interpreter shutdown
             pass
 
