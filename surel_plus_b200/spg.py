@@ -60,7 +60,7 @@ class _PinnedPool:
         self._free: list[tuple[int, int]] = []  # (capacity, address)
         self._keep = keep_bytes
         self._lib = None
-        self._lock = threading.Lock()  # blocks come back from __del__, i.e. from whichever thread drops the last view
+        self._lock = threading.RLock()  # re-entrant: blocks come back from __del__, i.e. from whichever thread drops the last view
 
     def take(self, nbytes: int) -> tuple[int, int]:
         with self._lock:
