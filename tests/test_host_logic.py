@@ -88,3 +88,21 @@ def test_pinned_blocks_return_to_the_pool_when_the_last_view_dies(monkeypatch):
     del big
     gc.collect()
     assert sum(c for c, _ in pool._free) <= 1 << 20 and len(pool._lib.freed) >= 1
+
+
+def test_integration_md_python_blocks_parse_and_name_real_symbols():
+    """The stubs a reference maintainer would copy from INTEGRATION.md must at least be valid Python and bind symbols
+    that include/subg_b200.h really declares."""
+    import ast
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    assert len(blocks) >= 4
+    for b in blocks:
+        ast.parse(b)
+    header = open(os.path.join(root, "include", "subg_b200.h")).read()
+    declared = set(re.findall(r"\b(subg_[a-z0-9_]+)\s*\(", re.sub(r"/\*.*?\*/", "", header, flags=re.S)))
+    used = set(re.findall(r"L\.(subg_[a-z0-9_]+)", text))
+    assert used and used <= declared, sorted(used - declared)
