@@ -275,7 +275,7 @@ def run_ours(args):
                 "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic("gset_sample", args),
                 "peak_source": peaks["source"], "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_ms_per_launch": k_avg_ms, "kernel_share_of_step": k_ms / ms_total,
-                "spg_build_ms_per_step": b_ms / args.steps, "avg_set_size": T_avg / n}
+                "spg_build_ms_per_step": b_ms / args.steps, "avg_set_size": T_avg / n, "unique_lp_rows": int(spg.c)}
 
     # ---- e2e: reference-facing call with host buffers (H2D graph + seeds, D2H nsize/remap/enc) --
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731

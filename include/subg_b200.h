@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SUBG_ABI_VERSION 3
+#define SUBG_ABI_VERSION 4
 
 #define SUBG_OK          0
 #define SUBG_ERR_ARG    -1
@@ -147,6 +147,10 @@ int subg_spg_views(subg_spg *s, void *stream, const int64_t **indptr, const int3
 int subg_spg_rows(const subg_spg *s, const int64_t **rowbeg, const int32_t **nsize,
                   const int32_t **indices, const void **data, int64_t *extent);
 
+/* The LP table alone: enc int16[c, ncol] on the device (c, ncol from subg_spg_info), without compacting the rows as
+ * subg_spg_views does.  Work queued on `stream` afterwards is ordered behind the kernels that fill the table. */
+int subg_spg_enc(const subg_spg *s, void *stream, const int16_t **enc);
+
 /* Wrap an existing CSR (e.g. the scipy matrix produced by the reference's
  * subg_matrix / topk_ppr_matrix+encoding) as an SpG for the join.
  * value_kind 0: int32 data (LP pointers), 1: float64 data (PPR / SPD values). */
@@ -160,6 +164,39 @@ int subg_spg_from_csr(const int64_t *indptr_hd, const int32_t *indices_hd, const
 int subg_spg_alloc(int64_t n, int64_t T, int device, void *stream, subg_spg **out);
 int subg_spg_seal(subg_spg *s, void *stream);
 void subg_spg_free(subg_spg *s);
+
+/* ---- multi-GPU exchange over NVLink peer memory ------------------------------
+ * Nothing like it exists in the reference (single process, README.md:24); this is the scaling path of
+ * gset_sampler + subg_matrix: one process per GPU, the graph replicated, every rank samples a contiguous
+ * seed range (subg_gset_sample_shard) and ends with the full SpG.
+ *   create   allocates the rank's *slab* (cudaMalloc, IPC-exportable), slab_bytes >= the packed size of the
+ *            largest shard the rank will publish (8 bytes per entry + 12 per seed + 16 per unique LP row is safe)
+ *   export   the 64-byte cudaIpcMemHandle_t of the slab; the host exchanges the handles of all ranks ...
+ *   open     ... and maps the peers' slabs (handles: world x 64 bytes in rank order; the own entry is ignored)
+ *   pack     shard -> slab in the packed wire format (4 / 5 / 6 / 8 bytes per entry, chosen from the node-id
+ *            and LP-id widths) + set sizes, row offsets, unique LP keys with their first positions;
+ *            header int64[8] (host) = {n, T, extent, c, format, max_set, status, bytes used}.  A shard that
+ *            does not fit reports format < 0.  Asynchronous on `stream`.
+ *   assemble headers int64[world, 8] of all ranks (the host all-gathers them; that collective is also the
+ *            barrier after which the peers' slabs are complete) -> the full SpG on this GPU: the LP tables are
+ *            merged on the device into the global first-occurrence order (subg_acc.c:957-978) and ONE kernel
+ *            pulls every peer's packed entries over NVLink, widens and relabels them in flight.  srcs: NULL =
+ *            the mapped peers; else `world` device pointers where the slabs can be read (e.g. slices of a
+ *            staging buffer filled by an NCCL all-gather).  num_walks / ncol = the sampling call's M and
+ *            num_steps + 1.  Synchronises the stream.
+ * The slab may be re-packed only after every peer has finished its assemble (the host runs a barrier).
+ * Time of the pull kernel: subg_timing_read(SUBG_TIMING_EXCHANGE). */
+typedef struct subg_xchg subg_xchg;
+#define SUBG_XCHG_HANDLE_BYTES 64
+#define SUBG_XCHG_HEADER_WORDS 8
+int subg_xchg_create(int device, int rank, int world, int64_t slab_bytes, subg_xchg **out);
+int subg_xchg_export(const subg_xchg *x, void *handle64);
+int subg_xchg_open(subg_xchg *x, const void *handles);
+int subg_xchg_slab(const subg_xchg *x, void **slab_dev, int64_t *bytes);
+int subg_xchg_pack(subg_xchg *x, const subg_spg *shard, int64_t num_nodes, int64_t *header, void *stream);
+int subg_xchg_assemble(subg_xchg *x, const int64_t *headers, const void *const *srcs, int num_walks, int ncol,
+                       void *stream, subg_spg **out);
+void subg_xchg_free(subg_xchg *x);
 
 /* ---- SpJoin -------------------------------------------------------------------
  * Replaces gather / bgather / pgather / hgather (train.py:13-111).
@@ -262,12 +299,13 @@ int subg_walk_join(const int32_t *walks_hd, int64_t n, int64_t stride, const int
  * launching stream.  subg_timing_read synchronises those events, returns the summed
  * device time and number of launches of kernel class `which` since the last read and
  * clears them.  which: 0 set-sampler kernel, 1 SpJoin kernel, 2 SpG build (scan,
- * compaction, unique ranking, id remap), 3 PPR push kernel.  subg_launch_count: kernels launched by the
+ * compaction, unique ranking, id remap), 3 PPR push kernel, 4 multi-GPU pull kernel.  subg_launch_count: kernels launched by the
  * library since load (all classes). */
 #define SUBG_TIMING_SAMPLER 0
 #define SUBG_TIMING_SPJOIN  1
 #define SUBG_TIMING_BUILD   2
 #define SUBG_TIMING_PPR     3
+#define SUBG_TIMING_EXCHANGE 4 /* pull kernel of subg_xchg_assemble */
 int subg_timing_enable(int enable);
 int subg_timing_read(int which, double *ms, int64_t *launches);
 int64_t subg_launch_count(void);

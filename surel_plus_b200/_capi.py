@@ -16,14 +16,15 @@ SUBG_RNG_PHILOX, SUBG_RNG_RAND_R, SUBG_RNG_TRACE = 0, 1, 2
 STATUS_BUCKET_OVERFLOW, STATUS_DEAD_END, STATUS_PPR_SECOND_PASS = 1, 2, 4
 SAMPLE_NO_RANKS = 1
 ENCODER_NONE, ENCODER_PPR, ENCODER_SPD = 0, 1, 2
-TIMING_SAMPLER, TIMING_SPJOIN, TIMING_BUILD, TIMING_PPR = 0, 1, 2, 3
+TIMING_SAMPLER, TIMING_SPJOIN, TIMING_BUILD, TIMING_PPR, TIMING_EXCHANGE = 0, 1, 2, 3, 4
 
 #: every symbol include/subg_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
     "subg_abi_version", "subg_last_error",
     "subg_graph_create", "subg_graph_from_edges", "subg_graph_export", "subg_graph_info", "subg_graph_free",
-    "subg_gset_sample", "subg_gset_sample_shard", "subg_spg_set_lp_table", "subg_spg_info", "subg_spg_export", "subg_spg_views", "subg_spg_rows",
+    "subg_gset_sample", "subg_gset_sample_shard", "subg_spg_set_lp_table", "subg_spg_info", "subg_spg_export", "subg_spg_views", "subg_spg_rows", "subg_spg_enc",
     "subg_spg_from_csr", "subg_spg_alloc", "subg_spg_seal", "subg_spg_free",
+    "subg_xchg_create", "subg_xchg_export", "subg_xchg_open", "subg_xchg_slab", "subg_xchg_pack", "subg_xchg_assemble", "subg_xchg_free",
     "subg_spjoin_plan", "subg_spjoin_run", "subg_spjoin",
     "subg_ppr_topk", "subg_spg_encode", "subg_spg_pushes",
     "subg_walk_sample", "subg_walkset_info", "subg_walkset_export", "subg_walkset_views", "subg_walkset_free", "subg_walk_join",
@@ -64,12 +65,21 @@ def load() -> C.CDLL:
                                 C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]
     L.subg_spg_export.argtypes = [vp, vp, vp, vp, vp, vp]
     L.subg_spg_views.argtypes = [vp, vp] + [C.POINTER(vp)] * 6
+    L.subg_spg_enc.argtypes = [vp, vp, C.POINTER(vp)]
     L.subg_spg_rows.argtypes = [vp] + [C.POINTER(vp)] * 4 + [C.POINTER(i64)]
     L.subg_spg_from_csr.argtypes = [vp, vp, vp, i32, i64, i64, i32, vp, C.POINTER(vp)]
     L.subg_spg_alloc.argtypes = [i64, i64, i32, vp, C.POINTER(vp)]
     L.subg_spg_seal.argtypes = [vp, vp]
     L.subg_spg_free.argtypes = [vp]
     L.subg_spg_free.restype = None
+    L.subg_xchg_create.argtypes = [i32, i32, i32, i64, C.POINTER(vp)]
+    L.subg_xchg_export.argtypes = [vp, vp]
+    L.subg_xchg_open.argtypes = [vp, vp]
+    L.subg_xchg_slab.argtypes = [vp, C.POINTER(vp), C.POINTER(i64)]
+    L.subg_xchg_pack.argtypes = [vp, vp, i64, vp, vp]
+    L.subg_xchg_assemble.argtypes = [vp, vp, vp, i32, i32, vp, C.POINTER(vp)]
+    L.subg_xchg_free.argtypes = [vp]
+    L.subg_xchg_free.restype = None
     L.subg_spjoin_plan.argtypes = [vp, vp, i64, i32, vp, vp, C.POINTER(i64), vp]
     L.subg_spjoin_run.argtypes = [vp, vp, i64, i32, vp, vp, i32, vp, vp, vp]
     L.subg_spjoin.argtypes = [vp, vp, i64, i32, vp, vp, vp, i32, vp, i64, vp, C.POINTER(i64), C.POINTER(i32), vp]

@@ -85,6 +85,14 @@ int spg_encode_impl(const Graph *g, const SpG *x, int encoder, cudaStream_t st, 
 int graph_from_edges_impl(const int64_t *row_hd, const int64_t *col_hd, int64_t E, int64_t N_in, int symmetrize,
                           int drop_self_loops, int device, cudaStream_t st, Graph **out);
 int graph_export_impl(const Graph *g, int64_t *rowptr_hd, int32_t *col_hd, cudaStream_t st);
+struct Xchg;
+int xchg_create_impl(int device, int rank, int world, int64_t slab_bytes, Xchg **out);
+int xchg_export_impl(const Xchg *x, void *handle64);
+int xchg_open_impl(Xchg *x, const void *handles);
+int xchg_slab_impl(const Xchg *x, void **slab_dev, int64_t *bytes);
+int xchg_pack_impl(Xchg *x, const SpG *s, int64_t n_nodes, int64_t *header, cudaStream_t st);
+int xchg_assemble_impl(Xchg *x, const int64_t *headers, const void *const *srcs, int M, int ncol, cudaStream_t st, SpG **out);
+void xchg_free_impl(Xchg *x);
 struct WalkSet;
 int walk_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, int M, int m, uint64_t seed, int rng_mode,
                      int without, cudaStream_t st, WalkSet **out);
@@ -152,6 +160,7 @@ int subg_graph_create(const void *rowptr_hd, int rowptr_is64, const int32_t *col
     DeviceGuard guard(device);
     cudaStream_t st = (cudaStream_t)stream;
     Graph *g = new Graph();
+    g->tag.last = st;
     g->device = device; g->N = N; g->E = E;
     g->rowptr64 = E >= (1ll << 31);
     cudaDeviceGetAttribute(&g->num_sms, cudaDevAttrMultiProcessorCount, device);
@@ -222,9 +231,10 @@ void subg_graph_free(subg_graph *g_) {
     Graph *g = reinterpret_cast<Graph *>(g_);
     if (!g) return;
     DeviceGuard guard(g->device);
-    if (g->rowptr) cudaFreeAsync(g->rowptr, 0);
-    if (g->col) cudaFreeAsync(g->col, 0);
-    if (g->rowinfo) cudaFreeAsync(g->rowinfo, 0);
+    const cudaStream_t st = g->tag.free_stream();  // behind the last kernel that read the graph
+    if (g->rowptr) cudaFreeAsync(g->rowptr, st);
+    if (g->col) cudaFreeAsync(g->col, st);
+    if (g->rowinfo) cudaFreeAsync(g->rowinfo, st);
     delete g;
 }
 
@@ -278,6 +288,15 @@ int subg_spg_rows(const subg_spg *s_, const int64_t **rowbeg, const int32_t **ns
     return SUBG_OK;
 }
 
+int subg_spg_enc(const subg_spg *s_, void *stream, const int16_t **enc) {
+    const SpG *s = reinterpret_cast<const SpG *>(s_);
+    if (!s || !enc) return fail(SUBG_ERR_ARG, "null SpG");
+    DeviceGuard guard(s->device);
+    s->tag.use_on((cudaStream_t)stream);
+    *enc = s->enc;
+    return SUBG_OK;
+}
+
 int subg_spg_views(subg_spg *s_, void *stream, const int64_t **indptr, const int32_t **indices, const void **data,
                    const uint16_t **slot, const int16_t **enc, const int32_t **nsize) {
     SpG *s = reinterpret_cast<SpG *>(s_);
@@ -306,6 +325,25 @@ int subg_spg_alloc(int64_t n, int64_t T, int device, void *stream, subg_spg **ou
 int subg_spg_seal(subg_spg *s, void *stream) { return spg_seal_impl(reinterpret_cast<SpG *>(s), (cudaStream_t)stream); }
 
 void subg_spg_free(subg_spg *s) { spg_free_impl(reinterpret_cast<SpG *>(s)); }
+
+int subg_xchg_create(int device, int rank, int world, int64_t slab_bytes, subg_xchg **out) {
+    if (int rc = init_device(device)) return rc;
+    return xchg_create_impl(device, rank, world, slab_bytes, reinterpret_cast<Xchg **>(out));
+}
+int subg_xchg_export(const subg_xchg *x, void *handle64) { return xchg_export_impl(reinterpret_cast<const Xchg *>(x), handle64); }
+int subg_xchg_open(subg_xchg *x, const void *handles) { return xchg_open_impl(reinterpret_cast<Xchg *>(x), handles); }
+int subg_xchg_slab(const subg_xchg *x, void **slab_dev, int64_t *bytes) {
+    return xchg_slab_impl(reinterpret_cast<const Xchg *>(x), slab_dev, bytes);
+}
+int subg_xchg_pack(subg_xchg *x, const subg_spg *shard, int64_t num_nodes, int64_t *header, void *stream) {
+    return xchg_pack_impl(reinterpret_cast<Xchg *>(x), reinterpret_cast<const SpG *>(shard), num_nodes, header, (cudaStream_t)stream);
+}
+int subg_xchg_assemble(subg_xchg *x, const int64_t *headers, const void *const *srcs, int num_walks, int ncol, void *stream,
+                       subg_spg **out) {
+    return xchg_assemble_impl(reinterpret_cast<Xchg *>(x), headers, srcs, num_walks, ncol, (cudaStream_t)stream,
+                              reinterpret_cast<SpG **>(out));
+}
+void subg_xchg_free(subg_xchg *x) { xchg_free_impl(reinterpret_cast<Xchg *>(x)); }
 
 int subg_spjoin_plan(const subg_spg *s, const int64_t *edge_hd, int64_t B, int arity, int64_t *edge_dev,
                      int64_t *indptr_dev, int64_t *N_out, void *stream) {

@@ -80,8 +80,38 @@ inline void dfree(void *p, cudaStream_t st) {
     if (p) cudaFreeAsync(p, st);
 }
 
+// ------------------------------------------------------------------ stream ordering of handles
+// Every handle remembers the stream its memory was last used on.  An entry point called with a different stream first
+// makes that stream wait for the work queued so far (event), and the handle's memory is released on the last stream,
+// so a kernel still queued on a non-blocking side stream never sees its operands handed out again by the pool.
+struct StreamTag {
+    mutable cudaStream_t last = nullptr;
+    void use_on(cudaStream_t st) const {
+        if (st == last) return;
+        cudaEvent_t ev;
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) {
+            if (cudaEventRecord(ev, last) == cudaSuccess) cudaStreamWaitEvent(st, ev, 0);
+            else cudaGetLastError();  // the old stream is gone: its work has completed
+            cudaEventDestroy(ev);
+        }
+        last = st;
+    }
+    // stream to free on (if it was destroyed meanwhile, everything queued on it has run: fall back to a full sync)
+    cudaStream_t free_stream() const {
+        if (last && cudaStreamQuery(last) == cudaErrorInvalidResourceHandle) {
+            cudaGetLastError();
+            cudaDeviceSynchronize();
+            last = nullptr;
+        } else {
+            cudaGetLastError();
+        }
+        return last;
+    }
+};
+
 // ------------------------------------------------------------------ object layouts
 struct Graph {
+    StreamTag tag;
     int device = 0;
     int64_t N = 0, E = 0;
     bool rowptr64 = false;
@@ -94,6 +124,7 @@ struct Graph {
 };
 
 struct SpG {
+    StreamTag tag;
     int device = 0;
     int64_t n = 0;         // rows (sets), in seed order
     int64_t T = 0;         // total entries
@@ -115,6 +146,11 @@ struct SpG {
     void *data = nullptr;        // int32 (id+1) or float64
     uint16_t *slot = nullptr;    // first-visit rank (sampler-built SpGs that asked for it)
     int16_t *enc = nullptr;      // [c, ncol]
+    // sampler-built LP SpGs keep the 64-bit key of every unique LP row and the stream position of its first occurrence
+    // ((global seed index << 16) | first-visit order), both in id order: what the multi-GPU merge of the shards' tables needs
+    unsigned long long *lp_key = nullptr;  // [c]
+    unsigned long long *lp_pos = nullptr;  // [c]
+    int32_t shift = 0;           // bits per LP column in the key (32 - clz(M))
     int32_t *nsize = nullptr;    // [n]
     int32_t *seeds = nullptr;    // [n] node id of each row
     int64_t pushes = 0;          // PPR sampler: forward pushes performed (measurement)
@@ -127,6 +163,10 @@ struct SpG {
 };
 
 void spg_free_impl(SpG *s);
+// LP-key table -> ids in first-occurrence order (spg.cu)
+int rank_unique_keys(const unsigned long long *tab_key, const unsigned long long *tab_pos, uint32_t cap, uint32_t c_max,
+                     bool count_exact, int M, int m, int SHIFT, int32_t *rank_of_slot, int16_t *enc,
+                     unsigned long long *lp_key, unsigned long long *lp_pos, uint32_t *d_cnt, int num_sms, cudaStream_t st);
 int spg_ensure_csr(SpG *s, cudaStream_t st);  // scattered -> compact (no-op when compact)
 
 // ------------------------------------------------------------------ device helpers

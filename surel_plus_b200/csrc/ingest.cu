@@ -111,6 +111,7 @@ int graph_from_edges_impl(const int64_t *row_hd, const int64_t *col_hd, int64_t 
     if (!out || E < 0 || (E > 0 && (!row_hd || !col_hd))) return fail(SUBG_ERR_ARG, "Input parsing error.");
     DeviceGuard guard(device);
     Graph *g = new Graph();
+    g->tag.last = st;
     g->device = device;
     cudaDeviceGetAttribute(&g->num_sms, cudaDevAttrMultiProcessorCount, device);
     long long *d_row = nullptr, *d_col = nullptr, *d_minmax = nullptr, *d_tile_off = nullptr, *d_scratch = nullptr;
@@ -238,6 +239,7 @@ done:
 int graph_export_impl(const Graph *g, int64_t *rowptr_hd, int32_t *col_hd, cudaStream_t st) {
     if (!g) return fail(SUBG_ERR_ARG, "null graph");
     DeviceGuard guard(g->device);
+    g->tag.use_on(st);
     long long *wide = nullptr;
     if (rowptr_hd) {
         const void *src = g->rowptr;

@@ -605,7 +605,9 @@ int ppr_topk_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, float alph
     if (!sorted)
         return fail(SUBG_ERR_UNSUPPORTED, "PPR sampler needs CSR rows with strictly ascending columns (scipy canonical format)");
 
+    g->tag.use_on(st);
     SpG *s = new SpG();
+    s->tag.last = st;
     s->device = g->device; s->n = n; s->value_kind = 1; s->num_sms = g->num_sms; s->ncol = 1;
     int rc = SUBG_OK;
     PushWorkspace ws;
@@ -752,7 +754,10 @@ int spg_encode_impl(const Graph *g, const SpG *x, int encoder, cudaStream_t st, 
     if (encoder != SUBG_ENCODER_PPR && encoder != SUBG_ENCODER_SPD) return fail(SUBG_ERR_UNSUPPORTED, "encoder must be 'PPR' or 'SPD'");  // utils.py:37-38
     DeviceGuard guard(x->device);
     int rc = SUBG_OK;
+    if (g) g->tag.use_on(st);
+    x->tag.use_on(st);
     SpG *s = new SpG();
+    s->tag.last = st;
     s->device = x->device; s->n = x->n; s->value_kind = 1; s->num_sms = x->num_sms; s->ncol = 1;
     unsigned long long *mx_bits = nullptr;
     uint8_t *code = nullptr;

@@ -87,18 +87,50 @@ __global__ void collect_unique_kernel(const unsigned long long *tab_key, const u
         }
 }
 
-// sorted by first occurrence: id j <- table slot; decode the key back into an int16 LP row
-__global__ void finalize_unique_kernel(const uint32_t *sorted_slot, uint32_t c, const unsigned long long *tab_key,
-                                       int M, int m, int SHIFT, int32_t *rank_of_slot, int16_t *enc) {
+// sorted by first occurrence: id j <- table slot; decode the key back into an int16 LP row.
+// c_dev (nullable): the number of valid entries lives on the device (the multi-GPU merge sorts an upper bound)
+__global__ void finalize_unique_kernel(const uint32_t *sorted_slot, uint32_t c, const uint32_t *c_dev,
+                                       const unsigned long long *tab_key, int M, int m, int SHIFT,
+                                       int32_t *rank_of_slot, int16_t *enc, unsigned long long *lp_key) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= c) return;
+    if (j >= c || (c_dev && j >= *c_dev)) return;
     const uint32_t h = sorted_slot[j];
-    rank_of_slot[h] = (int32_t)j;
+    if (rank_of_slot) rank_of_slot[h] = (int32_t)j;
     const unsigned long long key = tab_key[h];
+    if (lp_key) lp_key[j] = key;
     const int ncol = m + 1;
     const unsigned long long fm = (1ull << SHIFT) - 1ull;
     enc[(int64_t)j * ncol] = ((key >> (m * SHIFT)) & 1ull) ? (int16_t)M : (int16_t)0;
     for (int q = 1; q <= m; q++) enc[(int64_t)j * ncol + q] = (int16_t)((key >> (SHIFT * (m - q))) & fm);
+}
+
+// LP-key table -> ids in first-occurrence order (subg_acc.c:957-978 without the serial scan): the occupied slots are
+// collected, sorted by the smallest stream position of their key, and numbered.  c_max bounds the number of keys (the
+// exact count is left in *d_cnt).  Outputs: rank_of_slot[cap] (slot -> id), enc int16[c, m+1], lp_key[c], lp_pos[c]
+// (ids ascending); entries beyond the count are undefined.  All launches on `st`, no synchronisation.
+int rank_unique_keys(const unsigned long long *tab_key, const unsigned long long *tab_pos, uint32_t cap, uint32_t c_max,
+                     bool count_exact, int M, int m, int SHIFT, int32_t *rank_of_slot, int16_t *enc,
+                     unsigned long long *lp_key, unsigned long long *lp_pos, uint32_t *d_cnt, int num_sms, cudaStream_t st) {
+    if (c_max == 0) return SUBG_OK;
+    unsigned long long *u_pos = nullptr;
+    uint32_t *u_slot = nullptr, *u_slot2 = nullptr;
+    void *cub_tmp = nullptr;
+    SUBG_CUDA(dmalloc(&u_pos, (size_t)c_max, st));
+    SUBG_CUDA(dmalloc(&u_slot, (size_t)c_max, st));
+    SUBG_CUDA(dmalloc(&u_slot2, (size_t)c_max, st));
+    if (!count_exact) SUBG_CUDA(cudaMemsetAsync(u_pos, 0xff, (size_t)c_max * 8, st));  // padding sorts behind every key
+    SUBG_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(uint32_t), st));
+    collect_unique_kernel<<<4 * num_sms, 256, 0, st>>>(tab_key, tab_pos, cap, u_pos, u_slot, d_cnt);
+    size_t tmp_bytes = 0;
+    SUBG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, u_pos, lp_pos, u_slot, u_slot2, (int)c_max, 0, 64, st));
+    SUBG_CUDA(cudaMallocAsync(&cub_tmp, tmp_bytes ? tmp_bytes : 1, st));
+    SUBG_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, tmp_bytes, u_pos, lp_pos, u_slot, u_slot2, (int)c_max, 0, 64, st));
+    finalize_unique_kernel<<<(c_max + 255) / 256, 256, 0, st>>>(u_slot2, c_max, count_exact ? nullptr : d_cnt, tab_key, M, m, SHIFT,
+                                                              rank_of_slot, enc, lp_key);
+    SUBG_CUDA(cudaGetLastError());
+    dfree(u_pos, st); dfree(u_slot, st); dfree(u_slot2, st); dfree(cub_tmp, st);
+    count_launch(4);
+    return SUBG_OK;
 }
 
 // provisional table slot -> LP-row id + 1, in place: one streaming pass (16-byte accesses; the slot -> id map is a few
@@ -157,9 +189,9 @@ __global__ void row_sizes_kernel(const long long *indptr, int64_t n, int32_t *ns
 static void free_spg_arrays(SpG *s, cudaStream_t st) {
     if (s->rowbeg && (void *)s->rowbeg != (void *)s->indptr) dfree(s->rowbeg, st);
     dfree(s->indptr, st); dfree(s->indices, st); dfree(s->data, st); dfree(s->slot, st);
-    dfree(s->enc, st); dfree(s->nsize, st); dfree(s->seeds, st);
+    dfree(s->enc, st); dfree(s->nsize, st); dfree(s->seeds, st); dfree(s->lp_key, st); dfree(s->lp_pos, st);
     s->indptr = nullptr; s->rowbeg = nullptr; s->indices = nullptr; s->data = nullptr; s->slot = nullptr;
-    s->enc = nullptr; s->nsize = nullptr; s->seeds = nullptr;
+    s->enc = nullptr; s->nsize = nullptr; s->seeds = nullptr; s->lp_key = nullptr; s->lp_pos = nullptr;
 }
 
 // scattered rows -> compact CSR (rows back to back in seed order); frees the slack of the cursor layout
@@ -167,6 +199,7 @@ int spg_ensure_csr(SpG *s, cudaStream_t st) {
     if (!s) return fail(SUBG_ERR_ARG, "null SpG");
     if (s->indptr) return SUBG_OK;
     DeviceGuard guard(s->device);
+    s->tag.use_on(st);
     const int64_t n = s->n;
     int64_t *indptr = nullptr;
     long long *scratch = nullptr;
@@ -272,8 +305,11 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
     const bool want_slot = !(flags & SUBG_SAMPLE_NO_RANKS);
     const bool want_rank = want_slot || pl.stride < pl.Kt;
 
+    g->tag.use_on(st);
     SpG *s = new SpG();
+    s->tag.last = st;
     s->device = g->device; s->n = n; s->ncol = m + 1; s->M = M; s->num_sms = g->num_sms; s->value_kind = 0;
+    s->shift = pl.SHIFT;
     HostProf prof;
 
     // everything below that is not part of the SpG is scratch
@@ -281,10 +317,9 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
     int32_t *c_node = nullptr, *c_prov = nullptr;  // chunk rows (chunked mode only)
     uint16_t *c_slot = nullptr;
     long long *call_base = nullptr, *scan_scratch = nullptr, *c_rowbeg = nullptr;
-    unsigned long long *tab_key = nullptr, *tab_pos = nullptr, *u_pos = nullptr, *u_pos2 = nullptr, *d_ctr = nullptr;
-    uint32_t *u_slot = nullptr, *u_slot2 = nullptr, *d_flags = nullptr;  // [0]=status [1]=tab_count [2]=bad seeds [3]=unique cnt
+    unsigned long long *tab_key = nullptr, *tab_pos = nullptr, *d_ctr = nullptr;
+    uint32_t *d_flags = nullptr;  // [0]=status [1]=tab_count [2]=bad seeds [3]=unique cnt
     int32_t *d_maxset = nullptr;
-    void *cub_tmp = nullptr;
     bool walks_owned = false;
     int rc = SUBG_OK;
     int64_t cap = 0;
@@ -517,22 +552,18 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
             CK(dmalloc(&s->enc, (size_t)c * (m + 1), st));
             if (c > 0) {
                 timing_begin(SUBG_TIMING_BUILD, st);
-                CK(dmalloc(&u_pos, (size_t)c, st)); CK(dmalloc(&u_pos2, (size_t)c, st));
-                CK(dmalloc(&u_slot, (size_t)c, st)); CK(dmalloc(&u_slot2, (size_t)c, st));
+                CK(dmalloc(&s->lp_pos, (size_t)c, st));
+                CK(dmalloc(&s->lp_key, (size_t)c, st));
                 CK(dmalloc(&rank_of_slot, (size_t)tab_cap, st));
                 CK(cudaMemsetAsync(rank_of_slot, 0, (size_t)tab_cap * 4, st));
-                collect_unique_kernel<<<4 * g->num_sms, 256, 0, st>>>(tab_key, tab_pos, tab_cap, u_pos, u_slot, d_flags + 3);
-                size_t tmp_bytes = 0;
-                CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, u_pos, u_pos2, u_slot, u_slot2, (int)c, 0, 64, st));
-                CK(cudaMallocAsync(&cub_tmp, tmp_bytes ? tmp_bytes : 1, st));
-                CK(cub::DeviceRadixSort::SortPairs(cub_tmp, tmp_bytes, u_pos, u_pos2, u_slot, u_slot2, (int)c, 0, 64, st));
-                finalize_unique_kernel<<<(c + 255) / 256, 256, 0, st>>>(u_slot2, c, tab_key, M, m, pl.SHIFT, rank_of_slot, s->enc);
+                if (int urc = rank_unique_keys(tab_key, tab_pos, tab_cap, c, true, M, m, pl.SHIFT, rank_of_slot, s->enc, s->lp_key,
+                                               s->lp_pos, d_flags + 3, g->num_sms, st)) { rc = urc; goto done; }
                 if (extent > 0 && env_i64("SUBG_SAMPLER_STOP", 0) == 0) {  // a truncated measurement run leaves no valid rows
                     const int64_t rb = std::min<int64_t>((extent / 4 + 255) / 256 + 1, 16 * (int64_t)g->num_sms);
                     remap_ids_kernel<<<(unsigned)rb, 256, 0, st>>>((int32_t *)s->data, extent, rank_of_slot);
                 }
                 timing_end(SUBG_TIMING_BUILD, st);
-                count_launch(4);
+                count_launch(1);
             }
             break;
         }
@@ -564,9 +595,8 @@ done:
     if (walks_owned) dfree(d_walks, st);
     dfree(d_calls, st); dfree(call_base, st); dfree(scan_scratch, st); dfree(d_all_seeds, st);
     dfree(c_node, st); dfree(c_prov, st); dfree(c_slot, st); dfree(c_rowbeg, st);
-    dfree(tab_key, st); dfree(tab_pos, st); dfree(u_pos, st); dfree(u_pos2, st);
-    dfree(u_slot, st); dfree(u_slot2, st); dfree(rank_of_slot, st);
-    dfree(d_flags, st); dfree(d_ctr, st); dfree(cub_tmp, st);
+    dfree(tab_key, st); dfree(tab_pos, st); dfree(rank_of_slot, st);
+    dfree(d_flags, st); dfree(d_ctr, st);
     if (rc != SUBG_OK) {
         free_spg_arrays(s, st);
         delete s;
@@ -585,6 +615,7 @@ int spg_set_lp_table_impl(SpG *s, const int32_t *id_map_hd, const int16_t *enc_h
     if (ncol > 0) s->ncol = ncol;
     if (s->ncol < 1) return fail(SUBG_ERR_ARG, "LP table width unknown");
     DeviceGuard guard(s->device);
+    s->tag.use_on(st);
     int32_t *d_map = nullptr;
     int16_t *d_enc = nullptr;
     SUBG_CUDA(dmalloc(&d_map, (size_t)s->c + 1, st));
@@ -619,6 +650,7 @@ int spg_alloc_impl(int64_t n, int64_t T, int device, cudaStream_t st, SpG **out)
     if (!out || n < 0 || T < 0) return fail(SUBG_ERR_ARG, "Input parsing error.");
     DeviceGuard guard(device);
     SpG *s = new SpG();
+    s->tag.last = st;
     s->device = device; s->n = n; s->T = T; s->value_kind = 0;
     cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, device);
     cudaError_t e = dmalloc(&s->indptr, (size_t)n + 1, st);
@@ -638,6 +670,7 @@ int spg_alloc_impl(int64_t n, int64_t T, int device, cudaStream_t st, SpG **out)
 int spg_seal_impl(SpG *s, cudaStream_t st) {
     if (!s || !s->indptr || !s->nsize) return fail(SUBG_ERR_ARG, "seal needs an SpG from subg_spg_alloc");
     DeviceGuard guard(s->device);
+    s->tag.use_on(st);
     long long *scratch = nullptr;
     int32_t *d_max = nullptr;
     SUBG_CUDA(dmalloc(&scratch, (size_t)std::max(1, scan_num_blocks(s->n)), st));
@@ -666,6 +699,7 @@ int spg_export_impl(const SpG *s, int32_t *nsize_hd, int32_t *remap_hd, int16_t 
     if (s->value_kind != 0 || !s->slot)
         return fail(SUBG_ERR_ARG, "export needs a sampler-built LP SpG with first-visit ranks (not SUBG_SAMPLE_NO_RANKS)");
     DeviceGuard guard(s->device);
+    s->tag.use_on(st);
     const int64_t T = s->T, n = s->n;
     const int ncol = s->ncol;
     if (nsize_hd && n > 0)
@@ -715,6 +749,7 @@ int spg_from_csr_impl(const int64_t *indptr_hd, const int32_t *indices_hd, const
     if (value_kind != 0 && value_kind != 1) return fail(SUBG_ERR_ARG, "value_kind must be 0 (int32) or 1 (float64)");
     DeviceGuard guard(device);
     SpG *s = new SpG();
+    s->tag.last = st;
     s->device = device; s->n = n_rows; s->T = nnz; s->value_kind = value_kind;
     cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, device);
     const size_t vb = value_kind ? 8 : 4;
@@ -755,9 +790,10 @@ int spg_from_csr_impl(const int64_t *indptr_hd, const int32_t *indices_hd, const
 void spg_free_impl(SpG *s) {
     if (!s) return;
     DeviceGuard guard(s->device);
-    free_spg_arrays(s, 0);
-    dfree(s->join_sizes, 0);
-    dfree(s->join_tot, 0);
+    const cudaStream_t st = s->tag.free_stream();  // the stream of the last kernel that touched the arrays
+    free_spg_arrays(s, st);
+    dfree(s->join_sizes, st);
+    dfree(s->join_tot, st);
     if (s->join_host) cudaFreeHost(s->join_host);
     delete s;
 }

@@ -409,6 +409,7 @@ int spjoin_plan_impl(const SpG *s, const int64_t *edge_hd, int64_t B, int arity,
     if (!s || !edge_hd || !indptr_dev || !N_out || B < 0 || (arity != 2 && arity != 3))
         return fail(SUBG_ERR_ARG, "Input parsing error.");
     DeviceGuard guard(s->device);
+    s->tag.use_on(st);
     const int64_t nseg = (arity == 2 ? 2 : 4) * B;
     const long long *edge = (const long long *)edge_hd;
     if (!is_device_ptr(edge_hd)) {
@@ -485,6 +486,7 @@ static int join_launch(const SpG *s, const int64_t *edge_dev, int64_t B, int ari
     if (B > 0 && !out_dev) return fail(SUBG_ERR_ARG, "null output");
     if (enc_table_dev && (s->value_kind != 0 || k < 1)) return fail(SUBG_ERR_ARG, "table lookup needs an int SpG and k >= 1");
     DeviceGuard guard(s->device);
+    s->tag.use_on(st);
     JoinArgs p{};
     p.rowbeg = (const long long *)s->rowbeg; p.nsize = s->indptr ? nullptr : s->nsize; p.indices = s->indices; p.data = s->data; p.n_rows = s->n;
     p.edge = (const long long *)edge_dev; p.B = B; p.arity = arity; p.seg_ptr = (const long long *)indptr_dev;
@@ -526,6 +528,7 @@ int spjoin_fused_impl(const SpG *s, const int64_t *edge_hd, int64_t B, int arity
     if (!s || !edge_hd || !edge_dev || !indptr_dev || !N_out || !ran || B < 0 || out_capacity < 0 || (arity != 2 && arity != 3))
         return fail(SUBG_ERR_ARG, "Input parsing error.");
     DeviceGuard guard(s->device);
+    s->tag.use_on(st);
     HostProf prof;
     const int64_t nseg = (arity == 2 ? 2 : 4) * B;
     if (edge_dev != edge_hd)

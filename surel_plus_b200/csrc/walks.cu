@@ -23,6 +23,7 @@
 namespace subg {
 
 struct WalkSet {
+    StreamTag tag;
     int device = 0;
     int64_t n = 0, T = 0;
     int M = 0, m = 0;
@@ -303,7 +304,9 @@ int walk_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, int M, 
     if (without > 0 && M > kMaxFyWalks)
         return fail(SUBG_ERR_UNSUPPORTED, "walk_sampler without replacement: num_walks must be <= 4096");
     DeviceGuard guard(g->device);
+    g->tag.use_on(st);
     WalkSet *w = new WalkSet();
+    w->tag.last = st;
     w->device = g->device; w->n = n; w->M = M; w->m = m;
     const int ncol = m + 1;
     int32_t *d_seeds = nullptr, *d_calls = nullptr, *d_nsize = nullptr;
@@ -417,6 +420,7 @@ done:
 int walkset_export_impl(const WalkSet *w, int32_t *walks_hd, int64_t *off_hd, int32_t *ids_hd, int32_t *rpe_hd, cudaStream_t st) {
     if (!w) return fail(SUBG_ERR_ARG, "null walk set");
     DeviceGuard guard(w->device);
+    w->tag.use_on(st);
     const size_t ncol = (size_t)w->m + 1;
     if (walks_hd && w->n > 0)
         SUBG_CUDA(cudaMemcpyAsync(walks_hd, w->walks, (size_t)w->n * w->M * ncol * sizeof(int32_t), cudaMemcpyDefault, st));
@@ -609,7 +613,7 @@ int walkset_views_impl(const WalkSet *w, const int32_t **walks, const int64_t **
 void walkset_free_impl(WalkSet *w) {
     if (!w) return;
     DeviceGuard guard(w->device);
-    free_walkset_arrays(w, 0);
+    free_walkset_arrays(w, w->tag.free_stream());
     delete w;
 }
 

@@ -3,15 +3,16 @@ HBM, seeds range-partitioned, SpG shards all-gathered once (NCCL over NVLink/NVS
 then joined locally on the replicated SpG.  The reference has no
 distributed code at all; this is the B200 scaling path of the same operators.
 
-Exchange step (the only collectives on the path; `sharded_sample`):
-  1. one small equal-size all-gather with every rank's sizes (n_r, T_r, c_r, status) and its unique LP table
-     (c_r x ncol int16, KBs) -> every rank merges the tables in rank order, which reproduces the
-     first-occurrence order of the single-process scan (subg_acc.c:957-978) because shards are contiguous seed
-     ranges; local LP ids are re-labelled on the device (subg_spg_set_lp_table);
-  2. the full SpG is allocated once (subg_spg_alloc) and nsize / indices / data of every peer (8 B per set entry)
-     are received straight into their slices in ONE NCCL group of sends and receives; subg_spg_seal derives the
-     row pointer on the device.
-`assemble_shards` is the same exchange on plain tensors with staged all-gathers (any backend).
+Exchange step (`sharded_sample`; kernels in csrc/xchg.cu):
+  1. the shard is packed (4-8 bytes per set entry) into the rank's IPC-exported slab, together with its set sizes,
+     row offsets and unique LP keys + first stream positions;
+  2. one 64-byte header all-gather (sizes, wire format): the only host-visible collective, and the barrier after
+     which every slab is complete;
+  3. on every GPU: the unique LP tables are merged ON THE DEVICE in first-occurrence order (positions are global, so
+     this is the order of the single-process scan, subg_acc.c:957-978), and ONE kernel pulls all peers' packed
+     entries over NVLink (plain loads from the mapped slabs), widens and relabels them in flight and writes the full
+     SpG in place.  Mode 'nccl' moves the slabs with an NCCL all-gather into a staging buffer instead.
+`assemble_shards` is the same exchange on plain tensors with staged all-gathers (any backend; CPU tests).
 The host-side logic below is device-agnostic (it is exercised with gloo on CPU tensors in
 tests/test_parallel_gloo.py); the sampling itself is CUDA only.
 """
@@ -132,30 +133,6 @@ def all_gather_varlen(local: torch.Tensor, counts: np.ndarray, out: torch.Tensor
     return out
 
 
-_LP_INLINE_ROWS = 4096  # unique LP rows of a shard that travel with the sizes in the first (small) all-gather
-
-
-def _p2p_ops(local: torch.Tensor, counts: np.ndarray, out: torch.Tensor, group=None) -> list:
-    """Send / recv operations that put every rank's `local` rows into its slice of `out` (byte views; the own slice
-    is copied locally).  The caller batches the operations of several arrays into ONE NCCL group."""
-    world, rank, _ = _group_info(group)
-    offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
-    ob = out.reshape(out.shape[0], -1).view(torch.uint8) if out.shape[0] else out.reshape(0, 1).view(torch.uint8)
-    lb = local.contiguous().reshape(local.shape[0], -1).view(torch.uint8) if local.shape[0] else ob[:0]
-    if counts[rank]:
-        ob[offs[rank]:offs[rank + 1]].copy_(lb)
-    ops = []
-    for r in range(world):
-        if r == rank:
-            continue
-        peer = r if group is None else dist.get_global_rank(group, r)
-        if counts[rank]:
-            ops.append(dist.P2POp(dist.isend, lb, peer, group))
-        if counts[r]:
-            ops.append(dist.P2POp(dist.irecv, ob[offs[r]:offs[r + 1]], peer, group))
-    return ops
-
-
 def assemble_shards(nsize: torch.Tensor, indices: torch.Tensor, data: torch.Tensor, enc: torch.Tensor,
                     relabel: Optional[Callable[[np.ndarray, np.ndarray], torch.Tensor]] = None, group=None) -> dict:
     """The exchange step on plain tensors.  Inputs are this rank's shard: nsize int32 [n_r],
@@ -194,100 +171,162 @@ def assemble_shards(nsize: torch.Tensor, indices: torch.Tensor, data: torch.Tens
 
 
 # ------------------------------------------------------------------------------ the CUDA path
+def slab_bytes_needed(n_seeds: int, row_cap: int, lp_rows: int = 1 << 20) -> int:
+    """Upper bound of a shard's packed size (csrc/xchg.cu slab_layout): 8 bytes per entry in the widest wire
+    format, rows padded to 4 entries, 12 bytes per seed, 16 per unique LP row, 128-byte aligned sections."""
+    row_cap = (int(row_cap) + 3) & ~3
+    return 8 * n_seeds * row_cap + 12 * n_seeds + 16 * lp_rows + 8 * 128 + 64
+
+
+def agree(flag: bool, device=None, group=None) -> bool:
+    """True on every rank iff `flag` is true on every rank (a decision all ranks have to take together,
+    e.g. whether the peers' slabs could be mapped)."""
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return bool(int(t.item()))
+
+
+class ShardExchange:
+    """This rank's side of the multi-GPU exchange (include/subg_b200.h, subg_xchg_*): the IPC-exported slab the
+    rank's shard is packed into, and the mappings of the peers' slabs.  mode 'peer': the assemble kernel pulls the
+    peers' slabs over NVLink itself; mode 'nccl': the slabs are all-gathered into a staging buffer with NCCL and
+    unpacked from there (fallback when cudaIpcOpenMemHandle is not possible, and the comparison point)."""
+
+    def __init__(self, device: int, slab_bytes: int, group=None, mode: Optional[str] = None):
+        self._lib = _capi.load()
+        self.device, self.group = device, group
+        self.world, self.rank, self.backend = _group_info(group)
+        self._h = C.c_void_p()
+        _capi.check(self._lib.subg_xchg_create(device, self.rank, self.world, int(slab_bytes), C.byref(self._h)))
+        p, b = C.c_void_p(), C.c_int64()
+        _capi.check(self._lib.subg_xchg_slab(self._h, C.byref(p), C.byref(b)))
+        self.slab_ptr, self.slab_bytes = p.value, b.value
+        tdev = torch.device("cuda", device)
+        want = (mode or os.environ.get("SUBG_EXCHANGE", "peer")).lower()
+        self.mode = "nccl"
+        self.why = "requested"
+        if want == "peer" and self.world > 1:
+            # the 64-byte IPC handles travel through the process group; every rank maps every peer
+            mine = np.zeros(64, np.uint8)
+            _capi.check(self._lib.subg_xchg_export(self._h, mine.ctypes.data))
+            allh = torch.empty((self.world, 64), dtype=torch.uint8, device=tdev)
+            dist.all_gather_into_tensor(allh, torch.from_numpy(mine).to(tdev), group=group)
+            handles = np.ascontiguousarray(allh.cpu().numpy())
+            rc = self._lib.subg_xchg_open(self._h, handles.ctypes.data)
+            err = self._lib.subg_last_error().decode("utf-8", "replace") if rc else ""
+            if agree(rc == 0, tdev, group):
+                self.mode = "peer"
+            else:
+                self.why = f"peer mapping unavailable ({err or 'on another rank'})"
+                if self.rank == 0:
+                    print(f"[surel_plus_b200] exchange falls back to NCCL staging: {self.why}", file=sys.stderr, flush=True)
+        elif self.world == 1:
+            self.mode = "peer"
+
+    def slab_view(self, nbytes: int) -> torch.Tensor:
+        from .spg import _view
+        return _view(self.slab_ptr, (int(nbytes),), "|u1", self.device, self)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.subg_xchg_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_exchanges: dict = {}
+
+
+def exchange_for(device: int, need_bytes: int, group=None, mode: Optional[str] = None) -> ShardExchange:
+    """Cached ShardExchange of (device, group).  `need_bytes` must be the same on every rank (the slab is
+    re-created collectively when it is too small)."""
+    key = (device, id(group) if group is not None else None, mode)
+    x = _exchanges.get(key)
+    if x is not None and x.slab_bytes >= need_bytes:
+        return x
+    if x is not None:
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)  # nobody is still reading the old slab
+        x.close()
+    x = ShardExchange(device, int(need_bytes * 1.05) + (1 << 20), group, mode)
+    _exchanges[key] = x
+    return x
+
+
+def close_exchanges():
+    for x in list(_exchanges.values()):
+        x.close()
+    _exchanges.clear()
+
+
+H_N, H_T, H_EXTENT, H_C, H_FMT, H_MAXSET, H_STATUS, H_BYTES = range(8)
+
+
 def sharded_sample(graph, query, num_walks=100, num_steps=3, bucket=-1, seed=111413, rng_mode=None, group=None,
-                   bounds: Optional[np.ndarray] = None):
+                   bounds: Optional[np.ndarray] = None, mode: Optional[str] = None):
     """Sample this rank's seed range on its GPU and exchange shards: returns the full SpG (replicated
-    on every rank), identical to SpG.sample(graph, query, ...) of a single process (bit for bit in
-    RAND_R / TRACE-free modes: seed indices, rand_r offsets and LP ids are global)."""
-    from .spg import SpG, _ptr, _stream, _view
+    on every rank), identical to SpG.sample(graph, query, ...) of a single process (bit for bit: seed
+    indices, Philox counters, rand_r offsets and LP first-occurrence positions are global).
+
+    Pass = sample (one kernel) -> pack into the rank's slab -> header all-gather (barrier) -> device-side LP
+    table merge + ONE pull kernel over the peers' slabs (NVLink) -> end barrier.  See csrc/xchg.cu."""
+    from .spg import SpG, _ptr, _stream
     lib = _capi.load()
     world, rank, _ = _group_info(group)
-    q = np.ascontiguousarray(np.asarray(query).astype(np.int32, copy=False))
-    n = q.size
-    lo, hi = partition(n, world, rank) if bounds is None else (int(bounds[rank]), int(bounds[rank + 1]))
-    h = C.c_void_p()
-    mode = _capi.SUBG_RNG_PHILOX if rng_mode is None else rng_mode
-    _capi.check(lib.subg_gset_sample_shard(graph._h, _ptr(q), n, lo, hi, int(num_walks), int(num_steps), int(bucket),
-                                           int(seed) & 0xFFFFFFFFFFFFFFFF, int(mode), None, _capi.SAMPLE_NO_RANKS,
-                                           _stream(graph.device), C.byref(h)))
-    shard = SpG(h, graph.device, n_nodes=graph.N, num_walks=num_walks)
-    v = shard.views()
-    dev = v["indices"].device
+    q = query if isinstance(query, torch.Tensor) else np.ascontiguousarray(np.asarray(query).astype(np.int32, copy=False))
+    n = q.numel() if isinstance(q, torch.Tensor) else q.size
+    if bounds is None:
+        bounds = np.array([partition(n, world, r)[0] for r in range(world)] + [n], dtype=np.int64)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    Kt = num_walks * num_steps + 1
+    row_cap = min(Kt, bucket) if bucket > 0 else Kt
+    need = slab_bytes_needed(int(np.max(np.diff(bounds))), row_cap)
+    xc = exchange_for(graph.device, need, group, mode)
     st = _stream(graph.device)
+    tdev = torch.device("cuda", graph.device)
+    h = C.c_void_p()
+    rmode = _capi.SUBG_RNG_PHILOX if rng_mode is None else rng_mode
+    _capi.check(lib.subg_gset_sample_shard(graph._h, _ptr(q), n, lo, hi, int(num_walks), int(num_steps), int(bucket),
+                                           int(seed) & 0xFFFFFFFFFFFFFFFF, int(rmode), None, _capi.SAMPLE_NO_RANKS,
+                                           st, C.byref(h)))
+    shard = SpG(h, graph.device, n_nodes=graph.N, num_walks=num_walks)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     ev[0].record()
-    prof = os.environ.get("SUBG_PROFILE_HOST") is not None   # per-phase host times (adds a device sync per phase)
-    marks, t_last = [], time.perf_counter()
-
-    def mark(name):
-        nonlocal t_last
-        if prof:
-            torch.cuda.synchronize()
-            t = time.perf_counter()
-            marks.append(f"{name}={1e3 * (t - t_last):.2f}")
-            t_last = t
-    ncol = num_steps + 1
-    enc_local = v["enc"] if "enc" in v else torch.zeros((0, ncol), dtype=torch.int16, device=dev)
-    nsize_local = v["nsize"] if "nsize" in v else torch.zeros(0, dtype=torch.int32, device=dev)
-    # (1) ONE small equal-size all-gather carries every rank's sizes AND its unique LP table (a few hundred to a few
-    # thousand int16 rows; _LP_INLINE_ROWS of them ride along, a larger table falls back to a second exchange)
-    row_b = 2 * ncol
-    blob = torch.zeros(32 + _LP_INLINE_ROWS * row_b, dtype=torch.uint8, device=dev)
-    blob[:32] = torch.tensor([shard.n, shard.T, shard.c, shard.status], dtype=torch.int64).view(torch.uint8).to(dev)
-    c_in = min(shard.c, _LP_INLINE_ROWS)
-    if c_in:
-        blob[32:32 + c_in * row_b] = enc_local[:c_in].contiguous().view(torch.uint8).reshape(-1)
-    blobs = torch.empty((world, blob.numel()), dtype=torch.uint8, device=dev)
-    dist.all_gather_into_tensor(blobs, blob, group=group)
-    hb = blobs.cpu().numpy()
-    counts = hb[:, :32].copy().view(np.int64).reshape(world, 4)
-    n_r, T_r, c_r = counts[:, 0], counts[:, 1], counts[:, 2]
-    n_tot, T_tot = int(n_r.sum()), int(T_r.sum())
-    mark("sizes + LP tables")
-    if int(c_r.max()) <= _LP_INLINE_ROWS:
-        tables = [hb[r, 32:32 + int(c_r[r]) * row_b].copy().view(np.int16).reshape(int(c_r[r]), ncol) for r in range(world)]
-    else:
-        enc_all = torch.empty((int(c_r.sum()), ncol), dtype=torch.int16, device=dev)
-        all_gather_varlen(enc_local.contiguous(), c_r, enc_all, group)
-        enc_np = enc_all.cpu().numpy()
-        offs = np.concatenate([[0], np.cumsum(c_r)])
-        tables = [enc_np[offs[r]:offs[r + 1]] for r in range(world)]
-    merged, maps = merge_lp_tables(tables)
-    merged = np.ascontiguousarray(merged, dtype=np.int16)
-    mark("lp merge")
-    # (2) this rank's ids become global ids, the full SpG is allocated once and every shard lands in place
-    _capi.check(lib.subg_spg_set_lp_table(shard._h, _ptr(maps[rank]), _ptr(merged), merged.shape[0], -1, st))
-    mark("relabel")
+    hdr = np.zeros(8, np.int64)
+    _capi.check(lib.subg_xchg_pack(xc._h, shard._h, graph.N, hdr.ctypes.data, st))
+    # the header all-gather is the barrier: when it completes here, every peer's pack kernel has completed
+    allh = torch.empty((world, 8), dtype=torch.int64, device=tdev)
+    dist.all_gather_into_tensor(allh, torch.from_numpy(hdr).to(tdev), group=group)
+    headers = np.ascontiguousarray(allh.cpu().numpy())
+    if (headers[:, H_FMT] < 0).any():
+        shard.close()
+        raise MemoryError("a shard did not fit its exchange slab")
+    srcs = None
+    staging = None
+    if xc.mode == "nccl" and world > 1:
+        stride = (int(headers[:, H_BYTES].max()) + 4095) & ~4095
+        staging = torch.empty((world, stride), dtype=torch.uint8, device=tdev)
+        dist.all_gather_into_tensor(staging, xc.slab_view(stride), group=group)
+        srcs = (C.c_void_p * world)(*[staging.data_ptr() + r * stride for r in range(world)])
     fh = C.c_void_p()
-    _capi.check(lib.subg_spg_alloc(n_tot, T_tot, graph.device, st, C.byref(fh)))
-    try:
-        p = [C.c_void_p() for _ in range(6)]
-        _capi.check(lib.subg_spg_views(fh, st, *[C.byref(x) for x in p]))
-        g_indices = _view(p[1].value, (T_tot,), "<i4", graph.device, None)
-        g_data = _view(p[2].value, (T_tot,), "<i4", graph.device, None)
-        g_nsize = _view(p[5].value, (n_tot,), "<i4", graph.device, None)
-        # (3) one NCCL group: set sizes, node ids and LP ids of every peer (grouped send / recv over NVLink)
-        ops = []
-        for local, cnt, out in ((nsize_local, n_r, g_nsize), (v["indices"], T_r, g_indices), (v["data"], T_r, g_data)):
-            ops += _p2p_ops(local, cnt, out, group)
-        for w in (dist.batch_isend_irecv(ops) if ops else []):
-            w.wait()
-        mark("shards")
-        _capi.check(lib.subg_spg_seal(fh, st))
-        _capi.check(lib.subg_spg_set_lp_table(fh, None, _ptr(merged), merged.shape[0], ncol, st))
-        mark("seal")
-        if prof and rank == 0:
-            print("[subg host ms] exchange: " + " ".join(marks), file=sys.stderr, flush=True)
-    except Exception:
-        lib.subg_spg_free(fh)
-        raise
-    status = int(np.bitwise_or.reduce(counts[:, 3]))
+    _capi.check(lib.subg_xchg_assemble(xc._h, headers.ctypes.data, srcs, int(num_walks), int(num_steps) + 1, st, C.byref(fh)))
+    if xc.mode == "peer" and world > 1:
+        # nobody may re-pack its slab before every peer has pulled it
+        dist.all_reduce(torch.zeros(1, dtype=torch.int32, device=tdev), group=group)
     shard.close()
     full = SpG(fh, graph.device, n_nodes=graph.N, num_walks=num_walks)
-    full.status = status
     ev[1].record()
-    full.exchange_bytes = 8 * T_tot + 4 * n_tot + 2 * ncol * int(c_r.sum())
-    full.exchange_events = ev   # elapsed = LP-table merge + all-gathers + CSR assembly (device time)
+    received = int(headers[:, H_BYTES].sum() - headers[rank, H_BYTES])
+    full.exchange_mode = xc.mode
+    full.exchange_bytes = int(headers[:, H_BYTES].sum())         # packed bytes of all shards
+    full.exchange_received = received                            # what this GPU read from its peers
+    full.exchange_entry_bytes = 4 + int(headers[rank, H_FMT] & 0xff)
+    full.exchange_events = ev   # elapsed = pack + header all-gather + LP merge + pull (+ end barrier), device time
     return full
 
 
@@ -297,7 +336,11 @@ def sharded_subg_matrix(G, train_idx, num_walks=200, num_steps=4, device=None, s
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device())
     graph = DeviceGraph.from_scipy(G, device)
-    z = sharded_sample(graph, np.asarray(train_idx), num_walks=num_walks, num_steps=num_steps - 1, seed=seed,
-                       rng_mode=rng_mode, group=group)
+    world, _, _ = _group_info(group)
+    deg = np.diff(G.indptr)
+    idx = np.asarray(train_idx)
+    w = 0.5 * num_walks * (num_steps - 1) + 1.5 * np.minimum(deg[idx], num_walks)   # set-size estimate per seed
+    z = sharded_sample(graph, idx, num_walks=num_walks, num_steps=num_steps - 1, seed=seed,
+                       rng_mode=rng_mode, group=group, bounds=partition_by_work(w, world))
     graph.close()
     return z, z.enc_table()

@@ -45,7 +45,8 @@ class _DevView:
 
 def _view(ptr, shape, typestr, dev, owner):
     if ptr is None or any(s == 0 for s in shape):
-        dt = {"<i8": torch.int64, "<i4": torch.int32, "<i2": torch.int16, "<u2": torch.uint16, "<f8": torch.float64}[typestr]
+        dt = {"<i8": torch.int64, "<i4": torch.int32, "<i2": torch.int16, "<u2": torch.uint16, "<f8": torch.float64,
+              "|u1": torch.uint8}[typestr]
         return torch.empty(shape, dtype=dt, device=f"cuda:{dev}")
     return torch.as_tensor(_DevView(ptr, shape, typestr, owner), device=f"cuda:{dev}")
 
@@ -352,8 +353,11 @@ class SpG:
 
     def enc_table(self) -> np.ndarray:
         """int16 [c+1, ncol] LP table with the all-zero row 0 (random_walks.py:81)."""
-        v = self.views()
-        enc = v["enc"].cpu().numpy() if "enc" in v else np.zeros((0, self.ncol), np.int16)
+        p = C.c_void_p()
+        _capi.check(self._lib.subg_spg_enc(self._h, _stream(self.device), C.byref(p)))
+        if self.value_kind or not p.value or self.c == 0 or self.ncol < 1:
+            return np.zeros((1, max(self.ncol, 0)), np.int16)
+        enc = _view(p.value, (self.c, self.ncol), "<i2", self.device, self).cpu().numpy()  # no row compaction (views() would)
         return np.concatenate([np.zeros((1, self.ncol), np.int16), enc], axis=0)
 
     @property

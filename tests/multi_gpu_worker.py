@@ -22,14 +22,24 @@ def main():
     n = A.shape[0]
     q = np.arange(n, dtype=np.int32)
     g = DeviceGraph.from_scipy(A, f"cuda:{local}")
-    for mode in (_capi.SUBG_RNG_RAND_R, _capi.SUBG_RNG_PHILOX):
-        full = SpG.sample(g, q, 60, 3, seed=5, rng_mode=mode)
-        rep = sharded_sample(g, q, 60, 3, seed=5, rng_mode=mode)
-        fv, rv = full.views(), rep.views()
-        for k in ("indptr", "indices", "data"):
-            assert torch.equal(fv[k], rv[k]), k
-        assert np.array_equal(full.enc_table(), rep.enc_table())
-        assert rep.exchange_bytes >= 8 * full.T
+    modes_seen = set()
+    for xmode in ("peer", "nccl"):
+        for mode in (_capi.SUBG_RNG_RAND_R, _capi.SUBG_RNG_PHILOX):
+            full = SpG.sample(g, q, 60, 3, seed=5, rng_mode=mode)
+            rep = sharded_sample(g, q, 60, 3, seed=5, rng_mode=mode, mode=xmode)
+            modes_seen.add(rep.exchange_mode)
+            xz0, p0 = gather(np.stack([q[:500], q[::-1][:500]]).astype(np.int64), full, f"cuda:{local}", True, None)
+            xz1, p1 = gather(np.stack([q[:500], q[::-1][:500]]).astype(np.int64), rep, f"cuda:{local}", True, None)
+            assert torch.equal(xz0, xz1) and torch.equal(p0, p1)     # the scattered result joins in place
+            fv, rv = full.views(), rep.views()
+            for k in ("indptr", "indices", "data"):
+                assert torch.equal(fv[k], rv[k]), k
+            assert np.array_equal(full.enc_table(), rep.enc_table())
+            assert rep.exchange_bytes >= 4 * full.T
+            full.close()
+            if not (xmode == "nccl" and mode == _capi.SUBG_RNG_PHILOX):
+                rep.close()
+    print("EXCHANGE_MODES", sorted(modes_seen), flush=True)
     # queries sliced per rank, joined locally on the replicated SpG, gathered for comparison
     xpe = torch.from_numpy(rep.enc_table()).float().cuda() / 60
     edge = np.random.default_rng(0).integers(0, n, (2, 1024))

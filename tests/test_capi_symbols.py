@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     for name in decl:
         assert hasattr(L, name), f"{name} declared in include/subg_b200.h but not exported"
     assert sorted(_capi.SYMBOLS) == decl
-    assert L.subg_abi_version() == 3
+    assert L.subg_abi_version() == 4
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -58,6 +58,87 @@ def test_shards_concatenate_to_single_call(mid_graph, mode_name, cuts):
         assert np.array_equal(fv["nsize"].cpu().numpy(), nsize) and np.array_equal(merged, enc)
 
 
+def _exchange_in_one_process(g, shards, M, m):
+    """world = len(shards) exchange contexts in ONE process on one GPU: every shard is packed into its own slab and
+    every 'rank' assembles the full SpG reading the slabs through `srcs` (what the NCCL-staged mode does; the peer
+    mode differs only in where the same kernels read from).  Returns the full SpG of every rank."""
+    from surel_plus_b200 import SpG, _capi
+    from surel_plus_b200 import parallel as par
+    from surel_plus_b200.spg import _stream
+    lib = _capi.load()
+    W = len(shards)
+    need = max(par.slab_bytes_needed(s.n, M * m + 1, lp_rows=max(s.c, 1)) for s in shards)
+    ctx = []
+    for r in range(W):
+        h = C.c_void_p()
+        _capi.check(lib.subg_xchg_create(g.device, r, W, need, C.byref(h)))
+        ctx.append(h)
+    headers = np.zeros((W, 8), np.int64)
+    slabs = []
+    for r in range(W):
+        _capi.check(lib.subg_xchg_pack(ctx[r], shards[r]._h, g.N, headers[r].ctypes.data, _stream(g.device)))
+        p = C.c_void_p()
+        _capi.check(lib.subg_xchg_slab(ctx[r], C.byref(p), None))
+        slabs.append(p.value)
+    assert (headers[:, par.H_FMT] >= 0).all()
+    srcs = (C.c_void_p * W)(*slabs)
+    fulls = []
+    for r in range(W):
+        fh = C.c_void_p()
+        _capi.check(lib.subg_xchg_assemble(ctx[r], headers.ctypes.data, srcs, M, m + 1, _stream(g.device), C.byref(fh)))
+        fulls.append(SpG(fh, g.device, n_nodes=g.N, num_walks=M))
+    torch.cuda.synchronize()
+    for h in ctx:
+        lib.subg_xchg_free(h)
+    return fulls, headers
+
+
+@pytest.mark.parametrize("extra", [0, 1, 2, 4])
+@pytest.mark.parametrize("mode_name,cuts", [("RAND_R", (0.5,)), ("PHILOX", (0.1, 0.35, 0.9)), ("PHILOX", (0.0, 0.5))])
+def test_exchange_pack_merge_pull(mid_graph, mode_name, cuts, extra, monkeypatch):
+    """The device-side exchange (csrc/xchg.cu): pack -> LP-table merge -> pull rebuilds exactly the single-call SpG
+    (rows, LP ids, LP table: global first-occurrence order), in every wire format, with an empty shard, and the
+    scattered result joins like the single-GPU one."""
+    from surel_plus_b200 import DeviceGraph, SpG, _capi, gather
+    from surel_plus_b200 import parallel as par
+    A = mid_graph
+    n = A.shape[0]
+    M, m, seed = 50, 3, 7
+    if extra:
+        monkeypatch.setenv("SUBG_XCHG_EXTRA", str(extra))
+    mode = getattr(_capi, f"SUBG_RNG_{mode_name}")
+    q = np.random.default_rng(1).permutation(n).astype(np.int32)
+    g = DeviceGraph.from_scipy(A)
+    full = SpG.sample(g, q, M, m, seed=seed, rng_mode=mode, first_visit_ranks=False)
+    bounds = [0] + [int(c * n) for c in cuts] + [n]
+    shards = []
+    for i in range(len(bounds) - 1):
+        h = C.c_void_p()
+        from surel_plus_b200.spg import _ptr, _stream
+        _capi.check(_capi.load().subg_gset_sample_shard(g._h, _ptr(q), q.size, bounds[i], bounds[i + 1], M, m, -1, seed, mode,
+                                                         None, _capi.SAMPLE_NO_RANKS, _stream(g.device), C.byref(h)))
+        shards.append(SpG(h, g.device, n_nodes=g.N, num_walks=M))
+    reps, headers = _exchange_in_one_process(g, shards, M, m)
+    assert set((headers[:, par.H_FMT] & 0xff).tolist()) <= {extra} or extra == 0
+    xpe = torch.from_numpy(full.enc_table()).float().cuda() / M
+    edge = np.random.default_rng(0).integers(0, n, (2, 700))
+    want_xz, want_ptr = gather(edge, full, "cuda", True, xpe)
+    for rep in reps:
+        assert (rep.n, rep.T, rep.c, rep.max_set) == (full.n, full.T, full.c, full.max_set)
+        assert np.array_equal(rep.enc_table(), full.enc_table())
+        got_xz, got_ptr = gather(edge, rep, "cuda", True, xpe)      # joins the scattered layout in place
+        assert torch.equal(got_xz, want_xz) and torch.equal(got_ptr, want_ptr)
+    fv = full.views()
+    for rep in reps:
+        rv = rep.views()
+        for key in ("indptr", "indices", "data"):
+            assert torch.equal(rv[key], fv[key]), key
+    if mode_name == "RAND_R":  # and that is the reference's single stream (oracle replay)
+        nsize, remap, enc = po.gset_sampler_replay(A.indptr, A.indices, q, M, m, -1, seed)
+        assert np.array_equal(reps[0].enc_table()[1:], enc)
+        assert np.array_equal(reps[0].views()["nsize"].cpu().numpy(), nsize)
+
+
 def test_from_device_csr_roundtrip(mid_graph):
     from surel_plus_b200 import DeviceGraph, SpG, gather
     A = mid_graph

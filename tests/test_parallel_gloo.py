@@ -69,31 +69,20 @@ def _worker(rank, world, port, ret):
         parts = par.assemble_shards(torch.from_numpy(ns), torch.from_numpy(ind), torch.from_numpy(dat),
                                     torch.from_numpy(np.ascontiguousarray(tab)))
         assert parts["indices"].numel() == remap.shape[1] and np.array_equal(parts["enc"], enc)
-        # the exchange the CUDA path uses (parallel.sharded_sample): every array of every peer lands in its slice of
-        # the final arrays through ONE group of sends and receives (parallel._p2p_ops), incl. an int16 table and an
-        # uneven / empty contribution
-        lo, hi = par.partition(n, world, rank)
+        # host-side decisions of the CUDA exchange (parallel.sharded_sample / ShardExchange) that every rank has to
+        # take identically: the peer-mapping vote, and the slab size derived from the largest seed range
+        assert par.agree(True, "cpu") is True
+        assert par.agree(rank == 0, "cpu") is False          # one rank could not map its peers -> all fall back
+        assert par.agree(False, "cpu") is False
+        bounds = par.partition_by_work(np.minimum(np.diff(A.indptr), M) + M * (m - 1.0), world)
+        need = par.slab_bytes_needed(int(np.max(np.diff(bounds))), M * m + 1)
+        t = torch.tensor([need], dtype=torch.int64)
+        both = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(both, t)
+        assert all(int(x) == need for x in both)               # same slab size everywhere without communicating
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
         ns, ind, dat, tab = _local_shard(nsize, remap, enc, lo, hi)
-        counts = par.all_gather_sizes([len(ns), len(ind), len(tab)], "cpu")
-        outs = [torch.empty(int(counts[:, 0].sum()), dtype=torch.int32), torch.empty(int(counts[:, 1].sum()), dtype=torch.int32),
-                torch.empty((int(counts[:, 2].sum()), m + 1), dtype=torch.int16)]
-        ops = []
-        for local, cnt, out in ((torch.from_numpy(ns), counts[:, 0], outs[0]), (torch.from_numpy(ind), counts[:, 1], outs[1]),
-                                (torch.from_numpy(np.ascontiguousarray(tab)), counts[:, 2], outs[2])):
-            ops += par._p2p_ops(local, cnt, out)
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
-        assert np.array_equal(outs[0].numpy(), nsize)
-        shards = [_local_shard(nsize, remap, enc, *par.partition(n, world, r)) for r in range(world)]
-        assert np.array_equal(outs[1].numpy(), np.concatenate([sh[1] for sh in shards]))
-        assert np.array_equal(outs[2].numpy(), np.concatenate([sh[3] for sh in shards]))
-        empty = torch.zeros(0, dtype=torch.int32)
-        mine = torch.arange(5, dtype=torch.int32) if rank == 0 else empty
-        out = torch.full((5,), -1, dtype=torch.int32)
-        ops = par._p2p_ops(mine, np.array([5, 0]), out)
-        for w in (dist.batch_isend_irecv(ops) if ops else []):
-            w.wait()
-        assert out.tolist() == [0, 1, 2, 3, 4]
+        assert need >= 8 * len(ind) + 12 * len(ns) + 16 * len(tab)   # the widest wire format of this rank's shard fits
         ret[rank] = 1
     finally:
         dist.destroy_process_group()
