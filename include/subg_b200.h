@@ -55,6 +55,10 @@ extern "C" {
 #define SUBG_SAMPLE_NO_RANKS 1 /* skip the first-visit ranks (`slot`): the SpG (sorted CSR-of-sets + LP table, what
                                   subg_matrix builds) is identical, only subg_spg_export needs the ranks */
 
+#define SUBG_SAMPLE_DUMP_WALKS 2 /* keep the walks the sampler drew (int32 [n, num_walks, num_steps], subg_spg_walks): feeding
+                                   them back as SUBG_RNG_TRACE, or to a CPU restatement of subg_acc.c:778-844, must
+                                   reproduce the SpG bit for bit -- the parity hook of the Philox fast path */
+
 /* structure encoders of utils.py:20-39 (the 'DEG' branch is broken upstream and not provided) */
 #define SUBG_ENCODER_NONE 0
 #define SUBG_ENCODER_PPR  1 /* utils.py:35-36 */
@@ -150,6 +154,16 @@ int subg_spg_rows(const subg_spg *s, const int64_t **rowbeg, const int32_t **nsi
 /* The LP table alone: enc int16[c, ncol] on the device (c, ncol from subg_spg_info), without compacting the rows as
  * subg_spg_views does.  Work queued on `stream` afterwards is ordered behind the kernels that fill the table. */
 int subg_spg_enc(const subg_spg *s, void *stream, const int16_t **enc);
+
+/* Rows in seed order -> one row per graph node: row seeds[i] = set i, every other row empty.  This is the (N, N) matrix
+ * subg_matrix builds for a query that is not arange(N) (csr_matrix((data, (repeat(idx, nsize), nodes)), (N, N)),
+ * sampler/random_walks.py:79), so that SpJoin can index rows by node id.  Seeds must be distinct.  The entries are not
+ * moved.  Afterwards subg_spg_info reports n = num_nodes. */
+int subg_spg_expand_rows(subg_spg *s, int64_t num_nodes, void *stream);
+
+/* The walks kept by SUBG_SAMPLE_DUMP_WALKS: int32 [n, num_walks, num_steps] on the device (NULL otherwise);
+ * walk w of seed i visits walks[i][w][0..num_steps) after the seed itself. */
+int subg_spg_walks(const subg_spg *s, void *stream, const int32_t **walks);
 
 /* Wrap an existing CSR (e.g. the scipy matrix produced by the reference's
  * subg_matrix / topk_ppr_matrix+encoding) as an SpG for the join.

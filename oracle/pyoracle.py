@@ -270,6 +270,40 @@ def scipy_pair_join(edge, x):
     return left, right, ma.getnnz(axis=1), mb.getnnz(axis=1)
 
 
+def scipy_pgather(edge, x, njobs: int = 4):
+    """pgather (train.py:88-111) restated for the SpJoin CPU baseline: the batch is split into `njobs` column blocks,
+    one Python thread per block runs the bgather formulation (scipy_pair_join), and the blocks are concatenated
+    [all left | all right] with the cumulative segment pointer.  Returns (xz int [N,2], indptr int64 [2B+1])."""
+    import threading
+    blocks = np.array_split(np.asarray(edge), njobs, axis=1)
+    out = [None] * njobs
+
+    def work(i):
+        out[i] = scipy_pair_join(blocks[i], x)
+    th = [threading.Thread(target=work, args=(i,)) for i in range(njobs)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    xz = np.vstack([*[o[0] for o in out], *[o[1] for o in out]])
+    indptr = np.cumsum(np.concatenate([[0], *[o[2] for o in out], *[o[3] for o in out]])).astype(np.int64)
+    return xz, indptr
+
+
+def scipy_triplet_join(hedge, x):
+    """hgather (train.py:48-72) restated with the same scipy CSR algebra: segments [u|w, w|u, v|w, w|v]."""
+    u, v, w = x[hedge[0]], x[hedge[1]], x[hedge[2]]
+    mu, mv, mw = u > 0, v > 0, w > 0
+    parts = []
+    for a, b, ma, mb in ((u, w, mu, mw), (v, w, mv, mw)):
+        ba = b.multiply(ma) + ma
+        ab = a.multiply(mb) + mb
+        parts.append(np.stack([a.data, ba.data - 1]).T)
+        parts.append(np.stack([b.data, ab.data - 1]).T)
+    sizes = np.concatenate([mu.getnnz(axis=1), mw.getnnz(axis=1), mv.getnnz(axis=1), mw.getnnz(axis=1)])
+    return np.vstack(parts), np.repeat(np.arange(len(sizes), dtype=np.int64), sizes)
+
+
 # ------------------------------------------------------------------------- PPR
 def ppr_push(indptr, indices, deg, node: int, alpha: float, eps: float, cap: int = 1 << 16):
     """sampler/pprgo.py:9-38 for one seed: (keys int64, vals float32) in p-insertion order."""

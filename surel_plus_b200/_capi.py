@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "_lib", "libsubg_b200.so")
 
 SUBG_RNG_PHILOX, SUBG_RNG_RAND_R, SUBG_RNG_TRACE = 0, 1, 2
 STATUS_BUCKET_OVERFLOW, STATUS_DEAD_END, STATUS_PPR_SECOND_PASS = 1, 2, 4
-SAMPLE_NO_RANKS = 1
+SAMPLE_NO_RANKS, SAMPLE_DUMP_WALKS = 1, 2
 ENCODER_NONE, ENCODER_PPR, ENCODER_SPD = 0, 1, 2
 TIMING_SAMPLER, TIMING_SPJOIN, TIMING_BUILD, TIMING_PPR, TIMING_EXCHANGE = 0, 1, 2, 3, 4
 
@@ -22,7 +22,7 @@ TIMING_SAMPLER, TIMING_SPJOIN, TIMING_BUILD, TIMING_PPR, TIMING_EXCHANGE = 0, 1,
 SYMBOLS = [
     "subg_abi_version", "subg_last_error",
     "subg_graph_create", "subg_graph_from_edges", "subg_graph_export", "subg_graph_info", "subg_graph_free",
-    "subg_gset_sample", "subg_gset_sample_shard", "subg_spg_set_lp_table", "subg_spg_info", "subg_spg_export", "subg_spg_views", "subg_spg_rows", "subg_spg_enc",
+    "subg_gset_sample", "subg_gset_sample_shard", "subg_spg_set_lp_table", "subg_spg_info", "subg_spg_export", "subg_spg_views", "subg_spg_rows", "subg_spg_enc", "subg_spg_walks", "subg_spg_expand_rows",
     "subg_spg_from_csr", "subg_spg_alloc", "subg_spg_seal", "subg_spg_free",
     "subg_xchg_create", "subg_xchg_export", "subg_xchg_open", "subg_xchg_slab", "subg_xchg_pack", "subg_xchg_assemble", "subg_xchg_free",
     "subg_spjoin_plan", "subg_spjoin_run", "subg_spjoin",
@@ -66,6 +66,8 @@ def load() -> C.CDLL:
     L.subg_spg_export.argtypes = [vp, vp, vp, vp, vp, vp]
     L.subg_spg_views.argtypes = [vp, vp] + [C.POINTER(vp)] * 6
     L.subg_spg_enc.argtypes = [vp, vp, C.POINTER(vp)]
+    L.subg_spg_expand_rows.argtypes = [vp, i64, vp]
+    L.subg_spg_walks.argtypes = [vp, vp, C.POINTER(vp)]
     L.subg_spg_rows.argtypes = [vp] + [C.POINTER(vp)] * 4 + [C.POINTER(i64)]
     L.subg_spg_from_csr.argtypes = [vp, vp, vp, i32, i64, i64, i32, vp, C.POINTER(vp)]
     L.subg_spg_alloc.argtypes = [i64, i64, i32, vp, C.POINTER(vp)]

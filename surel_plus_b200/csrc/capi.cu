@@ -68,6 +68,7 @@ int spg_set_lp_table_impl(SpG *s, const int32_t *id_map_hd, const int16_t *enc_h
                           cudaStream_t st);
 int spg_export_impl(const SpG *s, int32_t *nsize_hd, int32_t *remap_hd, int16_t *enc_hd, int16_t *raw_hd,
                     cudaStream_t st);
+int spg_expand_rows_impl(SpG *s, int64_t num_nodes, cudaStream_t st);
 int spg_from_csr_impl(const int64_t *indptr_hd, const int32_t *indices_hd, const void *data_hd, int value_kind,
                       int64_t n_rows, int64_t nnz, int device, cudaStream_t st, SpG **out);
 int spg_alloc_impl(int64_t n, int64_t T, int device, cudaStream_t st, SpG **out);
@@ -294,6 +295,19 @@ int subg_spg_enc(const subg_spg *s_, void *stream, const int16_t **enc) {
     DeviceGuard guard(s->device);
     s->tag.use_on((cudaStream_t)stream);
     *enc = s->enc;
+    return SUBG_OK;
+}
+
+int subg_spg_expand_rows(subg_spg *s, int64_t num_nodes, void *stream) {
+    return spg_expand_rows_impl(reinterpret_cast<SpG *>(s), num_nodes, (cudaStream_t)stream);
+}
+
+int subg_spg_walks(const subg_spg *s_, void *stream, const int32_t **walks) {
+    const SpG *s = reinterpret_cast<const SpG *>(s_);
+    if (!s || !walks) return fail(SUBG_ERR_ARG, "null SpG");
+    DeviceGuard guard(s->device);
+    s->tag.use_on((cudaStream_t)stream);
+    *walks = s->walks;
     return SUBG_OK;
 }
 

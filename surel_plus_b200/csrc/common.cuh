@@ -153,6 +153,7 @@ struct SpG {
     int32_t shift = 0;           // bits per LP column in the key (32 - clz(M))
     int32_t *nsize = nullptr;    // [n]
     int32_t *seeds = nullptr;    // [n] node id of each row
+    int32_t *walks = nullptr;    // [n, M, m] the walks the sampler drew (SUBG_SAMPLE_DUMP_WALKS only)
     int64_t pushes = 0;          // PPR sampler: forward pushes performed (measurement)
     int num_sms = 148;
     // per-handle SpJoin scratch, kept between batches (handles are not thread-safe)

@@ -53,6 +53,7 @@ struct SamplerArgs {
     uint32_t rng_lo, rng_hi;
     const int64_t *call_base;  // RAND_R: exclusive prefix of rand_r calls, global seed index
     const int32_t *walks;      // TRACE: chunk-local [n_chunk, M, m]
+    int32_t *dump_walks;       // nullable, chunk-local [n_chunk, M, m]: the walks drawn (SUBG_SAMPLE_DUMP_WALKS)
     // output rows: row i occupies [rowbeg[i], rowbeg[i] + nsize[i]) of the three arrays
     int32_t *out_node;
     int32_t *out_prov;
@@ -404,7 +405,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
                         rr0 += rstep;
                         if (rr0 >= d) rr0 -= d;
                     }
-                    if (w < M) keys[1 + w] = ((K)cur[tt] << OB) | (K)(((uint32_t)w + 1u) << LS);
+                    if (w < M) {
+                        keys[1 + w] = ((K)cur[tt] << OB) | (K)(((uint32_t)w + 1u) << LS);
+                        if (a.dump_walks) a.dump_walks[(i * M + w) * m] = (int32_t)cur[tt];
+                    }
                 }
                 // ---- later hops, uniform with replacement (subg_acc.c:802-809)
                 uint32_t rst[kGW];
@@ -445,6 +449,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
                                 atomicOr(a.status, SUBG_STATUS_DEAD_END);
                             }
                             keys[1 + s * M + w] = ((K)cur[tt] << OB) | (K)((((uint32_t)w + 1u) << LS) | (uint32_t)s);
+                            if (a.dump_walks) a.dump_walks[(i * M + w) * m + s] = (int32_t)cur[tt];
                         }
                     }
                 }

@@ -15,7 +15,7 @@
 #include <string>
 #include <vector>
 
-#include "sampler.cuh"
+#include "sampler_hash.cuh"
 #include "scan.cuh"
 
 namespace subg {
@@ -38,6 +38,9 @@ static cudaError_t launch_gset_sample_k64(const SamplerArgs &a, int EPL, int num
     if (EPL <= 33) return launch_gset_sample_k64c(a, EPL, num_sms, st);
     return launch_gset_sample_k64d(a, EPL, num_sms, st);
 }
+// implemented in sampler_hash32.cu / sampler_hash64.cu (TOP = keys per lane of the largest sort class)
+cudaError_t launch_gset_hash_k32(const SamplerArgs &a, const HashPlan &hp, int TOP, int num_sms, cudaStream_t st);
+cudaError_t launch_gset_hash_k64(const SamplerArgs &a, const HashPlan &hp, int TOP, int num_sms, cudaStream_t st);
 static const int kEplList[] = {3, 5, 7, 9, 11, 13, 15, 17, 19, 21, 25, 29, 33, 41, 49, 63};
 
 static int ceil_log2(uint64_t x) {
@@ -189,7 +192,8 @@ __global__ void row_sizes_kernel(const long long *indptr, int64_t n, int32_t *ns
 static void free_spg_arrays(SpG *s, cudaStream_t st) {
     if (s->rowbeg && (void *)s->rowbeg != (void *)s->indptr) dfree(s->rowbeg, st);
     dfree(s->indptr, st); dfree(s->indices, st); dfree(s->data, st); dfree(s->slot, st);
-    dfree(s->enc, st); dfree(s->nsize, st); dfree(s->seeds, st); dfree(s->lp_key, st); dfree(s->lp_pos, st);
+    dfree(s->enc, st); dfree(s->nsize, st); dfree(s->seeds, st); dfree(s->lp_key, st); dfree(s->lp_pos, st); dfree(s->walks, st);
+    s->walks = nullptr;
     s->indptr = nullptr; s->rowbeg = nullptr; s->indices = nullptr; s->data = nullptr; s->slot = nullptr;
     s->enc = nullptr; s->nsize = nullptr; s->seeds = nullptr; s->lp_key = nullptr; s->lp_pos = nullptr;
 }
@@ -288,6 +292,41 @@ static int make_plan(const Graph *g, int M, int m, int bucket, SamplePlan *p) {
     return SUBG_OK;
 }
 
+// The hash-dedup kernel (sampler_hash.cuh) takes the configurations of the fast path: Philox draws, no first-visit
+// ranks, no bucket cap, LP row in 32 bits, at most 8 walks per lane and 608 visits per seed.
+struct HashChoice {
+    bool ok = false, key64 = false;
+    int TOP = 0;
+    HashPlan hp{};
+};
+static HashChoice choose_hash(const Graph *g, const SamplePlan &pl, int M, int m, int rng_mode, bool want_rank) {
+    HashChoice c;
+    if (env_i64("SUBG_SAMPLER_HASH", 1) == 0) return c;
+    if (rng_mode != SUBG_RNG_PHILOX || want_rank || pl.stride < pl.Kt || pl.lp64 || M > 256 || pl.Kt > 608 || pl.OB > 16) return c;
+    for (int t : {3, 7, 13, 19})
+        if (32 * t >= pl.Kt) { c.TOP = t; break; }
+    if (!c.TOP) return c;
+    const int nbits = std::max(1, ceil_log2((uint64_t)std::max<int64_t>(g->N, 2)));
+    c.hp.IB = std::max(1, ceil_log2((uint64_t)pl.Kt + 1));
+    const int need_bits = nbits + std::max(pl.OB, c.hp.IB);
+    if (need_bits > 64) return c;
+    c.key64 = need_bits > 32;
+    const int ksz = c.key64 ? 8 : 4;
+    int cap = ((int)(pl.Kt * 1.28) + 31) & ~31;
+    cap = std::max(cap, (33 * c.TOP + 31) & ~31);      // the padded sorted list of the largest class lives in the key area
+    cap = (int)env_i64("SUBG_HASH_CAP", cap);
+    cap = std::max((cap + 31) & ~31, (33 * c.TOP + 31) & ~31);
+    if (cap <= pl.Kt) return c;
+    c.hp.cap = cap;
+    c.hp.cnt_off = (cap * ksz + 15) & ~15;
+    c.hp.ord_off = c.hp.cnt_off + 4 * cap;
+    int total = (c.hp.ord_off + 2 * pl.Kt + 15) & ~15;
+    total = std::max(total, (8 * M + 8 * pl.fy_cap + 15) & ~15);   // Fisher-Yates scratch overlays the table
+    c.hp.smem_per_warp = total;
+    c.ok = true;
+    return c;
+}
+
 // seeds_hd holds the whole query (n_all entries); the sets of the window [lo, hi) are sampled.  Seed
 // indices stay global (Philox counters, rand_r call offsets, first-occurrence positions), so the
 // shards of a range-partitioned query concatenate to exactly the single-call result.
@@ -306,6 +345,7 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
     const bool want_rank = want_slot || pl.stride < pl.Kt;
 
     g->tag.use_on(st);
+    const HashChoice hc = choose_hash(g, pl, M, m, rng_mode, want_rank);
     SpG *s = new SpG();
     s->tag.last = st;
     s->device = g->device; s->n = n; s->ncol = m + 1; s->M = M; s->num_sms = g->num_sms; s->value_kind = 0;
@@ -384,6 +424,8 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
             if (bad) { rc = fail(SUBG_ERR_ARG, "query contains node ids outside [0, N)"); goto done; }
         }
 
+        if ((flags & SUBG_SAMPLE_DUMP_WALKS) && rng_mode != SUBG_RNG_TRACE && n > 0)
+            CK(dmalloc(&s->walks, (size_t)n * M * m, st));
         prof.mark("setup");
         // Rows are written once, at a cursor, into arrays sized for the worst case (rowcap entries per
         // seed).  If that does not fit the budget the seeds go through in chunks and every chunk is
@@ -451,6 +493,7 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
                 a.rng_mode = rng_mode; a.rng_lo = (uint32_t)seed; a.rng_hi = (uint32_t)(seed >> 32);
                 a.call_base = (const int64_t *)call_base;
                 a.walks = d_walks ? d_walks + base * (int64_t)M * m : nullptr;
+                a.dump_walks = s->walks ? s->walks + base * (int64_t)M * m : nullptr;
                 a.out_node = chunked ? c_node : s->indices;
                 a.out_prov = chunked ? c_prov : (int32_t *)s->data;
                 a.out_slot = chunked ? c_slot : s->slot;
@@ -462,8 +505,9 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
                     // bound by that count, so shared memory is capped to leave about 80 KB of the SM to L1 (sweep: profiles/r1_sampler_sweeps.txt)
                     const int64_t csr_bytes = 4 * g->E + 8 * g->N;
                     int cap_blocks = 0;
+                    const int warp_smem = hc.ok ? hc.hp.smem_per_warp : pl.smem_per_warp;
                     if (csr_bytes > (96ll << 20))
-                        cap_blocks = std::max(2, (int)((152 << 10) / (kWarpsPerBlock * pl.smem_per_warp + 1024)));
+                        cap_blocks = std::max(2, (int)((152 << 10) / (kWarpsPerBlock * warp_smem + 1024)));
                     a.blocks_per_sm = (int)env_i64("SUBG_SAMPLER_BLOCKS", cap_blocks);
                 }
                 a.tab_key = tab_key; a.tab_pos = tab_pos; a.tab_mask = tab_cap - 1;
@@ -484,8 +528,12 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
                 }
                 prof.mark("table_init");
                 timing_begin(SUBG_TIMING_SAMPLER, st);
-                CK(pl.key64 ? launch_gset_sample_k64(a, pl.EPL, g->num_sms, st)
-                            : launch_gset_sample_k32(a, pl.EPL, g->num_sms, st));
+                if (hc.ok)
+                    CK(hc.key64 ? launch_gset_hash_k64(a, hc.hp, hc.TOP, g->num_sms, st)
+                                : launch_gset_hash_k32(a, hc.hp, hc.TOP, g->num_sms, st));
+                else
+                    CK(pl.key64 ? launch_gset_sample_k64(a, pl.EPL, g->num_sms, st)
+                                : launch_gset_sample_k32(a, pl.EPL, g->num_sms, st));
                 timing_end(SUBG_TIMING_SAMPLER, st);
                 count_launch(1);
                 if (l2_persist) {
@@ -690,6 +738,42 @@ int spg_seal_impl(SpG *s, cudaStream_t st) {
     dfree(scratch, st); dfree(d_max, st);
     if (total != s->T) return fail(SUBG_ERR_ARG, "set sizes do not add up to the number of entries");
     s->max_set = mx;
+    return SUBG_OK;
+}
+
+// Rows in seed order -> one row per graph node (what subg_matrix's csr_matrix((data, (repeat(idx, nsize), nodes)), (N, N))
+// gives for a query that is not arange(N), random_walks.py:79): row idx[i] = set i, every other row empty.  The entries stay
+// where they are (scattered layout); only the row table is rebuilt.
+__global__ void expand_rows_kernel(const int32_t *seeds, const long long *rowbeg, const int32_t *nsize, int64_t n,
+                                   long long *out_rowbeg, int32_t *out_nsize) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t u = seeds[i];
+        out_rowbeg[u] = rowbeg[i];
+        out_nsize[u] = nsize[i];
+    }
+}
+int spg_expand_rows_impl(SpG *s, int64_t num_nodes, cudaStream_t st) {
+    if (!s || num_nodes < 0) return fail(SUBG_ERR_ARG, "Input parsing error.");
+    if (!s->seeds || !s->nsize) return fail(SUBG_ERR_ARG, "expand needs a sampler-built SpG (rows in seed order)");
+    DeviceGuard guard(s->device);
+    s->tag.use_on(st);
+    long long *rb = nullptr;
+    int32_t *ns = nullptr;
+    SUBG_CUDA(dmalloc(&rb, (size_t)std::max<int64_t>(num_nodes, 1), st));
+    SUBG_CUDA(dmalloc(&ns, (size_t)std::max<int64_t>(num_nodes, 1), st));
+    SUBG_CUDA(cudaMemsetAsync(rb, 0, (size_t)std::max<int64_t>(num_nodes, 1) * 8, st));
+    SUBG_CUDA(cudaMemsetAsync(ns, 0, (size_t)std::max<int64_t>(num_nodes, 1) * 4, st));
+    if (s->n > 0) {
+        const unsigned blocks = (unsigned)std::min<int64_t>((s->n + 255) / 256, 4 * (int64_t)s->num_sms);
+        expand_rows_kernel<<<blocks, 256, 0, st>>>(s->seeds, (const long long *)s->rowbeg, s->nsize, s->n, rb, ns);
+        SUBG_CUDA(cudaGetLastError());
+        count_launch(1);
+    }
+    if (s->indptr) dfree(s->indptr, st);                       // compact layout: rowbeg aliases indptr
+    else dfree(s->rowbeg, st);
+    dfree(s->nsize, st); dfree(s->seeds, st);
+    s->indptr = nullptr; s->rowbeg = (int64_t *)rb; s->nsize = ns; s->seeds = nullptr;
+    s->n = num_nodes;
     return SUBG_OK;
 }
 

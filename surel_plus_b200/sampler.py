@@ -15,13 +15,15 @@ def subg_matrix(G, train_idx, num_walks=200, num_steps=4, device="cuda", seed=11
     (random_walks.py:78)."""
     print(f'Start sampling for #{len(train_idx)} nodes with {num_walks} {num_steps}-step walks')
     idx = np.asarray(train_idx)
-    if idx.shape[0] != G.shape[0] or not np.array_equal(idx, np.arange(G.shape[0])):
-        raise NotImplementedError("subg_matrix expects train_idx == arange(G.shape[0]) (as every reference caller passes)")
     own = graph is None
     if own:
         graph = DeviceGraph.from_scipy(G, device)
     z = SpG.sample(graph, idx, num_walks=num_walks, num_steps=num_steps - 1, seed=seed,
                    rng_mode=_capi.SUBG_RNG_PHILOX if rng_mode is None else rng_mode, first_visit_ranks=False)
+    if idx.shape[0] != G.shape[0] or not np.array_equal(idx, np.arange(G.shape[0])):
+        # a subset / permutation of the nodes: the reference's (N, N) matrix has row idx[i] = set i and empty rows
+        # elsewhere (random_walks.py:79); only the row table is rebuilt, the entries stay in place
+        z.expand_rows(G.shape[0])
     if own:
         graph.close()
     return z, z.enc_table()

@@ -224,11 +224,12 @@ class SpG:
     # ---- construction -------------------------------------------------------
     @classmethod
     def sample(cls, graph: DeviceGraph, query, num_walks=100, num_steps=3, bucket=-1, seed=111413,
-               rng_mode=_capi.SUBG_RNG_PHILOX, walks=None, first_visit_ranks=True) -> "SpG":
+               rng_mode=_capi.SUBG_RNG_PHILOX, walks=None, first_visit_ranks=True, dump_walks=False) -> "SpG":
         """Walk-based set sampling + LP encoding + SpG build on the device
         (subg_acc.c:649-1034 and random_walks.py:79).  `num_steps` is the walk length m.
         first_visit_ranks=False skips the per-entry first-visit rank that only export_reference()
-        (the reference's `remap` order) needs; the SpG itself is identical."""
+        (the reference's `remap` order) needs; the SpG itself is identical.  dump_walks=True keeps the
+        walks the kernel drew (walks()): the parity hook of the Philox path."""
         lib = _capi.load()
         if isinstance(query, torch.Tensor):
             q = query.to(torch.int32).contiguous()
@@ -246,9 +247,12 @@ class SpG:
         h = C.c_void_p()
         _capi.check(lib.subg_gset_sample(graph._h, _ptr(q), n, int(num_walks), int(num_steps), int(bucket),
                                          int(seed) & 0xFFFFFFFFFFFFFFFF, int(rng_mode), _ptr(w) if w is not None else None,
-                                         0 if first_visit_ranks else _capi.SAMPLE_NO_RANKS, _stream(graph.device),
+                                         (0 if first_visit_ranks else _capi.SAMPLE_NO_RANKS)
+                                         | (_capi.SAMPLE_DUMP_WALKS if dump_walks else 0), _stream(graph.device),
                                          C.byref(h)))
-        return cls(h, graph.device, n_nodes=graph.N, num_walks=num_walks)
+        out = cls(h, graph.device, n_nodes=graph.N, num_walks=num_walks)
+        out.num_steps = int(num_steps)
+        return out
 
     @classmethod
     def from_scipy(cls, x, device="cuda") -> "SpG":
@@ -311,6 +315,22 @@ class SpG:
             if p[5].value:
                 out["nsize"] = _view(p[5].value, (self.n,), "<i4", d, self)
         return out
+
+    def expand_rows(self, num_nodes: int) -> "SpG":
+        """Rows in seed order -> one (possibly empty) row per graph node (subg_spg_expand_rows): what
+        subg_matrix's (N, N) csr_matrix is for a query that is not arange(N)."""
+        _capi.check(self._lib.subg_spg_expand_rows(self._h, int(num_nodes), _stream(self.device)))
+        self.n = int(num_nodes)
+        self.shape = (self.n, self.shape[1])
+        return self
+
+    def walks(self) -> torch.Tensor:
+        """int32 [n, num_walks, num_steps] view of the walks kept by sample(..., dump_walks=True)."""
+        p = C.c_void_p()
+        _capi.check(self._lib.subg_spg_walks(self._h, _stream(self.device), C.byref(p)))
+        if not p.value:
+            raise RuntimeError("this SpG was sampled without dump_walks=True")
+        return _view(p.value, (self.n, self.num_walks, self.ncol - 1), "<i4", self.device, self)
 
     def set_sizes(self) -> torch.Tensor:
         """int32 [n] set sizes without forcing the CSR layout."""

@@ -36,9 +36,9 @@ def main():
                 assert torch.equal(fv[k], rv[k]), k
             assert np.array_equal(full.enc_table(), rep.enc_table())
             assert rep.exchange_bytes >= 4 * full.T
-            full.close()
             if not (xmode == "nccl" and mode == _capi.SUBG_RNG_PHILOX):
                 rep.close()
+                full.close()
     print("EXCHANGE_MODES", sorted(modes_seen), flush=True)
     # queries sliced per rank, joined locally on the replicated SpG, gathered for comparison
     xpe = torch.from_numpy(rep.enc_table()).float().cuda() / 60

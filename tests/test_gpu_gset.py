@@ -161,3 +161,39 @@ def test_subg_acc_module_signature(small_graph):
     # callers then do remap[1]+1, np.repeat(idx, nsize), np.insert(enc, 0, ...) (random_walks.py:79-81)
     z, enc0 = po.subg_matrix_from(out[0], out[1], out[2], q, A.shape[0], 4)
     assert z.nnz == out[0].sum() and enc0.shape[0] == out[2].shape[0] + 1
+
+
+def test_subg_matrix_on_a_permuted_subset_of_the_nodes(small_graph):
+    """subg_matrix(G, idx) with idx != arange(N): the reference builds an (N, N) matrix with row idx[i] = set i and
+    empty rows elsewhere (random_walks.py:79); here the device SpG's row table is expanded (subg_spg_expand_rows).
+    Checked against the oracle's replay of the same stream, through the top-level `subg_acc` name as well."""
+    import subg_acc as top
+    from surel_plus_b200 import _capi, gather, subg_matrix
+    A = small_graph
+    N, M, K = A.shape[0], 30, 4
+    idx = np.random.default_rng(3).permutation(N)[: N // 3].astype(np.int64)
+    z, enc0 = subg_matrix(A, idx, num_walks=M, num_steps=K, seed=77, rng_mode=_capi.SUBG_RNG_RAND_R)
+    nsize, remap, enc = po.gset_sampler_replay(A.indptr, A.indices, idx, M, K - 1, -1, 77)
+    keep = np.repeat(np.diff(A.indptr)[idx] > 0, nsize)
+    remap = remap.copy()
+    remap[0][~keep] = np.repeat(idx, nsize)[~keep]        # isolated seeds: the reference leaves the id unwritten
+    z_ref, enc_ref = po.subg_matrix_from(nsize, remap, enc, idx, N, K)
+    assert z.shape == (N, N) and z.n == N
+    got = z.to_scipy()
+    assert np.array_equal(got.indptr, z_ref.indptr) and np.array_equal(got.indices, z_ref.indices)
+    assert np.array_equal(got.data, z_ref.data) and np.array_equal(enc0, enc_ref)
+    # joins index rows by node id; nodes outside idx have empty sets
+    edge = np.random.default_rng(4).integers(0, N, (2, 300))
+    xz, ptr = gather(edge, z, "cuda", True, None)
+    want, sl, sr = po.spjoin_pair(z_ref, edge)
+    assert np.array_equal(xz.cpu().numpy()[..., 0].astype(np.int64), want)
+    assert np.array_equal(ptr.cpu().numpy(), po.pair_index(sl, sr, True))
+    # the reference's own call through the top-level module name, then its 3-line CSR build (random_walks.py:77-81)
+    os_env = __import__("os").environ
+    os_env["SUBG_RNG"] = "rand_r"
+    try:
+        ns2, rm2, enc2 = top.gset_sampler(A.indptr.astype(np.int32), A.indices.astype(np.int32), idx, num_walks=M, num_steps=K - 1, seed=77)
+    finally:
+        os_env.pop("SUBG_RNG", None)
+    z2, _ = po.subg_matrix_from(ns2, rm2, enc2, idx, N, K)
+    assert (z2 != z_ref).nnz == 0

@@ -106,3 +106,50 @@ def test_integration_md_python_blocks_parse_and_name_real_symbols():
     declared = set(re.findall(r"\b(subg_[a-z0-9_]+)\s*\(", re.sub(r"/\*.*?\*/", "", header, flags=re.S)))
     used = set(re.findall(r"L\.(subg_[a-z0-9_]+)", text))
     assert used and used <= declared, sorted(used - declared)
+
+
+def test_top_level_subg_acc_is_the_b200_module():
+    """`from subg_acc import gset_sampler, walk_sampler` (sampler/random_walks.py:18) resolves to this repository."""
+    import subg_acc
+    from surel_plus_b200 import subg_acc as ours
+    assert subg_acc.gset_sampler is ours.gset_sampler and subg_acc.walk_sampler is ours.walk_sampler
+    assert subg_acc.walk_join is ours.walk_join and subg_acc.batch_sampler is ours.batch_sampler
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.reference
+def test_unmodified_reference_sampler_module_binds_the_shim():
+    """The reference's sampler/random_walks.py, imported UNMODIFIED from /root/reference, picks up this repository's
+    `subg_acc` (north star: "sampler/ runs unchanged").  Its other imports are not in this image (fastremap, and
+    utils / dataloader pull in torch_geometric + ogb): they are stubbed with the few names subg_matrix uses."""
+    import importlib.util
+    import os
+    import sys
+    import types
+    import scipy.sparse as sp
+    ref_root = "/root/reference"
+    saved = {k: sys.modules.get(k) for k in ("fastremap", "utils", "dataloader")}
+    saved_path = list(sys.path)
+    try:
+        sys.modules["fastremap"] = types.ModuleType("fastremap")
+        for name in ("utils", "dataloader"):
+            mod = types.ModuleType(name)
+            mod.np, mod.csr_matrix = np, sp.csr_matrix
+            mod.__all__ = ["np", "csr_matrix"]
+            sys.modules[name] = mod
+        spec = importlib.util.spec_from_file_location("ref_random_walks", os.path.join(ref_root, "sampler", "random_walks.py"))
+        rw = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(rw)      # runs `sys.path.append(/root/reference)` and `from subg_acc import ...`
+        from surel_plus_b200 import subg_acc as ours
+        assert rw.gset_sampler is ours.gset_sampler and rw.walk_sampler is ours.walk_sampler
+        # the body of the reference's subg_matrix needs exactly these names besides the sampler
+        assert callable(rw.subg_matrix) and rw.csr_matrix is sp.csr_matrix
+    finally:
+        sys.path[:] = saved_path
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v

@@ -102,6 +102,9 @@ def test_pair_join_equals_reference_gather(spjoin):
     # the scipy restatement used as the SpJoin CPU baseline computes the same rows
     left, right, nl2, nr2 = po.scipy_pair_join(edge, z)
     assert np.array_equal(np.vstack([left, right]), xz)
+    # ... and so does the threaded pgather restatement (train.py:88-111, njobs = 4), incl. its segment pointer
+    xz4, ptr4 = po.scipy_pgather(edge, z, njobs=4)
+    assert np.array_equal(xz4, xz) and np.array_equal(ptr4, spjoin["pair_ptr"])
 
 
 def test_triplet_join_equals_reference_hgather(spjoin):
@@ -111,6 +114,8 @@ def test_triplet_join_equals_reference_hgather(spjoin):
     xz, sizes = po.spjoin_triplet(z, hedge)
     assert np.array_equal(xpe[xz], spjoin["trip_xz"])
     assert np.array_equal(np.repeat(np.arange(4 * hedge.shape[1]), sizes), spjoin["trip_ind"])
+    xz2, ind2 = po.scipy_triplet_join(hedge, z)     # the scipy restatement timed as the triplet CPU baseline
+    assert np.array_equal(xz2, xz) and np.array_equal(ind2, spjoin["trip_ind"])
 
 
 def _adj(gset):
