@@ -240,6 +240,28 @@ int subg_spjoin(const subg_spg *s, const int64_t *edge_hd, int64_t B, int arity,
                 int64_t *indptr_dev, const float *enc_table_dev, int k, void *out_dev, int64_t out_capacity,
                 int64_t *segid_dev, int64_t *N_out, int *ran, void *stream);
 
+/* The per-batch join of a training / evaluation loop (train.py:121-127: one gather per mini-batch of 1024 queries;
+ * main_horder.py:33: 2048 triplets) without allocation or host synchronisation: a joiner fixes the SpG, the batch size,
+ * the arity, the LP table and the output capacity, and captures [plan -> join -> row count to pinned memory] as a CUDA
+ * graph for each of `depth` ring slots.  submit copies the batch's edges (int64[arity*B]; edge_on_device: 1 device memory,
+ * 0 host memory, < 0 ask the driver) into the next slot and launches its graph on `stream` (host edges: one memcpy into
+ * pinned staging + one cudaGraphLaunch; device edges: a copy on the stream + the same kernels launched directly); it
+ * returns the slot's device buffers at once:
+ *   out_dev     rows [0, N) of the layout of subg_spjoin_run; rows beyond N are not written
+ *   indptr_dev  int64[nseg+1] segment pointers (train.py:21-30)      segid_dev  int64 rows' segment ids (want_segid)
+ *   nrows_dev   int64[2] on the device: {N, bad-node flag}
+ * A slot is reused after `depth` submits: consume (or copy) its buffers on the same stream before that.
+ * rows waits for the slot's last batch and returns N; SUBG_ERR_MEM if N exceeded capacity_rows (the batch was not
+ * joined: run it through subg_spjoin), SUBG_ERR_ARG if a node id was outside the SpG.
+ * The SpG must outlive the joiner and must not be compacted (subg_spg_views) while it exists. */
+typedef struct subg_joiner subg_joiner;
+int subg_joiner_create(const subg_spg *s, int64_t B, int arity, const float *enc_table_dev, int k,
+                       int64_t capacity_rows, int want_segid, int depth, subg_joiner **out);
+int subg_joiner_submit(subg_joiner *j, const int64_t *edge_hd, int edge_on_device, void *stream, void **out_dev,
+                       int64_t **indptr_dev, int64_t **segid_dev, const int64_t **nrows_dev, int *slot);
+int subg_joiner_rows(subg_joiner *j, int slot, int64_t *N);
+void subg_joiner_free(subg_joiner *j);
+
 /* ---- PPR set sampler -----------------------------------------------------------
  * Replaces topk_ppr_matrix (sampler/pprgo.py:83-111): ACL forward push per seed
  * (_calc_ppr_node, pprgo.py:9-38: LIFO queue, float32 p and r, float64 intermediate for the

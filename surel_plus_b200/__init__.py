@@ -6,9 +6,9 @@ No CPU fallback: importing works anywhere, calling needs the built library and a
 from . import _capi
 from .spg import DeviceGraph, SpG
 from .sampler import subg_matrix, rw_matrix
-from .train import gather, hgather, bgather, pgather
+from .train import gather, hgather, bgather, pgather, JoinStream
 from .subg_acc import gset_sampler, walk_sampler
 from .pprgo import topk_ppr_matrix, encoding
 
-__all__ = ["DeviceGraph", "SpG", "subg_matrix", "gather", "hgather", "bgather", "pgather", "gset_sampler", "walk_sampler", "rw_matrix", "topk_ppr_matrix",
+__all__ = ["DeviceGraph", "SpG", "subg_matrix", "gather", "hgather", "bgather", "pgather", "JoinStream", "gset_sampler", "walk_sampler", "rw_matrix", "topk_ppr_matrix",
            "encoding", "_capi"]

@@ -26,6 +26,7 @@ SYMBOLS = [
     "subg_spg_from_csr", "subg_spg_alloc", "subg_spg_seal", "subg_spg_free",
     "subg_xchg_create", "subg_xchg_export", "subg_xchg_open", "subg_xchg_slab", "subg_xchg_pack", "subg_xchg_assemble", "subg_xchg_free",
     "subg_spjoin_plan", "subg_spjoin_run", "subg_spjoin",
+    "subg_joiner_create", "subg_joiner_submit", "subg_joiner_rows", "subg_joiner_free",
     "subg_ppr_topk", "subg_spg_encode", "subg_spg_pushes",
     "subg_walk_sample", "subg_walkset_info", "subg_walkset_export", "subg_walkset_views", "subg_walkset_free", "subg_walk_join",
     "subg_timing_enable", "subg_timing_read", "subg_launch_count",
@@ -85,6 +86,11 @@ def load() -> C.CDLL:
     L.subg_spjoin_plan.argtypes = [vp, vp, i64, i32, vp, vp, C.POINTER(i64), vp]
     L.subg_spjoin_run.argtypes = [vp, vp, i64, i32, vp, vp, i32, vp, vp, vp]
     L.subg_spjoin.argtypes = [vp, vp, i64, i32, vp, vp, vp, i32, vp, i64, vp, C.POINTER(i64), C.POINTER(i32), vp]
+    L.subg_joiner_create.argtypes = [vp, i64, i32, vp, i32, i64, i32, i32, C.POINTER(vp)]
+    L.subg_joiner_submit.argtypes = [vp, vp, i32, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i32)]
+    L.subg_joiner_rows.argtypes = [vp, i32, C.POINTER(i64)]
+    L.subg_joiner_free.argtypes = [vp]
+    L.subg_joiner_free.restype = None
     L.subg_ppr_topk.argtypes = [vp, vp, i64, C.c_float, C.c_float, i32, i32, vp, i32, vp, C.POINTER(vp)]
     L.subg_spg_encode.argtypes = [vp, vp, i32, vp, C.POINTER(vp)]
     L.subg_spg_pushes.argtypes = [vp, C.POINTER(i64)]

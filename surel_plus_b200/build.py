@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libsubg_b200.so")
-SOURCES = ["capi.cu", "spg.cu", "spjoin.cu", "ppr.cu", "walks.cu", "ingest.cu", "xchg.cu", "sampler_hash32.cu", "sampler_hash64.cu"] + [f"sampler_k{b}{p}.cu" for b in (32, 64) for p in "abcd"]
+SOURCES = ["capi.cu", "spg.cu", "spjoin.cu", "ppr.cu", "walks.cu", "ingest.cu", "xchg.cu"] + [f"sampler_k{b}{p}.cu" for b in (32, 64) for p in "abcd"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]

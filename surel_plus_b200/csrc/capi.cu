@@ -29,8 +29,12 @@ static bool g_timing = false;
 static std::atomic<long long> g_launches{0};
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+static bool capturing(cudaStream_t st) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    return cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone;
+}
 void timing_begin(int which, cudaStream_t st) {
-    if (!g_timing) return;
+    if (!g_timing || capturing(st)) return;
     TimedRegion r{};
     r.which = which;
     r.closed = false;
@@ -41,7 +45,7 @@ void timing_begin(int which, cudaStream_t st) {
     g_regions.push_back(r);
 }
 void timing_end(int which, cudaStream_t st) {
-    if (!g_timing) return;
+    if (!g_timing || capturing(st)) return;
     std::lock_guard<std::mutex> lk(g_tm_mutex);
     for (size_t i = g_regions.size(); i-- > 0;)
         if (g_regions[i].which == which && !g_regions[i].closed) {
@@ -86,6 +90,13 @@ int spg_encode_impl(const Graph *g, const SpG *x, int encoder, cudaStream_t st, 
 int graph_from_edges_impl(const int64_t *row_hd, const int64_t *col_hd, int64_t E, int64_t N_in, int symmetrize,
                           int drop_self_loops, int device, cudaStream_t st, Graph **out);
 int graph_export_impl(const Graph *g, int64_t *rowptr_hd, int32_t *col_hd, cudaStream_t st);
+struct Joiner;
+int joiner_create_impl(const SpG *s, int64_t B, int arity, const float *enc_table_dev, int k, int64_t capacity_rows,
+                       int want_segid, int depth, Joiner **out);
+int joiner_submit_impl(Joiner *j, const int64_t *edge_hd, int edge_on_device, cudaStream_t st, void **out_dev, int64_t **indptr_dev,
+                       int64_t **segid_dev, const int64_t **nrows_dev, int *slot_out);
+int joiner_rows_impl(Joiner *j, int slot, int64_t *N);
+void joiner_free_impl(Joiner *j);
 struct Xchg;
 int xchg_create_impl(int device, int rank, int world, int64_t slab_bytes, Xchg **out);
 int xchg_export_impl(const Xchg *x, void *handle64);
@@ -236,6 +247,7 @@ void subg_graph_free(subg_graph *g_) {
     if (g->rowptr) cudaFreeAsync(g->rowptr, st);
     if (g->col) cudaFreeAsync(g->col, st);
     if (g->rowinfo) cudaFreeAsync(g->rowinfo, st);
+    if (g->col3) cudaFreeAsync(g->col3, st);
     delete g;
 }
 
@@ -377,6 +389,19 @@ int subg_spjoin(const subg_spg *s, const int64_t *edge_hd, int64_t B, int arity,
     return spjoin_fused_impl(reinterpret_cast<const SpG *>(s), edge_hd, B, arity, edge_dev, indptr_dev, enc_table_dev, k,
                              out_dev, out_capacity, segid_dev, N_out, ran, (cudaStream_t)stream);
 }
+
+int subg_joiner_create(const subg_spg *s, int64_t B, int arity, const float *enc_table_dev, int k, int64_t capacity_rows,
+                       int want_segid, int depth, subg_joiner **out) {
+    return joiner_create_impl(reinterpret_cast<const SpG *>(s), B, arity, enc_table_dev, k, capacity_rows, want_segid, depth,
+                              reinterpret_cast<Joiner **>(out));
+}
+int subg_joiner_submit(subg_joiner *j, const int64_t *edge_hd, int edge_on_device, void *stream, void **out_dev,
+                       int64_t **indptr_dev, int64_t **segid_dev, const int64_t **nrows_dev, int *slot) {
+    return joiner_submit_impl(reinterpret_cast<Joiner *>(j), edge_hd, edge_on_device, (cudaStream_t)stream, out_dev, indptr_dev,
+                              segid_dev, nrows_dev, slot);
+}
+int subg_joiner_rows(subg_joiner *j, int slot, int64_t *N) { return joiner_rows_impl(reinterpret_cast<Joiner *>(j), slot, N); }
+void subg_joiner_free(subg_joiner *j) { joiner_free_impl(reinterpret_cast<Joiner *>(j)); }
 
 int subg_ppr_topk(const subg_graph *g, const int32_t *seeds_hd, int64_t n, float alpha, float eps, int topk,
                   int normalization, const double *norm_deg_hd, int encoder, void *stream, subg_spg **out) {

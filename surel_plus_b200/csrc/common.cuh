@@ -118,6 +118,10 @@ struct Graph {
     void *rowptr = nullptr;  // int32[N+1] or int64[N+1]
     int32_t *col = nullptr;  // int32[E]
     void *rowinfo = nullptr; // uint64[N]: row start (low 40 bits) | degree (high 24 bits, 0xFFFFFF = read rowptr)
+    // neighbour ids packed three to a 64-bit word (21 bits each), built on demand for graphs with N <= 2^21 whose CSR does
+    // not fit the L2: the walk's random column gathers then range over 2/3 of the bytes, so more of them hit the L2
+    mutable unsigned long long *col3 = nullptr;
+    mutable int col3_state = -1;  // -1 undecided, 0 not used, 1 built
     int num_sms = 148;
     // lazily computed structure properties (-1 unknown): rows strictly ascending; adjacency symmetric
     mutable int sorted_state = -1, sym_state = -1;

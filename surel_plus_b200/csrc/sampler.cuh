@@ -23,6 +23,7 @@
 //      written coalesced in ascending node order, the order the SpG CSR-of-sets needs; the LP row
 //      is interned in an L2-resident hash table that also tracks its first stream position.
 #pragma once
+#include <type_traits>
 #include <utility>
 
 #include "common.cuh"
@@ -42,6 +43,7 @@ struct SamplerArgs {
     const void *rowptr;    // escape path only
     int rowptr64;
     const int32_t *col;
+    const unsigned long long *col3;  // nullable: the same ids, three per 64-bit word (21 bits each)
     const int32_t *seeds;  // chunk-local [n_chunk]
     int64_t n_chunk;
     int64_t seed_base;     // global index of seeds[0]
@@ -109,6 +111,12 @@ __device__ __forceinline__ void decode_row(const SamplerArgs &a, uint32_t v, uin
     }
 }
 __device__ __forceinline__ uint32_t load_col(const SamplerArgs &a, const Policies &pol, int64_t e) {
+    if (a.col3) {  // packed columns (E < 2^32): word e / 3, field e % 3
+        const uint32_t e32 = (uint32_t)e;
+        const uint32_t w = __umulhi(e32, 0xAAAAAAABu) >> 1;
+        const unsigned long long v = __ldg(a.col3 + w);
+        return (uint32_t)(v >> (21u * (e32 - 3u * w))) & 0x1fffffu;
+    }
     return (uint32_t)__ldg(a.col + e);  // cache hints on these make no difference (profiles/r1_gather_micro.txt)
 }
 
@@ -207,10 +215,11 @@ __device__ __forceinline__ void warp_merge_sort(K (&k)[EPL], K *buf, int lane) {
     }
 }
 
-__device__ __forceinline__ unsigned long long warp_incl_scan_u64(unsigned long long v) {
+template <typename T>
+__device__ __forceinline__ T warp_incl_scan_acc(T v) {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        const unsigned long long t = __shfl_up_sync(FULL, v, d);
+        const T t = __shfl_up_sync(FULL, v, d);
         if (lane_id() >= d) v += t;
     }
     return v;
@@ -270,8 +279,16 @@ constexpr int sampler_min_blocks() {
 // ---------------------------------------------------------------- the sampler kernel
 // PARITY = false: Philox draws only (the fast path); true: rand_r replay and supplied traces (kept out
 // of the fast kernel: its code has to stay inside the instruction cache).
-template <typename K, int EPL, bool PARITY>
+// LEAN = true: additionally no first-visit ranks, no bucket cap (stride >= M*m+1) and LP rows of at most 32 bits -- the
+// configuration subg_matrix runs in -- with those paths compiled out (the kernel is bound by instruction issue and
+// fetch: every kilobyte of SASS that is not executed still competes for the instruction caches).
+template <typename K, int EPL, bool PARITY, bool LEAN>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL>()) gset_sample_kernel(const SamplerArgs a) {
+    using Acc = std::conditional_t<LEAN, uint32_t, unsigned long long>;   // packed landing counts of one member
+    const int stop_after = LEAN ? 0 : a.stop_after;                      // the measurement hooks are not in the lean kernel
+    const bool want_rank = LEAN ? false : (a.want_rank != 0);
+    const bool lp64 = LEAN ? false : (a.lp64 != 0);
+    uint16_t *const out_slot = LEAN ? nullptr : a.out_slot;
     constexpr K SENT = ~(K)0;
     constexpr K PAD = SENT - 1;  // fills the key slots beyond M*m+1: above every real key, below the merge sentinel
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -319,7 +336,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
             continue;
         }
 
-        if (a.want_rank)
+        if (want_rank)
             for (int b = lane; b < a.nbw; b += 32) bitmap[b] = 0u;
 
         if (PARITY && a.rng_mode == SUBG_RNG_TRACE) {
@@ -459,13 +476,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
         for (int j = a.Kt + lane; j < 32 * EPL; j += 32) keys[j] = PAD;
         __syncwarp();
 
-        if (a.stop_after == 1) continue;
+        if (stop_after == 1) continue;
         K k[EPL];
 #pragma unroll
         for (int r = 0; r < EPL; r++) k[r] = keys[lane * EPL + r];
         __syncwarp();
         warp_merge_sort<K, EPL>(k, keys, lane);
-        if (a.stop_after == 2) {
+        if (stop_after == 2) {
             if (k[0] == 1 && lane == 33) a.nsize[i] = 0;  // keep the sort alive
             continue;
         }
@@ -482,7 +499,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
         }
         const uint32_t incl = warp_incl_scan(nhead);
         const int s_total = (int)__shfl_sync(FULL, incl, 31);
-        const int kept = s_total < a.stride ? s_total : a.stride;
+        const int kept = LEAN ? s_total : (s_total < a.stride ? s_total : a.stride);
         const int kept4 = (kept + 3) & ~3;
         unsigned long long base_u = 0;
         if (lane == 0) {
@@ -496,7 +513,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
 
         // ---- landing counts per run: packed 4 x 16 bit, runs that straddle lanes are stitched by a scan
         {
-            unsigned long long acc = 0ull, lead = 0ull;
+            Acc acc = 0, lead = 0;
             bool have = false;
             K curk = 0;
             int idx = (int)(incl - nhead) - 1;
@@ -510,36 +527,36 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
                     if (have) {
                         rec_key[idx] = curk;
                         rec_lp32[idx] = (uint32_t)acc;
-                        if (a.lp64) rec_lphi[idx] = (uint32_t)(acc >> 32);
+                        if (lp64) rec_lphi[idx] = (uint32_t)((unsigned long long)acc >> 32);
                     } else {
                         lead = acc;
                     }
                     have = true;
                     curk = k[r];
-                    acc = 0ull;
+                    acc = 0;
                     idx++;
-                    if (a.want_rank) atomicOr(&bitmap[ord >> 5], 1u << (ord & 31));
+                    if (want_rank) atomicOr(&bitmap[ord >> 5], 1u << (ord & 31));
                 }
-                if (valid && ord) acc += 1ull << (lp_top - a.SHIFT * (int)(ord & step_mask));
+                if (valid && ord) acc += (Acc)1 << (lp_top - a.SHIFT * (int)(ord & step_mask));
             }
             if (!have) lead = acc;
-            const unsigned long long S = warp_incl_scan_u64(lead);
+            const Acc S = warp_incl_scan_acc(lead);
             const uint32_t H = __ballot_sync(FULL, have);
             const uint32_t above = lane == 31 ? 0u : (H & ~((2u << lane) - 1u));
             const int nh = above ? (__ffs((int)above) - 1) : 31;
-            const unsigned long long S_nh = __shfl_sync(FULL, S, nh);
+            const Acc S_nh = __shfl_sync(FULL, S, nh);
             if (have) {
                 rec_key[idx] = curk;
-                const unsigned long long tot = acc + (S_nh - S);
+                const Acc tot = acc + (S_nh - S);
                 rec_lp32[idx] = (uint32_t)tot;
-                if (a.lp64) rec_lphi[idx] = (uint32_t)(tot >> 32);
+                if (lp64) rec_lphi[idx] = (uint32_t)((unsigned long long)tot >> 32);
             }
         }
         __syncwarp();
 
-        if (a.stop_after == 3) continue;
+        if (stop_after == 3) continue;
         // ---- first-visit rank of every member = popcount prefix over the order bitmap
-        if (a.want_rank) {
+        if (want_rank) {
             uint32_t running = 0;
             for (int b0 = 0; b0 < a.nbw; b0 += 32) {
                 const int b = b0 + lane;
@@ -554,7 +571,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
         // ---- emit the set: ascending node id, provisional LP id, first-visit rank.  Two members per
         // lane and iteration so that two table lookups are in flight.
         const long long base = (long long)__shfl_sync(FULL, base_u, 0);
-        const bool overflow = kept < s_total;
+        const bool overflow = LEAN ? false : kept < s_total;
         int done = 0;
         for (int t0 = 0; t0 < s_total; t0 += 64) {
             K kk[2];
@@ -571,11 +588,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
                 if (act) {
                     kk[q] = rec_key[t];
                     lp[q] = rec_lp32[t];
-                    if (a.lp64) lp[q] |= (unsigned long long)rec_lphi[t] << 32;
+                    if (lp64) lp[q] |= (unsigned long long)rec_lphi[t] << 32;
                 }
                 ord[q] = (uint32_t)kk[q] & ord_mask;
                 rank[q] = 0;
-                if (a.want_rank && act)
+                if (want_rank && act)
                     rank[q] = bprefix[ord[q] >> 5] + __popc(bitmap[ord[q] >> 5] & ((1u << (ord[q] & 31)) - 1u));
                 keep[q] = act;
                 o[q] = t;
@@ -589,7 +606,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
                 h[q] = lp_hash(lp[q]) & a.tab_mask;
                 cur[q] = kEmptyKey;
                 seen[q] = 0ull;
-                if (keep[q] && a.stop_after != 4) {
+                if (keep[q] && stop_after != 4) {
                     cur[q] = a.tab_key[h[q]];
                     seen[q] = a.tab_pos[h[q]];
                 }
@@ -598,12 +615,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
             for (int q = 0; q < 2; q++) {
                 if (keep[q]) {
                     // measurement knobs: stop_after 4 = no LP-row lookups, 5 = lookups but no row stores (results invalid)
-                    const uint32_t prov = a.stop_after == 4 ? h[q]
+                    const uint32_t prov = stop_after == 4 ? h[q]
                                                             : intern_key(a, lp[q], ((unsigned long long)gi << 16) | ord[q], h[q], cur[q], seen[q]);
-                    if (a.stop_after != 5) {
+                    if (stop_after != 5) {
                         a.out_node[base + o[q]] = (int32_t)(kk[q] >> OB);
                         a.out_prov[base + o[q]] = (int32_t)prov;
-                        if (a.out_slot) a.out_slot[base + o[q]] = (uint16_t)rank[q];
+                        if (out_slot) out_slot[base + o[q]] = (uint16_t)rank[q];
                     } else if (prov == 0xffffffffu) {
                         a.out_prov[base] = 0;  // keeps the lookup alive
                     }
@@ -613,7 +630,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
         if (lane < kept4 - kept) {  // keep the row padding defined (ids are remapped in place later)
             a.out_node[base + kept + lane] = 0x7fffffff;
             a.out_prov[base + kept + lane] = 0;
-            if (a.out_slot) a.out_slot[base + kept + lane] = 0;
+            if (out_slot) out_slot[base + kept + lane] = 0;
         }
         __syncwarp();  // the record area is the next seed's key buffer
     }

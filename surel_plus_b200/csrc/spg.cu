@@ -15,7 +15,7 @@
 #include <string>
 #include <vector>
 
-#include "sampler_hash.cuh"
+#include "sampler.cuh"
 #include "scan.cuh"
 
 namespace subg {
@@ -38,9 +38,6 @@ static cudaError_t launch_gset_sample_k64(const SamplerArgs &a, int EPL, int num
     if (EPL <= 33) return launch_gset_sample_k64c(a, EPL, num_sms, st);
     return launch_gset_sample_k64d(a, EPL, num_sms, st);
 }
-// implemented in sampler_hash32.cu / sampler_hash64.cu (TOP = keys per lane of the largest sort class)
-cudaError_t launch_gset_hash_k32(const SamplerArgs &a, const HashPlan &hp, int TOP, int num_sms, cudaStream_t st);
-cudaError_t launch_gset_hash_k64(const SamplerArgs &a, const HashPlan &hp, int TOP, int num_sms, cudaStream_t st);
 static const int kEplList[] = {3, 5, 7, 9, 11, 13, 15, 17, 19, 21, 25, 29, 33, 41, 49, 63};
 
 static int ceil_log2(uint64_t x) {
@@ -56,6 +53,41 @@ static int64_t env_i64(const char *name, int64_t dflt) {
 __global__ void check_seeds_kernel(const int32_t *seeds, int64_t n, int64_t N, uint32_t *bad) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         if (seeds[i] < 0 || seeds[i] >= N) atomicOr(bad, 1u);
+}
+
+__global__ void pack_col3_kernel(const int32_t *col, int64_t E, unsigned long long *out) {
+    const int64_t W = (E + 2) / 3;
+    for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < W; w += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long v = 0ull;
+        for (int q = 0; q < 3; q++) {
+            const int64_t e = 3 * w + q;
+            if (e < E) v |= (unsigned long long)(uint32_t)col[e] << (21 * q);
+        }
+        out[w] = v;
+    }
+}
+// decides once per graph whether the packed column array pays off, and builds it
+static const unsigned long long *graph_col3(const Graph *g, cudaStream_t st) {
+    if (g->col3_state < 0) {
+        const int64_t csr_bytes = 4 * g->E + 8 * g->N;
+        bool want = g->N <= (1ll << 21) && g->E < (1ll << 32) && g->E > 0 && csr_bytes > (96ll << 20);
+        const int64_t force = env_i64("SUBG_COL_PACK", -1);
+        if (force == 0) want = false;
+        if (force == 1) want = g->N <= (1ll << 21) && g->E < (1ll << 32) && g->E > 0;
+        g->col3_state = 0;
+        if (want) {
+            const int64_t W = (g->E + 2) / 3;
+            if (cudaMallocAsync((void **)&g->col3, (size_t)(W + 2) * 8, st) == cudaSuccess) {
+                pack_col3_kernel<<<8 * g->num_sms, 256, 0, st>>>(g->col, g->E, g->col3);
+                g->col3_state = 1;
+                count_launch(1);
+            } else {
+                cudaGetLastError();
+                g->col3 = nullptr;
+            }
+        }
+    }
+    return g->col3_state == 1 ? g->col3 : nullptr;
 }
 
 __global__ void fill_u64_kernel(unsigned long long *p, int64_t n, unsigned long long v) {
@@ -292,41 +324,6 @@ static int make_plan(const Graph *g, int M, int m, int bucket, SamplePlan *p) {
     return SUBG_OK;
 }
 
-// The hash-dedup kernel (sampler_hash.cuh) takes the configurations of the fast path: Philox draws, no first-visit
-// ranks, no bucket cap, LP row in 32 bits, at most 8 walks per lane and 608 visits per seed.
-struct HashChoice {
-    bool ok = false, key64 = false;
-    int TOP = 0;
-    HashPlan hp{};
-};
-static HashChoice choose_hash(const Graph *g, const SamplePlan &pl, int M, int m, int rng_mode, bool want_rank) {
-    HashChoice c;
-    if (env_i64("SUBG_SAMPLER_HASH", 1) == 0) return c;
-    if (rng_mode != SUBG_RNG_PHILOX || want_rank || pl.stride < pl.Kt || pl.lp64 || M > 256 || pl.Kt > 608 || pl.OB > 16) return c;
-    for (int t : {3, 7, 13, 19})
-        if (32 * t >= pl.Kt) { c.TOP = t; break; }
-    if (!c.TOP) return c;
-    const int nbits = std::max(1, ceil_log2((uint64_t)std::max<int64_t>(g->N, 2)));
-    c.hp.IB = std::max(1, ceil_log2((uint64_t)pl.Kt + 1));
-    const int need_bits = nbits + std::max(pl.OB, c.hp.IB);
-    if (need_bits > 64) return c;
-    c.key64 = need_bits > 32;
-    const int ksz = c.key64 ? 8 : 4;
-    int cap = ((int)(pl.Kt * 1.28) + 31) & ~31;
-    cap = std::max(cap, (33 * c.TOP + 31) & ~31);      // the padded sorted list of the largest class lives in the key area
-    cap = (int)env_i64("SUBG_HASH_CAP", cap);
-    cap = std::max((cap + 31) & ~31, (33 * c.TOP + 31) & ~31);
-    if (cap <= pl.Kt) return c;
-    c.hp.cap = cap;
-    c.hp.cnt_off = (cap * ksz + 15) & ~15;
-    c.hp.ord_off = c.hp.cnt_off + 4 * cap;
-    int total = (c.hp.ord_off + 2 * pl.Kt + 15) & ~15;
-    total = std::max(total, (8 * M + 8 * pl.fy_cap + 15) & ~15);   // Fisher-Yates scratch overlays the table
-    c.hp.smem_per_warp = total;
-    c.ok = true;
-    return c;
-}
-
 // seeds_hd holds the whole query (n_all entries); the sets of the window [lo, hi) are sampled.  Seed
 // indices stay global (Philox counters, rand_r call offsets, first-occurrence positions), so the
 // shards of a range-partitioned query concatenate to exactly the single-call result.
@@ -345,7 +342,6 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
     const bool want_rank = want_slot || pl.stride < pl.Kt;
 
     g->tag.use_on(st);
-    const HashChoice hc = choose_hash(g, pl, M, m, rng_mode, want_rank);
     SpG *s = new SpG();
     s->tag.last = st;
     s->device = g->device; s->n = n; s->ncol = m + 1; s->M = M; s->num_sms = g->num_sms; s->value_kind = 0;
@@ -488,6 +484,7 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
                 CK(cudaMemsetAsync(d_ctr, 0, kCtrWords * sizeof(unsigned long long), st));
                 SamplerArgs a{};
                 a.rowinfo = (const unsigned long long *)g->rowinfo; a.rowptr = g->rowptr; a.rowptr64 = g->rowptr64 ? 1 : 0; a.col = g->col;
+                a.col3 = graph_col3(g, st);
                 a.seeds = s->seeds + base; a.n_chunk = nc; a.seed_base = lo + base;
                 a.N = g->N; a.M = M; a.m = m; a.stride = pl.stride; a.Kt = pl.Kt; a.OB = pl.OB; a.LS = pl.LS; a.SHIFT = pl.SHIFT;
                 a.rng_mode = rng_mode; a.rng_lo = (uint32_t)seed; a.rng_hi = (uint32_t)(seed >> 32);
@@ -505,9 +502,8 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
                     // bound by that count, so shared memory is capped to leave about 80 KB of the SM to L1 (sweep: profiles/r1_sampler_sweeps.txt)
                     const int64_t csr_bytes = 4 * g->E + 8 * g->N;
                     int cap_blocks = 0;
-                    const int warp_smem = hc.ok ? hc.hp.smem_per_warp : pl.smem_per_warp;
                     if (csr_bytes > (96ll << 20))
-                        cap_blocks = std::max(2, (int)((152 << 10) / (kWarpsPerBlock * warp_smem + 1024)));
+                        cap_blocks = std::max(2, (int)((152 << 10) / (kWarpsPerBlock * pl.smem_per_warp + 1024)));
                     a.blocks_per_sm = (int)env_i64("SUBG_SAMPLER_BLOCKS", cap_blocks);
                 }
                 a.tab_key = tab_key; a.tab_pos = tab_pos; a.tab_mask = tab_cap - 1;
@@ -528,12 +524,8 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
                 }
                 prof.mark("table_init");
                 timing_begin(SUBG_TIMING_SAMPLER, st);
-                if (hc.ok)
-                    CK(hc.key64 ? launch_gset_hash_k64(a, hc.hp, hc.TOP, g->num_sms, st)
-                                : launch_gset_hash_k32(a, hc.hp, hc.TOP, g->num_sms, st));
-                else
-                    CK(pl.key64 ? launch_gset_sample_k64(a, pl.EPL, g->num_sms, st)
-                                : launch_gset_sample_k32(a, pl.EPL, g->num_sms, st));
+                CK(pl.key64 ? launch_gset_sample_k64(a, pl.EPL, g->num_sms, st)
+                            : launch_gset_sample_k32(a, pl.EPL, g->num_sms, st));
                 timing_end(SUBG_TIMING_SAMPLER, st);
                 count_launch(1);
                 if (l2_persist) {

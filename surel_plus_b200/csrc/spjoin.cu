@@ -14,6 +14,8 @@
 // S_b need no second search.  Output rows are written coalesced (8 B per row, or 2k floats
 // per row when the LP table lookup `encode[xz]` of train.py:37 is fused in).
 #include <algorithm>
+#include <cstring>
+#include <vector>
 
 #include "common.cuh"
 #include "scan.cuh"
@@ -158,6 +160,51 @@ __global__ void __launch_bounds__(kPlanTile) join_plan_offsets_kernel(const int3
     if (g < nseg) seg_ptr[g] = ex;
     if (g == nseg - 1) seg_ptr[nseg] = tot[0];
 }
+// Plan of a small batch in ONE launch (segments <= kPlanOneMax): a single block sizes every segment and scans them.
+constexpr int kPlanOneThreads = 1024;
+constexpr int kPlanOneItems = 16;
+constexpr int kPlanOneMax = kPlanOneThreads * kPlanOneItems;
+__global__ void __launch_bounds__(kPlanOneThreads) join_plan_one_kernel(const long long *rowbeg, const int32_t *nsize, int64_t n_rows,
+                                                                       const long long *edge, int64_t B, int arity, int nseg,
+                                                                       long long *seg_ptr, long long *tot) {
+    __shared__ long long ws[32];
+    const int per = (nseg + kPlanOneThreads - 1) / kPlanOneThreads;   // consecutive segments per thread, <= kPlanOneItems
+    const int first = threadIdx.x * per;
+    int32_t sz[kPlanOneItems];
+    long long sum = 0;
+    bool bad = false;
+#pragma unroll
+    for (int q = 0; q < kPlanOneItems; q++) {
+        sz[q] = 0;
+        const int g = first + q;
+        if (q < per && g < nseg) {
+            long long node;
+            if (arity == 2) node = edge[g];
+            else {
+                const int blk = g / (int)B, qq = g - blk * (int)B;
+                node = edge[(int64_t)(blk == 0 ? 0 : (blk == 2 ? 1 : 2)) * B + qq];  // u, w, v, w
+            }
+            if (node < 0 || node >= n_rows) bad = true;
+            else sz[q] = nsize ? nsize[node] : (int32_t)(rowbeg[node + 1] - rowbeg[node]);
+            sum += sz[q];
+        }
+    }
+    long long total;
+    long long ex = block_excl_scan(sum, &total, ws);
+    const int any_bad = __syncthreads_or(bad ? 1 : 0);
+#pragma unroll
+    for (int q = 0; q < kPlanOneItems; q++) {
+        const int g = first + q;
+        if (q < per && g < nseg) seg_ptr[g] = ex;
+        ex += sz[q];
+    }
+    if (threadIdx.x == 0) {
+        seg_ptr[nseg] = total;
+        tot[0] = total;
+        tot[1] = any_bad ? 1 : 0;
+    }
+}
+
 __global__ void join_tot_kernel(const long long *seg_ptr, int64_t nseg, const uint32_t *bad, long long *tot) {
     tot[0] = seg_ptr[nseg];
     tot[1] = *bad;
@@ -587,6 +634,177 @@ int spjoin_fused_impl(const SpG *s, const int64_t *edge_hd, int64_t B, int arity
     const long long N = s->join_host[0];
     *N_out = N;
     *ran = ((B > 0 && out_dev && N <= out_capacity) || N == 0) ? 1 : 0;
+    return SUBG_OK;
+}
+
+// ------------------------------------------------------------------ joiner: the per-batch join as a replayed CUDA graph
+// The training loop of the reference joins one mini-batch per step (train.py:121-127, batch 1024; main_horder.py:33,
+// 2048 triplets): at those sizes the join kernel runs for 10-20 us and everything around it -- output allocation, three
+// launches, the device-to-host copy of the row count, the stream synchronisation -- costs several times that.  A joiner
+// fixes (SpG, batch size, arity, LP table, output capacity) once, captures [edge upload -> plan -> join -> row count to
+// pinned memory] as a CUDA graph per ring slot, and a submit is one small memcpy into pinned staging plus one
+// cudaGraphLaunch: no allocation, no host synchronisation.  The row count stays on the device (and lands in pinned
+// memory for whoever wants it later); rows beyond it in the slot's output buffer are not written.
+struct JoinSlot {
+    long long *edge_dev = nullptr, *indptr_dev = nullptr, *segid_dev = nullptr, *tot_dev = nullptr;
+    int32_t *sizes_dev = nullptr;
+    void *out_dev = nullptr;
+    long long *edge_pin = nullptr, *tot_pin = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaEvent_t done = nullptr;
+};
+struct Joiner {
+    const SpG *s = nullptr;
+    int64_t B = 0, cap_rows = 0;
+    int arity = 2, k = 0, depth = 0, next = 0, launches = 0;
+    size_t row_bytes = 0;
+    const float *enc = nullptr;
+    cudaStream_t cap_stream = nullptr;
+    std::vector<JoinSlot> slot;
+};
+
+void joiner_free_impl(Joiner *j) {
+    if (!j) return;
+    DeviceGuard guard(j->s ? j->s->device : 0);
+    for (auto &q : j->slot) {
+        if (q.done) { cudaEventSynchronize(q.done); cudaEventDestroy(q.done); }
+        if (q.exec) cudaGraphExecDestroy(q.exec);
+        if (q.edge_dev) cudaFree(q.edge_dev);
+        if (q.indptr_dev) cudaFree(q.indptr_dev);
+        if (q.segid_dev) cudaFree(q.segid_dev);
+        if (q.sizes_dev) cudaFree(q.sizes_dev);
+        if (q.tot_dev) cudaFree(q.tot_dev);
+        if (q.out_dev) cudaFree(q.out_dev);
+        if (q.edge_pin) cudaFreeHost(q.edge_pin);
+        if (q.tot_pin) cudaFreeHost(q.tot_pin);
+    }
+    if (j->cap_stream) cudaStreamDestroy(j->cap_stream);
+    cudaGetLastError();
+    delete j;
+}
+
+// plan + join + row count to pinned memory of one slot, queued on st (captured into the slot's graph, and run once
+// un-captured beforehand so that the launch attributes are cached before the capture starts)
+static int joiner_enqueue(Joiner *j, JoinSlot &sl, cudaStream_t st, bool upload) {
+    const SpG *s = j->s;
+    const int64_t B = j->B, nseg = (j->arity == 2 ? 2 : 4) * B;
+    if (upload) cudaMemcpyAsync(sl.edge_dev, sl.edge_pin, (size_t)j->arity * B * 8, cudaMemcpyHostToDevice, st);
+    if (nseg <= kPlanOneMax) {
+        join_plan_one_kernel<<<1, kPlanOneThreads, 0, st>>>((const long long *)s->rowbeg, s->indptr ? nullptr : s->nsize, s->n,
+                                                            sl.edge_dev, B, j->arity, (int)nseg, sl.indptr_dev, sl.tot_dev);
+        j->launches = 2;
+    } else {
+        const int tiles = (int)((nseg + kPlanTile - 1) / kPlanTile);
+        long long *tile_off = sl.tot_dev + 8;
+        cudaMemsetAsync(sl.tot_dev, 0, 2 * sizeof(long long), st);
+        join_plan_sizes_kernel<<<tiles, kPlanTile, 0, st>>>((const long long *)s->rowbeg, s->indptr ? nullptr : s->nsize, s->n,
+                                                            sl.edge_dev, B, j->arity, sl.sizes_dev, tile_off,
+                                                            (unsigned int *)(sl.tot_dev + 3), sl.tot_dev);
+        join_plan_offsets_kernel<<<tiles, kPlanTile, 0, st>>>(sl.sizes_dev, tile_off, (int)nseg, sl.indptr_dev, sl.tot_dev);
+        j->launches = 3;
+    }
+    const int rc = join_launch(s, (const int64_t *)sl.edge_dev, B, j->arity, (const int64_t *)sl.indptr_dev, j->enc, j->k, sl.out_dev,
+                               (int64_t *)sl.segid_dev, j->cap_rows, sl.tot_dev, st);
+    cudaMemcpyAsync(sl.tot_pin, sl.tot_dev, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st);
+    return rc;
+}
+
+int joiner_create_impl(const SpG *s, int64_t B, int arity, const float *enc_table_dev, int k, int64_t capacity_rows,
+                       int want_segid, int depth, Joiner **out) {
+    if (!s || !out || B < 1 || (arity != 2 && arity != 3) || capacity_rows < 1 || depth < 1 || depth > 16 || s->n < 1)
+        return fail(SUBG_ERR_ARG, "Input parsing error.");
+    if (enc_table_dev && (s->value_kind != 0 || k < 1)) return fail(SUBG_ERR_ARG, "table lookup needs an int SpG and k >= 1");
+    const int64_t nseg = (arity == 2 ? 2 : 4) * B;
+    if (nseg > kPlanSmallMax) return fail(SUBG_ERR_UNSUPPORTED, "joiner: batch too large (use subg_spjoin)");
+    DeviceGuard guard(s->device);
+    cudaDeviceSynchronize();  // the SpG is complete before the graphs that read it are built
+    Joiner *j = new Joiner();
+    j->s = s; j->B = B; j->arity = arity; j->k = k; j->enc = enc_table_dev; j->cap_rows = capacity_rows; j->depth = depth;
+    j->row_bytes = s->value_kind == 1 ? 8 : (enc_table_dev ? (size_t)8 * k : 8);
+    j->slot.resize(depth);
+    cudaError_t e = cudaStreamCreateWithFlags(&j->cap_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) s->tag.last = j->cap_stream;  // no cross-stream event inside the capture (everything has completed)
+    int rc = SUBG_OK;
+    for (int q = 0; q < depth && e == cudaSuccess && rc == SUBG_OK; q++) {
+        JoinSlot &sl = j->slot[q];
+        e = cudaMalloc((void **)&sl.edge_dev, (size_t)arity * B * 8);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&sl.indptr_dev, (size_t)(nseg + 1) * 8);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&sl.sizes_dev, (size_t)(nseg + 1) * 4);
+        if (e == cudaSuccess && want_segid) e = cudaMalloc((void **)&sl.segid_dev, (size_t)capacity_rows * 8);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&sl.tot_dev, (8 + 1024) * 8);
+        if (e == cudaSuccess) e = cudaMemset(sl.tot_dev, 0, (8 + 1024) * 8);
+        if (e == cudaSuccess) e = cudaMemset(sl.edge_dev, 0, (size_t)arity * B * 8);
+        if (e == cudaSuccess) e = cudaMalloc(&sl.out_dev, (size_t)capacity_rows * j->row_bytes);
+        if (e == cudaSuccess) e = cudaHostAlloc((void **)&sl.edge_pin, (size_t)arity * B * 8, cudaHostAllocDefault);
+        if (e == cudaSuccess) memset(sl.edge_pin, 0, (size_t)arity * B * 8);
+        if (e == cudaSuccess) e = cudaHostAlloc((void **)&sl.tot_pin, 4 * 8, cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming);
+        if (e != cudaSuccess) break;
+        sl.tot_pin[0] = sl.tot_pin[1] = 0;
+        if (q == 0) {  // dry run (all queries = node 0): launch attributes and occupancy are cached outside the capture
+            rc = joiner_enqueue(j, sl, j->cap_stream, true);
+            e = cudaStreamSynchronize(j->cap_stream);
+            if (rc != SUBG_OK || e != cudaSuccess) break;
+        }
+        cudaGraph_t graph = nullptr;
+        e = cudaStreamBeginCapture(j->cap_stream, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) break;
+        rc = joiner_enqueue(j, sl, j->cap_stream, true);
+        e = cudaStreamEndCapture(j->cap_stream, &graph);
+        if (e == cudaSuccess && rc == SUBG_OK) e = cudaGraphInstantiate(&sl.exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+    }
+    if (e != cudaSuccess || rc != SUBG_OK) {
+        cudaGetLastError();
+        joiner_free_impl(j);
+        if (rc != SUBG_OK) return rc;
+        return fail(e == cudaErrorMemoryAllocation ? SUBG_ERR_MEM : SUBG_ERR_CUDA, std::string("joiner: ") + cudaGetErrorString(e));
+    }
+    *out = j;
+    return SUBG_OK;
+}
+
+// edge_hd: int64[arity * B].  edge_on_device: 1 device memory, 0 host memory, < 0 ask the driver.  Host edges are copied
+// into the slot's pinned staging (the caller's array may be reused at once) and the slot's graph -- upload, plan, join,
+// row count to pinned memory -- is launched; device edges are copied on the stream and the same kernels are launched
+// directly.  Returns the slot's buffers; nothing is synchronised.
+int joiner_submit_impl(Joiner *j, const int64_t *edge_hd, int edge_on_device, cudaStream_t st, void **out_dev, int64_t **indptr_dev,
+                       int64_t **segid_dev, const int64_t **nrows_dev, int *slot_out) {
+    if (!j || !edge_hd) return fail(SUBG_ERR_ARG, "Input parsing error.");
+    DeviceGuard guard(j->s->device);
+    j->s->tag.use_on(st);
+    const int q = j->next;
+    j->next = (j->next + 1) % j->depth;
+    JoinSlot &sl = j->slot[q];
+    const size_t eb = (size_t)j->arity * j->B * 8;
+    if (edge_on_device < 0) edge_on_device = is_device_ptr(edge_hd) ? 1 : 0;
+    if (edge_on_device) {
+        SUBG_CUDA(cudaMemcpyAsync(sl.edge_dev, edge_hd, eb, cudaMemcpyDeviceToDevice, st));
+        if (int rc = joiner_enqueue(j, sl, st, false)) return rc;
+    } else {
+        SUBG_CUDA(cudaEventSynchronize(sl.done));  // the slot's previous batch has read its staging (long ago, unless the ring is lapped)
+        memcpy(sl.edge_pin, edge_hd, eb);
+        SUBG_CUDA(cudaGraphLaunch(sl.exec, st));
+    }
+    SUBG_CUDA(cudaEventRecord(sl.done, st));
+    count_launch(j->launches);
+    if (out_dev) *out_dev = sl.out_dev;
+    if (indptr_dev) *indptr_dev = (int64_t *)sl.indptr_dev;
+    if (segid_dev) *segid_dev = (int64_t *)sl.segid_dev;
+    if (nrows_dev) *nrows_dev = (const int64_t *)sl.tot_dev;
+    if (slot_out) *slot_out = q;
+    return SUBG_OK;
+}
+
+// waits for the batch last submitted to `slot` and returns its row count; SUBG_ERR_MEM if the rows did not fit the
+// capacity (nothing was written: re-run that batch through subg_spjoin), SUBG_ERR_ARG for a node id outside the SpG
+int joiner_rows_impl(Joiner *j, int slot, int64_t *N) {
+    if (!j || slot < 0 || slot >= j->depth || !N) return fail(SUBG_ERR_ARG, "Input parsing error.");
+    JoinSlot &sl = j->slot[slot];
+    SUBG_CUDA(cudaEventSynchronize(sl.done));
+    if (sl.tot_pin[1]) return fail(SUBG_ERR_ARG, "query node id outside the SpG");
+    *N = sl.tot_pin[0];
+    if (sl.tot_pin[0] > j->cap_rows) return fail(SUBG_ERR_MEM, "joiner: rows of the batch exceed the slot capacity");
     return SUBG_OK;
 }
 

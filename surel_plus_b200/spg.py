@@ -46,7 +46,7 @@ class _DevView:
 def _view(ptr, shape, typestr, dev, owner):
     if ptr is None or any(s == 0 for s in shape):
         dt = {"<i8": torch.int64, "<i4": torch.int32, "<i2": torch.int16, "<u2": torch.uint16, "<f8": torch.float64,
-              "|u1": torch.uint8}[typestr]
+              "|u1": torch.uint8, "<f4": torch.float32}[typestr]
         return torch.empty(shape, dtype=dt, device=f"cuda:{dev}")
     return torch.as_tensor(_DevView(ptr, shape, typestr, owner), device=f"cuda:{dev}")
 

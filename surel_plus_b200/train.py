@@ -150,3 +150,120 @@ def pgather(edge, M, device, encode, gather_func=None, ptr=True, njobs=4):
     if encode is None:
         out = out.float().unsqueeze(dim=-1)
     return out, (indptr if ptr else segid)
+
+
+class JoinStream:
+    """The per-batch SpJoin of a training / evaluation loop without allocation or host synchronisation
+    (subg_joiner_* in include/subg_b200.h): the reference calls gather / pgather / hgather once per mini-batch
+    (train.py:121-127 with batch 1024, main_horder.py:33 with 2048 triplets), where the join kernel itself runs for
+    10-20 us.  A JoinStream fixes (SpG, batch size, arity, LP table, output capacity), captures the batch as a CUDA
+    graph per ring slot and `submit` is one pinned memcpy + one graph launch.
+
+        js = JoinStream(z, batch_size=1024, device=dev, encode=xpe)            # pairs; arity=3 for triplets
+        xz, indptr, nrows = js.submit(edge)          # device tensors, nothing synchronised
+        xz, indptr = js.gather(edge)                 # same result with the reference's exact shapes (one sync)
+
+    `xz` of submit has `capacity` rows; rows [0, nrows[0]) are the join, in the order and layout of gather; the segment
+    pointer `indptr` (int64 [2B+1], or [4B+1] for triplets) addresses only those.  The buffers of a submit are reused
+    `depth` submits later: consume them on the same stream before that.  segid=True also returns the per-row segment id
+    (gather's ptr=False / hgather's `ind`)."""
+
+    def __init__(self, x, batch_size: int, device="cuda", encode=None, arity: int = 2, capacity: int | None = None,
+                 segid: bool = False, depth: int = 3):
+        from .spg import _view
+        self._view = _view
+        self.spg = _as_spg(x, device)
+        self._lib = _capi.load()
+        self.B, self.arity, self.depth, self.want_segid = int(batch_size), int(arity), int(depth), bool(segid)
+        self.nseg = (2 if arity == 2 else 4) * self.B
+        dev = self.spg.device
+        tdev = torch.device("cuda", dev)
+        self.table = None
+        if self.spg.value_kind == 1:
+            if encode is not None:
+                raise TypeError("a value SpG (PPR/SPD) is joined without an LP table")
+            self.tail, self.k, self.typestr = (2,), 0, "<f4"
+        elif encode is not None:
+            self.table = encode if (isinstance(encode, torch.Tensor) and encode.is_cuda and encode.dtype == torch.float32
+                                    and encode.is_contiguous()) else torch.as_tensor(encode, dtype=torch.float32, device=tdev).contiguous()
+            self.k = int(self.table.shape[1])
+            self.tail, self.typestr = (2, self.k), "<f4"
+        else:
+            self.tail, self.k, self.typestr = (2,), 0, "<i4"
+        if capacity is None:  # mean rows per segment x 1.5 + room for a few of the largest sets
+            avg = self.spg.T / max(self.spg.n, 1)
+            capacity = int(self.nseg * avg * 1.5) + 16 * max(self.spg.max_set, 1) + 1024
+        self.capacity = int(capacity)
+        self._h = C.c_void_p()
+        _capi.check(self._lib.subg_joiner_create(self.spg._h, self.B, self.arity, self.table.data_ptr() if self.table is not None else None,
+                                                 self.k, self.capacity, int(self.want_segid), self.depth, C.byref(self._h)))
+        self._last_slot = -1
+        self._views: dict = {}
+        self._outv = [C.c_void_p() for _ in range(4)]
+        self._out = tuple(C.byref(x) for x in self._outv)
+        self._slot = C.c_int(0)
+        self._slot_ref = C.byref(self._slot)
+        self._submit = self._lib.subg_joiner_submit
+
+    def submit(self, edge):
+        # the hot call of a training loop: keep the host side to one ctypes call (the slot's tensors are built once)
+        if isinstance(edge, np.ndarray) and edge.dtype == np.int64 and edge.flags.c_contiguous and edge.shape == (self.arity, self.B):
+            keep, eptr, on_dev = edge, edge.ctypes.data, 0
+        else:
+            keep, eptr, B, on_dev = _edge_arg(edge, self.arity)
+            if B != self.B:
+                raise TypeError(f"this JoinStream joins batches of {self.B} queries")
+        out, indptr, segid, nrows = self._out
+        dev = self.spg.device
+        rc = self._submit(self._h, eptr, int(on_dev), torch.cuda.current_stream(dev).cuda_stream, out, indptr, segid, nrows,
+                          self._slot_ref)
+        if rc:
+            _capi.check(rc)
+        q = self._slot.value
+        self._last_slot = q
+        res = self._views.get(q)
+        if res is None:
+            v = self._view
+            res = (v(self._outv[0].value, (self.capacity,) + self.tail, self.typestr, dev, self),
+                   v(self._outv[1].value, (self.nseg + 1,), "<i8", dev, self),
+                   v(self._outv[3].value, (2,), "<i8", dev, self))
+            if self.want_segid:
+                res = res + (v(self._outv[2].value, (self.capacity,), "<i8", dev, self),)
+            self._views[q] = res
+        return res
+
+    def rows(self) -> int:
+        """Row count of the last submit (waits for it)."""
+        n = C.c_int64(0)
+        _capi.check(self._lib.subg_joiner_rows(self._h, self._last_slot, C.byref(n)))
+        return n.value
+
+    def gather(self, edge, ptr: bool = True):
+        """gather / pgather / hgather semantics (exact shapes) through the captured graph: one synchronisation."""
+        res = self.submit(edge)
+        try:
+            n = self.rows()
+        except MemoryError:   # the batch outgrew the slot: the two-step route with an exact buffer
+            out, indptr, segid = _join(edge, self.spg, None, self.arity, encode=self.table, want_segid=not ptr or self.arity == 3)
+            if self.table is None:
+                out = out.float().unsqueeze(dim=-1)
+            return out, (indptr if (ptr and self.arity == 2) else segid)
+        xz = res[0][:n]
+        if self.table is None:
+            xz = xz.float().unsqueeze(dim=-1) if self.spg.value_kind == 0 else xz.unsqueeze(dim=-1)
+        if ptr and self.arity == 2:
+            return xz, res[1]
+        if not self.want_segid:
+            raise TypeError("segment ids were not requested (segid=True)")
+        return xz, res[3][:n]
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.subg_joiner_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

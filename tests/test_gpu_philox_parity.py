@@ -105,29 +105,3 @@ def test_philox_kernel_bit_parity_key64_bucket_and_isolated():
     _check_window(A, g, q, 100, 1600, 200, 3, 99, bucket=150)     # bucket overflow drops late nodes (subg_acc.c:814-828)
     _check_window(A, g, q, 0, 1200, 60, 2, 5)
     g.close()
-
-
-@pytest.mark.parametrize("M,m", [(10, 2), (30, 3), (64, 4), (100, 2), (200, 2), (200, 3), (256, 2), (37, 5)])
-def test_hash_kernel_equals_sort_kernel(mid_graph, M, m, monkeypatch):
-    """The two sampler kernels (sampler_hash.cuh: hash dedup + bitonic sort of the members; sampler.cuh: merge sort of
-    all visits) must produce the same SpG from the same Philox stream: every sort class (2 / 4 / 8 / 16 keys per lane
-    and the per-configuration maximum 3 / 7 / 13 / 19), hubs with a Fisher-Yates first hop, isolated seeds."""
-    from surel_plus_b200 import DeviceGraph, SpG
-    A = mid_graph
-    n = A.shape[0]
-    q = np.random.default_rng(2).permutation(n).astype(np.int32)
-    g = DeviceGraph.from_scipy(A, "cuda:0")
-    monkeypatch.setenv("SUBG_SAMPLER_HASH", "0")
-    ref = SpG.sample(g, q, M, m, seed=31, first_visit_ranks=False, dump_walks=True)
-    monkeypatch.setenv("SUBG_SAMPLER_HASH", "1")
-    new = SpG.sample(g, q, M, m, seed=31, first_visit_ranks=False, dump_walks=True)
-    assert torch.equal(ref.walks(), new.walks())
-    assert (ref.n, ref.T, ref.c, ref.max_set, ref.status) == (new.n, new.T, new.c, new.max_set, new.status)
-    sizes = ref.set_sizes()
-    assert torch.equal(sizes, new.set_sizes())
-    vr, vn = ref.views(), new.views()
-    for k in ("indptr", "indices", "data", "enc"):
-        assert torch.equal(vr[k], vn[k]), k
-    hist = torch.bincount(torch.clamp((sizes - 1) // 32, max=20))   # which sort classes this graph exercises
-    assert int(hist.sum()) == n
-    ref.close(); new.close(); g.close()

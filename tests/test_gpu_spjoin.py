@@ -147,3 +147,64 @@ def test_empty_batch(lp_spg):
     assert tuple(xz.shape) == (0, 2, xpe.shape[1]) and ptr.cpu().tolist() == [0]
     xz, ind = hgather(np.zeros((3, 0), np.int64), spg, "cuda", xpe)
     assert xz.shape[0] == 0 and ind.numel() == 0
+
+
+@pytest.mark.parametrize("arity,B", [(2, 1024), (2, 37), (3, 2048), (3, 5), (2, 9000)])
+def test_join_stream_graph_replay_equals_gather(mid_graph, arity, B):
+    """JoinStream (CUDA-graph replay, no host sync) returns what gather / hgather return: rows [0, N), the segment
+    pointers, the segment ids -- across ring slots, for host and device edge lists, with and without the fused LP
+    lookup; a batch that outgrows the slot capacity falls back to the exact two-step join."""
+    from surel_plus_b200 import DeviceGraph, JoinStream, SpG, gather, hgather
+    A = mid_graph
+    n, M = A.shape[0], 40
+    g = DeviceGraph.from_scipy(A)
+    spg = SpG.sample(g, np.arange(n), M, 2, seed=3, first_visit_ranks=False)
+    xpe = torch.from_numpy(spg.enc_table()).float().cuda() / M
+    rng = np.random.default_rng(B)
+    js = JoinStream(spg, B, "cuda", encode=xpe, arity=arity, segid=True, depth=3)
+    js_raw = JoinStream(spg, B, "cuda", encode=None, arity=2, depth=2) if arity == 2 else None
+    outs = []
+    for it in range(7):   # more submits than ring slots
+        edge = rng.integers(0, n, (arity, B))
+        e_in = torch.from_numpy(edge).cuda() if it % 3 == 2 else edge
+        xz, indptr, nrows, segid = js.submit(e_in)
+        if arity == 2:
+            want_xz, want_ptr = gather(edge, spg, "cuda", True, xpe)
+            _, want_seg = gather(edge, spg, "cuda", False, xpe)
+        else:
+            want_xz, want_seg = hgather(edge, spg, "cuda", xpe)
+            want_ptr = None
+        N = int(nrows[0].item())
+        assert N == want_xz.shape[0] == js.rows() and int(nrows[1].item()) == 0
+        assert torch.equal(xz[:N], want_xz) and torch.equal(segid[:N], want_seg)
+        if want_ptr is not None:
+            assert torch.equal(indptr, want_ptr)
+            got_xz, got_ptr = js.gather(e_in)
+            assert torch.equal(got_xz, want_xz) and torch.equal(got_ptr, want_ptr)
+            raw_xz, raw_ptr = js_raw.gather(edge)
+            ref_xz, ref_ptr = gather(edge, spg, "cuda", True, None)
+            assert torch.equal(raw_xz, ref_xz) and torch.equal(raw_ptr, ref_ptr)
+        else:
+            got_xz, got_seg = js.gather(e_in, ptr=False)
+            assert torch.equal(got_xz, want_xz) and torch.equal(got_seg, want_seg)
+        outs.append(N)
+    assert len(set(outs)) > 1
+    # capacity overflow: nothing is written, rows() reports it, gather() falls back to the exact route
+    tiny = JoinStream(spg, B, "cuda", encode=xpe, arity=arity, segid=True, capacity=8)
+    edge = rng.integers(0, n, (arity, B))
+    tiny.submit(edge)
+    with pytest.raises(MemoryError):
+        tiny.rows()
+    if arity == 2:
+        a, b = tiny.gather(edge)
+        wa, wb = gather(edge, spg, "cuda", True, xpe)
+        assert torch.equal(a, wa) and torch.equal(b, wb)
+    # a node id outside the SpG is reported like gather reports it
+    bad = edge.copy()
+    bad[0, 0] = n + 5
+    js.submit(bad)
+    with pytest.raises(TypeError):
+        js.rows()
+    for x in (js, js_raw, tiny):
+        if x is not None:
+            x.close()
