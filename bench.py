@@ -509,14 +509,20 @@ def bench_sharded(c):
     spg, info, ms_total, launches, (k_ms, k_n, b_ms, T_avg) = timed(want, c.args.steps, max(c.args.warmup, 3))
     clk = c.clocks.stop() if c.rank == 0 else None
     # ---- the sharded result must BE the single-GPU SpG (indices are global; LP ids in global first-occurrence order)
-    ref = SpG.sample(c.graph, c.q_dev, num_walks=M, num_steps=m, seed=111413 + c.args.steps - 1, rng_mode=_capi.SUBG_RNG_PHILOX,
-                     first_visit_ranks=False)
-    same = (ref.n, ref.T, ref.c, ref.max_set) == (spg.n, spg.T, spg.c, spg.max_set) and np.array_equal(ref.enc_table(), spg.enc_table())
-    if same:
-        # rows compared in place (no compaction of the GB-sized arrays): a checksum per row over its (node, LP id) pairs
-        same = bool(torch.equal(row_checksums(torch, ref), row_checksums(torch, spg)))
+    parity_err = None
+    try:
+        ref = SpG.sample(c.graph, c.q_dev, num_walks=M, num_steps=m, seed=111413 + c.args.steps - 1, rng_mode=_capi.SUBG_RNG_PHILOX,
+                         first_visit_ranks=False)
+        same = (ref.n, ref.T, ref.c, ref.max_set) == (spg.n, spg.T, spg.c, spg.max_set) and np.array_equal(ref.enc_table(), spg.enc_table())
+        if same:
+            # rows compared in place (no compaction of the GB-sized arrays): a checksum per row over its (node, LP id) pairs
+            same = bool(torch.equal(row_checksums(torch, ref), row_checksums(torch, spg)))
+        ref.close()
+    except Exception as ex:  # noqa: BLE001 -- e.g. no room for a second full SpG beside the exchanged one
+        same, parity_err = False, repr(ex)
+        log(f"[bench] parity check failed to run on rank {c.rank}: {ex!r}")
     parity_ok = c.all_ok(same)
-    ref.close()
+    torch.cuda.empty_cache()
     other = None
     if info["mode"] == "peer" and not c.args.no_exchange_compare:
         spg.close()
@@ -525,7 +531,7 @@ def bench_sharded(c):
     roof = sampler_roofline(c, deg_r, M, m, T_avg * (hi - lo) / c.n, hi - lo, k_ms, k_n, b_ms, c.args.steps, ms_total, spg.c)
     roof["note"] = "rank 0's seed range (1/N of the seeds per launch)"
     pull = info["pull_GBps_per_gpu"] or 0.0
-    info.update({"value": info["seeds_per_s"], "unit": "seeds/s", "scaling": "strong", "parity_ok": parity_ok,
+    info.update({"value": info["seeds_per_s"], "unit": "seeds/s", "scaling": "strong", "parity_ok": parity_ok, "parity_error": parity_err,
                  "parity_check": "every rank: the exchanged SpG equals SpG.sample of all seeds on one GPU (sizes, LP table, "
                                  "per-row checksums of the (node, LP id) pairs)",
                  "what": "seed ranges sampled per rank, shards packed and pulled by the peers over NVLink; every rank holds "

@@ -4,7 +4,7 @@
     subg_matrix (set sampling + LP encoding + SpG, on the device)  ->  per batch: gather (SpJoin)  ->  Net  ->  BCE
 
 The model is a PyG-free restatement of the reference's Net (model.py:45-90: pe_embedding MLP, sum over the two
-slots, set pooling per segment, MergeLayer scorer) with mean or attention pooling written in plain PyTorch
+slots, set pooling per segment, MergeLayer scorer) with mean, attention or LSTM pooling written in plain PyTorch
 (torch_geometric is not in this image).  Purpose: the north star's acceptance item "link-prediction Hits@50
 unchanged" -- the same model trained on features from (a) the reference's own rand_r stream replayed on the GPU
 (bit-identical to the reference's arrays) and (b) the Philox fast path must reach the same Hits@50 up to
@@ -12,7 +12,7 @@ training noise.  Data: a synthetic graph (heavy-tailed background + planted comm
 train_ratio): 80 % of the edges form the observed graph the sets are sampled on, 10 % are training targets and
 10 % test positives -- neither is present in the observed graph.
 
-    python examples/link_prediction.py [--nodes 20000] [--edges 150000] [--steps 300] [--aggr mean|attn]
+    python examples/link_prediction.py [--nodes 20000] [--edges 150000] [--steps 300] [--aggr mean|attn|lstm]
 """
 import argparse
 import os
@@ -57,17 +57,40 @@ class AttnPool(nn.Module):
         return torch.zeros(sizes.numel(), x.shape[1], device=x.device).index_add_(0, seg, self.fnn(x) * w.unsqueeze(1))
 
 
+class LstmPool(nn.Module):
+    """aggr.LSTMAggregation(hidden, hidden) of model.py:63-66 (torch_geometric 2.2): the rows of every segment, in
+    order, are padded into a dense [segments, max_len, h] batch (to_dense_batch), run through one nn.LSTM
+    (batch_first) and the output of the LAST time step of the padded batch is the segment's embedding -- exactly
+    what PyG computes, padding included.  `index` is the per-row segment id (gather's ptr=False, train.py:24-30)."""
+
+    def __init__(self, h):
+        super().__init__()
+        self.lstm = nn.LSTM(h, h, batch_first=True)
+
+    def forward(self, x, index, num_segments):
+        sizes = torch.bincount(index, minlength=num_segments)
+        start = torch.cumsum(sizes, 0) - sizes
+        pos = torch.arange(x.shape[0], device=x.device) - start[index]
+        dense = x.new_zeros(num_segments, int(sizes.max()), x.shape[1])
+        dense[index, pos] = x
+        return self.lstm(dense)[0][:, -1]
+
+
 class Net(nn.Module):
     def __init__(self, input_dim, hidden, aggr="mean", dropout=0.1):
         super().__init__()
         self.pe_embedding = nn.Sequential(nn.Linear(input_dim, hidden), nn.ReLU(), nn.Linear(hidden, hidden))
-        self.pool = AttnPool(hidden) if aggr == "attn" else None
+        self.aggr = aggr
+        self.pool = AttnPool(hidden) if aggr == "attn" else (LstmPool(hidden) if aggr == "lstm" else None)
         self.fc1, self.fc2 = nn.Linear(2 * hidden, hidden), nn.Linear(hidden, 1)   # MergeLayer, model.py:7-33
         self.dropout = dropout
 
-    def forward(self, x, ptr):
+    def forward(self, x, ptr, num_segments=None):
         x = self.pe_embedding(x).sum(dim=-2)                                        # model.py:78
-        pooled = self.pool(x, ptr) if self.pool is not None else segment_mean(x, ptr)
+        if self.aggr == "lstm":                                                     # model.py:82-83: aggr(x, index=ptr)
+            pooled = self.pool(x, ptr, num_segments)
+        else:
+            pooled = self.pool(x, ptr) if self.pool is not None else segment_mean(x, ptr)
         xl, xr = pooled.view(2, -1, x.shape[-1])                                    # model.py:81
         h = F.dropout(F.relu(self.fc1(torch.cat([xl, xr], dim=-1))), p=self.dropout, training=self.training)
         return self.fc2(h).squeeze(1)
@@ -101,10 +124,18 @@ def numpy_walks(G, M, m, seed):
     return walks
 
 
+#: further sources of (SpG, LP table) to compare, appended by callers: (name, fn(G_obs, args, sample_seed) -> (z, enc)).
+#: tests/acceptance_hits50.py adds the compiled reference run with nthread = -1 (kept out of this file: the product side
+#: never touches the reference or the oracle).
+EXTRA_SOURCES = []
+
+
 def run(G_obs, pos_tr, pos_te, neg_te, rng_mode, args, model_seed, sample_seed):
     dev = "cuda:0"
     t0 = time.perf_counter()
-    if rng_mode == _capi.SUBG_RNG_TRACE:
+    if callable(rng_mode):
+        z, enc = rng_mode(G_obs, args, sample_seed)                 # e.g. a scipy CSR: gather uploads it once
+    elif rng_mode == _capi.SUBG_RNG_TRACE:
         from surel_plus_b200 import DeviceGraph, SpG
         g = DeviceGraph.from_scipy(G_obs, dev)
         z = SpG.sample(g, np.arange(G_obs.shape[0]), num_walks=args.num_walks, num_steps=args.num_steps - 1,
@@ -128,8 +159,8 @@ def run(G_obs, pos_tr, pos_te, neg_te, rng_mode, args, model_seed, sample_seed):
         q = rng.integers(0, n, (2, B))
         edge = torch.from_numpy(np.concatenate([p, q], axis=1))
         y = torch.cat([torch.ones(B), torch.zeros(B)]).to(dev)
-        xz, ptr = gather(edge, z, dev, True, xpe)                                  # train.py:119-121
-        loss = F.binary_cross_entropy_with_logits(net(xz, ptr), y)
+        xz, ptr = gather(edge, z, dev, args.aggr != "lstm", xpe)                   # train.py:119-127 (ptr=False for LSTM)
+        loss = F.binary_cross_entropy_with_logits(net(xz, ptr, 2 * edge.shape[1]), y)
         opt.zero_grad()
         loss.backward()
         opt.step()
@@ -138,11 +169,13 @@ def run(G_obs, pos_tr, pos_te, neg_te, rng_mode, args, model_seed, sample_seed):
         def score(e):
             out = []
             for i in range(0, e.shape[1], 4096):
-                xz, ptr = gather(torch.from_numpy(e[:, i:i + 4096]), z, dev, True, xpe)
-                out.append(net(xz, ptr))
+                ee = torch.from_numpy(e[:, i:i + 4096])
+                xz, ptr = gather(ee, z, dev, args.aggr != "lstm", xpe)
+                out.append(net(xz, ptr, 2 * ee.shape[1]))
             return torch.cat(out)
         h50 = hits_at_k(score(pos_te), score(neg_te), 50)
-    z.close()
+    if hasattr(z, "close"):
+        z.close()
     return h50, float(loss.detach()), t_prep
 
 
@@ -156,7 +189,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--lr", type=float, default=1e-3)
-    ap.add_argument("--aggr", default="mean", choices=["mean", "attn"])
+    ap.add_argument("--aggr", default="mean", choices=["mean", "attn", "lstm"])
     ap.add_argument("--communities", type=int, default=400)
     ap.add_argument("--model-seeds", type=int, default=3)
     ap.add_argument("--sample-seeds", type=int, default=4)
@@ -186,9 +219,11 @@ def main():
     print(f"graph: {A.shape[0]} nodes, {obs.shape[1]} observed edges, {pos_tr.shape[1]} training targets, {n_te} test positives; LP M={args.num_walks} "
           f"num_steps={args.num_steps}; Net hidden={args.hidden} aggr={args.aggr}; {args.steps} steps of {args.batch}+{args.batch}")
     res = {}
-    for name, mode in (("rand_r replay (the reference's nthread=1 stream, bit-identical arrays)", _capi.SUBG_RNG_RAND_R),
-                       ("philox (fast path)", _capi.SUBG_RNG_PHILOX),
-                       ("numpy PCG64 walks fed as traces (independent statement of the sampling law)", _capi.SUBG_RNG_TRACE)):
+    sources = [("rand_r replay (the reference's nthread=1 stream, bit-identical arrays)", _capi.SUBG_RNG_RAND_R),
+               ("philox (fast path)", _capi.SUBG_RNG_PHILOX),
+               ("numpy PCG64 walks fed as traces (independent statement of the sampling law)", _capi.SUBG_RNG_TRACE)]
+    sources += list(EXTRA_SOURCES)
+    for name, mode in sources:
         hs = []
         for ss in range(args.sample_seeds):          # one sampled SpG per sampling seed ...
             for ms in range(args.model_seeds):       # ... and several model initialisations / batch orders on it

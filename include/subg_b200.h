@@ -59,6 +59,9 @@ extern "C" {
                                    them back as SUBG_RNG_TRACE, or to a CPU restatement of subg_acc.c:778-844, must
                                    reproduce the SpG bit for bit -- the parity hook of the Philox fast path */
 
+#define SUBG_SAMPLE_NO_COMPACT 4 /* keep the rows where the sampler put them even when the worst-case allocation is mostly
+                                   empty (a shard that only lives until it is packed for the multi-GPU exchange) */
+
 /* structure encoders of utils.py:20-39 (the 'DEG' branch is broken upstream and not provided) */
 #define SUBG_ENCODER_NONE 0
 #define SUBG_ENCODER_PPR  1 /* utils.py:35-36 */
@@ -242,10 +245,10 @@ int subg_spjoin(const subg_spg *s, const int64_t *edge_hd, int64_t B, int arity,
 
 /* The per-batch join of a training / evaluation loop (train.py:121-127: one gather per mini-batch of 1024 queries;
  * main_horder.py:33: 2048 triplets) without allocation or host synchronisation: a joiner fixes the SpG, the batch size,
- * the arity, the LP table and the output capacity, and captures [plan -> join -> row count to pinned memory] as a CUDA
- * graph for each of `depth` ring slots.  submit copies the batch's edges (int64[arity*B]; edge_on_device: 1 device memory,
+ * the arity, the LP table and the output capacity, and captures [plan -> join] as a CUDA graph (two kernel nodes) for each
+ * of `depth` ring slots; the plan kernel reads the batch's edges straight from the slot's pinned staging.  submit copies the batch's edges (int64[arity*B]; edge_on_device: 1 device memory,
  * 0 host memory, < 0 ask the driver) into the next slot and launches its graph on `stream` (host edges: one memcpy into
- * pinned staging + one cudaGraphLaunch; device edges: a copy on the stream + the same kernels launched directly); it
+ * pinned staging + one cudaGraphLaunch; device edges: the same two kernels launched directly on the caller's array); it
  * returns the slot's device buffers at once:
  *   out_dev     rows [0, N) of the layout of subg_spjoin_run; rows beyond N are not written
  *   indptr_dev  int64[nseg+1] segment pointers (train.py:21-30)      segid_dev  int64 rows' segment ids (want_segid)

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "_lib", "libsubg_b200.so")
 
 SUBG_RNG_PHILOX, SUBG_RNG_RAND_R, SUBG_RNG_TRACE = 0, 1, 2
 STATUS_BUCKET_OVERFLOW, STATUS_DEAD_END, STATUS_PPR_SECOND_PASS = 1, 2, 4
-SAMPLE_NO_RANKS, SAMPLE_DUMP_WALKS = 1, 2
+SAMPLE_NO_RANKS, SAMPLE_DUMP_WALKS, SAMPLE_NO_COMPACT = 1, 2, 4
 ENCODER_NONE, ENCODER_PPR, ENCODER_SPD = 0, 1, 2
 TIMING_SAMPLER, TIMING_SPJOIN, TIMING_BUILD, TIMING_PPR, TIMING_EXCHANGE = 0, 1, 2, 3, 4
 

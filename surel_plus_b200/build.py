@@ -75,5 +75,52 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+#: SASS mnemonics worth seeing at a glance: TMA bulk copies + their mbarriers, global / shared atomics, read-only-path
+#: gathers, warp reductions, shuffles, votes, matrix pipes (there should be none: nothing here is a contraction)
+SASS_WATCH = ["UBLKCP", "UTMALDG", "SYNCS", "ATOMG", "ATOMS", "REDG", "RED.", "LDG.E.CONSTANT", "LDG.E.64.CONSTANT", "LDG.E.128",
+              "STG.E.128", "LDS", "STS", "REDUX", "SHFL", "VOTE", "MATCH", "VIMNMX", "POPC", "HMMA", "UTC", "LDTM", "BAR.SYNC",
+              "WARPSYNC", "LDL", "STL"]
+
+
+def sass_summary(out_path: str | None = None) -> str:
+    """Opcode histogram of every object of the library (cuobjdump -sass), written to profiles/sass_summary.txt:
+    the evidence that the kernels are sm_100a code and which Blackwell / memory-system instructions they use."""
+    import collections
+    import re
+    objdir = os.path.join(LIBDIR, "obj")
+    cuobjdump = os.path.join(os.path.dirname(NVCC), "cuobjdump")
+    lines = ["# cuobjdump -sass of surel_plus_b200/_lib/obj/*.o (regenerate: python -m surel_plus_b200.build --sass)",
+             "# per object: arch, kernels, instructions, then the watched mnemonics (prefix match) with their counts", ""]
+    for src in SOURCES:
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        if not os.path.exists(obj):
+            continue
+        r = subprocess.run([cuobjdump, "-sass", obj], capture_output=True, text=True)
+        arch = sorted(set(re.findall(r"arch = (sm_\w+)", r.stdout)))
+        kernels = re.findall(r"Function : (\S+)", r.stdout)
+        ops = collections.Counter()
+        for m in re.finditer(r"^\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", r.stdout, flags=re.M):
+            ops[m.group(1)] += 1
+        watched = []
+        for w in SASS_WATCH:
+            n = sum(c for o, c in ops.items() if o.startswith(w))
+            if n:
+                watched.append(f"{w}*={n}")
+        lines.append(f"{src}: arch {','.join(arch) or '?'}; {len(kernels)} kernels; {sum(ops.values())} instructions")
+        lines.append("    " + "  ".join(watched))
+        per = collections.Counter()
+        for k in kernels:
+            per[re.sub(r"I[A-Za-z0-9_]*E+v.*$", "", k)[:60]] += 1
+        lines.append("    kernels: " + ", ".join(f"{k} x{n}" if n > 1 else k for k, n in sorted(per.items())))
+        lines.append("")
+    text = "\n".join(lines)
+    out_path = out_path or os.path.join(os.path.dirname(HERE), "profiles", "sass_summary.txt")
+    with open(out_path, "w") as f:
+        f.write(text)
+    return out_path
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--sass" in sys.argv:
+        print(sass_summary())

@@ -55,6 +55,100 @@ void timing_end(int which, cudaStream_t st) {
         }
 }
 
+// ---- cache of large device blocks (see common.cuh)
+struct BigBlock {
+    void *p;
+    size_t bytes;
+    int device;
+    cudaStream_t st;
+    cudaEvent_t ev;
+};
+static std::mutex g_big_mutex;
+static std::vector<BigBlock> g_big_free;                      // cached, oldest first
+static std::vector<std::pair<void *, size_t>> g_big_live;    // handed out: (pointer, bytes)
+static long long g_big_limit = -1;
+
+static void big_release_locked(size_t i) {
+    BigBlock b = g_big_free[i];
+    g_big_free.erase(g_big_free.begin() + (long)i);
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != b.device) cudaSetDevice(b.device);
+    cudaEventSynchronize(b.ev);
+    cudaEventDestroy(b.ev);
+    cudaFree(b.p);
+    if (cur != b.device) cudaSetDevice(cur);
+}
+
+cudaError_t big_alloc(void **p, size_t bytes, cudaStream_t st) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_big_mutex);
+    size_t best = (size_t)-1;
+    for (size_t i = 0; i < g_big_free.size(); i++) {
+        const BigBlock &b = g_big_free[i];
+        if (b.device == dev && b.bytes >= bytes && b.bytes <= bytes + bytes / 4 + ((size_t)64 << 20) &&
+            (best == (size_t)-1 || b.bytes < g_big_free[best].bytes))
+            best = i;
+    }
+    if (best != (size_t)-1) {
+        BigBlock b = g_big_free[best];
+        g_big_free.erase(g_big_free.begin() + (long)best);
+        if (b.st != st) cudaStreamWaitEvent(st, b.ev, 0);   // same stream: already ordered behind the last use
+        cudaEventDestroy(b.ev);
+        *p = b.p;
+        g_big_live.emplace_back(b.p, b.bytes);
+        return cudaSuccess;
+    }
+    const size_t rounded = (bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+    cudaError_t e = cudaMalloc(p, rounded);
+    while (e == cudaErrorMemoryAllocation) {   // give cached blocks of this device back to the driver and retry
+        cudaGetLastError();
+        size_t victim = (size_t)-1;
+        for (size_t i = 0; i < g_big_free.size(); i++)
+            if (g_big_free[i].device == dev) { victim = i; break; }
+        if (victim == (size_t)-1) break;
+        big_release_locked(victim);
+        e = cudaMalloc(p, rounded);
+    }
+    if (e == cudaSuccess) g_big_live.emplace_back(*p, rounded);
+    return e;
+}
+
+bool big_free(void *p, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_big_mutex);
+    size_t at = (size_t)-1;
+    for (size_t i = g_big_live.size(); i-- > 0;)
+        if (g_big_live[i].first == p) { at = i; break; }
+    if (at == (size_t)-1) return false;
+    BigBlock b{};
+    b.p = p;
+    b.bytes = g_big_live[at].second;
+    g_big_live.erase(g_big_live.begin() + (long)at);
+    cudaGetDevice(&b.device);
+    b.st = st;
+    if (cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(b.ev, st) != cudaSuccess) {
+        cudaGetLastError();
+        cudaStreamSynchronize(st);
+        cudaFree(p);
+        return true;
+    }
+    g_big_free.push_back(b);
+    if (g_big_limit < 0) {   // cached bytes allowed per process: SUBG_BLOCK_CACHE_BYTES, default 45 % of the device
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const char *v = getenv("SUBG_BLOCK_CACHE_BYTES");
+        g_big_limit = v ? atoll(v) : (long long)(total_b * 0.45);
+    }
+    size_t held = 0;
+    for (const BigBlock &q : g_big_free) held += q.bytes;
+    while (held > (size_t)g_big_limit && !g_big_free.empty()) {
+        held -= g_big_free[0].bytes;
+        big_release_locked(0);
+    }
+    return true;
+}
+
 bool is_device_ptr(const void *p) {
     if (!p) return false;
     cudaPointerAttributes at;

@@ -71,13 +71,24 @@ void count_launch(int n = 1);
 void timing_begin(int which, cudaStream_t st);
 void timing_end(int which, cudaStream_t st);
 
-// stream-ordered scratch allocation
+// Device allocation.  Small blocks come from the driver's stream-ordered pool.  Large blocks (>= 64 MB: SpG row arrays,
+// the sampler's worst-case staging) come from a per-device cache of cudaMalloc'd blocks kept by the library (capi.cu):
+// a block goes back to the cache with an event recorded on the freeing stream and is handed out again to a request of
+// similar size, stream-ordered behind that event.  Measured reason: once peer mappings exist in the process (the
+// multi-GPU exchange), the driver pool re-creates multi-GB allocations on every pass (300 ms per 10 GB) instead of
+// reusing them.
+cudaError_t big_alloc(void **p, size_t bytes, cudaStream_t st);
+bool big_free(void *p, cudaStream_t st);   // true if p was a cached large block
+constexpr size_t kBigBlockBytes = (size_t)64 << 20;
+
 template <typename T>
 inline cudaError_t dmalloc(T **p, size_t count, cudaStream_t st) {
-    return cudaMallocAsync((void **)p, (count ? count : 1) * sizeof(T), st);
+    const size_t bytes = (count ? count : 1) * sizeof(T);
+    if (bytes >= kBigBlockBytes) return big_alloc((void **)p, bytes, st);
+    return cudaMallocAsync((void **)p, bytes, st);
 }
 inline void dfree(void *p, cudaStream_t st) {
-    if (p) cudaFreeAsync(p, st);
+    if (p && !big_free(p, st)) cudaFreeAsync(p, st);
 }
 
 // ------------------------------------------------------------------ stream ordering of handles

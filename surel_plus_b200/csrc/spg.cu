@@ -622,7 +622,7 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
         // No synchronisation here: the id remap is still in flight; everything that touches the SpG later
         // (SpJoin, export, views, free) is ordered behind it on the stream.
         // A mostly empty worst-case allocation is not worth keeping
-        if (!s->indptr && cap > s->extent + s->extent / 4 + (16ll << 20)) {
+        if (!s->indptr && !(flags & SUBG_SAMPLE_NO_COMPACT) && cap > s->extent + s->extent / 4 + (16ll << 20)) {
             timing_begin(SUBG_TIMING_BUILD, st);
             const int erc = spg_ensure_csr(s, st);
             timing_end(SUBG_TIMING_BUILD, st);

@@ -99,8 +99,9 @@ __global__ void join_sizes_kernel(const long long *rowbeg, const int32_t *nsize,
 constexpr int kPlanTile = 256;
 constexpr int kPlanSmallMax = 1024 * kPlanTile;
 __global__ void __launch_bounds__(kPlanTile) join_plan_sizes_kernel(const long long *rowbeg, const int32_t *nsize, int64_t n_rows,
-                                                                   const long long *edge, int64_t B, int arity, int32_t *sizes,
-                                                                   long long *tile_off, unsigned int *done, long long *tot) {
+                                                                   const long long *edge, long long *edge_out, int64_t B, int arity,
+                                                                   int32_t *sizes, long long *tile_off, unsigned int *done,
+                                                                   long long *tot) {
     __shared__ long long ws[32];
     __shared__ bool last;
     const int nseg = (int)(arity == 2 ? 2 * B : 4 * B);
@@ -108,12 +109,13 @@ __global__ void __launch_bounds__(kPlanTile) join_plan_sizes_kernel(const long l
     int32_t sz = 0;
     bool bad = false;
     if (g < nseg) {
-        long long node;
-        if (arity == 2) node = edge[g];
-        else {
+        int64_t at = g;
+        if (arity != 2) {
             const int blk = g / (int)B, q = g - blk * (int)B;
-            node = edge[(int64_t)(blk == 0 ? 0 : (blk == 2 ? 1 : 2)) * B + q];  // u, w, v, w
+            at = (int64_t)(blk == 0 ? 0 : (blk == 2 ? 1 : 2)) * B + q;  // u, w, v, w
         }
+        const long long node = edge[at];
+        if (edge_out) edge_out[at] = node;
         if (node < 0 || node >= n_rows) bad = true;
         else sz = nsize ? nsize[node] : (int32_t)(rowbeg[node + 1] - rowbeg[node]);
         sizes[g] = sz;
@@ -164,9 +166,10 @@ __global__ void __launch_bounds__(kPlanTile) join_plan_offsets_kernel(const int3
 constexpr int kPlanOneThreads = 1024;
 constexpr int kPlanOneItems = 16;
 constexpr int kPlanOneMax = kPlanOneThreads * kPlanOneItems;
+// edge may be pinned host memory (read once over PCIe); edge_out (nullable) receives the device copy the join kernel reads
 __global__ void __launch_bounds__(kPlanOneThreads) join_plan_one_kernel(const long long *rowbeg, const int32_t *nsize, int64_t n_rows,
-                                                                       const long long *edge, int64_t B, int arity, int nseg,
-                                                                       long long *seg_ptr, long long *tot) {
+                                                                       const long long *edge, long long *edge_out, int64_t B,
+                                                                       int arity, int nseg, long long *seg_ptr, long long *tot) {
     __shared__ long long ws[32];
     const int per = (nseg + kPlanOneThreads - 1) / kPlanOneThreads;   // consecutive segments per thread, <= kPlanOneItems
     const int first = threadIdx.x * per;
@@ -179,11 +182,13 @@ __global__ void __launch_bounds__(kPlanOneThreads) join_plan_one_kernel(const lo
         const int g = first + q;
         if (q < per && g < nseg) {
             long long node;
-            if (arity == 2) node = edge[g];
-            else {
+            int64_t at = g;
+            if (arity != 2) {
                 const int blk = g / (int)B, qq = g - blk * (int)B;
-                node = edge[(int64_t)(blk == 0 ? 0 : (blk == 2 ? 1 : 2)) * B + qq];  // u, w, v, w
+                at = (int64_t)(blk == 0 ? 0 : (blk == 2 ? 1 : 2)) * B + qq;  // u, w, v, w
             }
+            node = edge[at];
+            if (edge_out) edge_out[at] = node;
             if (node < 0 || node >= n_rows) bad = true;
             else sz[q] = nsize ? nsize[node] : (int32_t)(rowbeg[node + 1] - rowbeg[node]);
             sum += sz[q];
@@ -599,7 +604,7 @@ int spjoin_fused_impl(const SpG *s, const int64_t *edge_hd, int64_t B, int arity
         if (tiles > 0) {
             long long *tile_off = s->join_tot + 8;
             join_plan_sizes_kernel<<<tiles, kPlanTile, 0, st>>>((const long long *)s->rowbeg, s->indptr ? nullptr : s->nsize, s->n,
-                                                                (const long long *)edge_dev, B, arity, s->join_sizes, tile_off,
+                                                                (const long long *)edge_dev, nullptr, B, arity, s->join_sizes, tile_off,
                                                                 (unsigned int *)(s->join_tot + 3), s->join_tot);
             join_plan_offsets_kernel<<<tiles, kPlanTile, 0, st>>>(s->join_sizes, tile_off, (int)nseg, (long long *)indptr_dev,
                                                                   s->join_tot);
@@ -652,6 +657,7 @@ struct JoinSlot {
     long long *edge_pin = nullptr, *tot_pin = nullptr;
     cudaGraphExec_t exec = nullptr;
     cudaEvent_t done = nullptr;
+    cudaStream_t last_stream = nullptr;
 };
 struct Joiner {
     const SpG *s = nullptr;
@@ -685,28 +691,29 @@ void joiner_free_impl(Joiner *j) {
 
 // plan + join + row count to pinned memory of one slot, queued on st (captured into the slot's graph, and run once
 // un-captured beforehand so that the launch attributes are cached before the capture starts)
-static int joiner_enqueue(Joiner *j, JoinSlot &sl, cudaStream_t st, bool upload) {
+// plan + join of one slot, queued on st (captured into the slot's graph, and run once un-captured beforehand so that the
+// launch attributes are cached before the capture starts).  edge_src: where the plan kernel reads the batch's edges --
+// the slot's pinned host staging (zero-copy over PCIe, 16-48 KB) or the caller's device array; the plan kernel leaves
+// the device copy that the join kernel reads.  Two kernel nodes per batch, nothing else.
+static int joiner_enqueue(Joiner *j, JoinSlot &sl, cudaStream_t st, const long long *edge_src) {
     const SpG *s = j->s;
     const int64_t B = j->B, nseg = (j->arity == 2 ? 2 : 4) * B;
-    if (upload) cudaMemcpyAsync(sl.edge_dev, sl.edge_pin, (size_t)j->arity * B * 8, cudaMemcpyHostToDevice, st);
     if (nseg <= kPlanOneMax) {
         join_plan_one_kernel<<<1, kPlanOneThreads, 0, st>>>((const long long *)s->rowbeg, s->indptr ? nullptr : s->nsize, s->n,
-                                                            sl.edge_dev, B, j->arity, (int)nseg, sl.indptr_dev, sl.tot_dev);
+                                                            edge_src, sl.edge_dev, B, j->arity, (int)nseg, sl.indptr_dev, sl.tot_dev);
         j->launches = 2;
     } else {
         const int tiles = (int)((nseg + kPlanTile - 1) / kPlanTile);
         long long *tile_off = sl.tot_dev + 8;
         cudaMemsetAsync(sl.tot_dev, 0, 2 * sizeof(long long), st);
         join_plan_sizes_kernel<<<tiles, kPlanTile, 0, st>>>((const long long *)s->rowbeg, s->indptr ? nullptr : s->nsize, s->n,
-                                                            sl.edge_dev, B, j->arity, sl.sizes_dev, tile_off,
+                                                            edge_src, sl.edge_dev, B, j->arity, sl.sizes_dev, tile_off,
                                                             (unsigned int *)(sl.tot_dev + 3), sl.tot_dev);
         join_plan_offsets_kernel<<<tiles, kPlanTile, 0, st>>>(sl.sizes_dev, tile_off, (int)nseg, sl.indptr_dev, sl.tot_dev);
         j->launches = 3;
     }
-    const int rc = join_launch(s, (const int64_t *)sl.edge_dev, B, j->arity, (const int64_t *)sl.indptr_dev, j->enc, j->k, sl.out_dev,
-                               (int64_t *)sl.segid_dev, j->cap_rows, sl.tot_dev, st);
-    cudaMemcpyAsync(sl.tot_pin, sl.tot_dev, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st);
-    return rc;
+    return join_launch(s, (const int64_t *)sl.edge_dev, B, j->arity, (const int64_t *)sl.indptr_dev, j->enc, j->k, sl.out_dev,
+                       (int64_t *)sl.segid_dev, j->cap_rows, sl.tot_dev, st);
 }
 
 int joiner_create_impl(const SpG *s, int64_t B, int arity, const float *enc_table_dev, int k, int64_t capacity_rows,
@@ -742,14 +749,14 @@ int joiner_create_impl(const SpG *s, int64_t B, int arity, const float *enc_tabl
         if (e != cudaSuccess) break;
         sl.tot_pin[0] = sl.tot_pin[1] = 0;
         if (q == 0) {  // dry run (all queries = node 0): launch attributes and occupancy are cached outside the capture
-            rc = joiner_enqueue(j, sl, j->cap_stream, true);
+            rc = joiner_enqueue(j, sl, j->cap_stream, sl.edge_pin);
             e = cudaStreamSynchronize(j->cap_stream);
             if (rc != SUBG_OK || e != cudaSuccess) break;
         }
         cudaGraph_t graph = nullptr;
         e = cudaStreamBeginCapture(j->cap_stream, cudaStreamCaptureModeThreadLocal);
         if (e != cudaSuccess) break;
-        rc = joiner_enqueue(j, sl, j->cap_stream, true);
+        rc = joiner_enqueue(j, sl, j->cap_stream, sl.edge_pin);
         e = cudaStreamEndCapture(j->cap_stream, &graph);
         if (e == cudaSuccess && rc == SUBG_OK) e = cudaGraphInstantiate(&sl.exec, graph, 0);
         if (graph) cudaGraphDestroy(graph);
@@ -779,14 +786,14 @@ int joiner_submit_impl(Joiner *j, const int64_t *edge_hd, int edge_on_device, cu
     const size_t eb = (size_t)j->arity * j->B * 8;
     if (edge_on_device < 0) edge_on_device = is_device_ptr(edge_hd) ? 1 : 0;
     if (edge_on_device) {
-        SUBG_CUDA(cudaMemcpyAsync(sl.edge_dev, edge_hd, eb, cudaMemcpyDeviceToDevice, st));
-        if (int rc = joiner_enqueue(j, sl, st, false)) return rc;
+        if (int rc = joiner_enqueue(j, sl, st, (const long long *)edge_hd)) return rc;
     } else {
         SUBG_CUDA(cudaEventSynchronize(sl.done));  // the slot's previous batch has read its staging (long ago, unless the ring is lapped)
         memcpy(sl.edge_pin, edge_hd, eb);
         SUBG_CUDA(cudaGraphLaunch(sl.exec, st));
     }
     SUBG_CUDA(cudaEventRecord(sl.done, st));
+    sl.last_stream = st;
     count_launch(j->launches);
     if (out_dev) *out_dev = sl.out_dev;
     if (indptr_dev) *indptr_dev = (int64_t *)sl.indptr_dev;
@@ -801,7 +808,9 @@ int joiner_submit_impl(Joiner *j, const int64_t *edge_hd, int edge_on_device, cu
 int joiner_rows_impl(Joiner *j, int slot, int64_t *N) {
     if (!j || slot < 0 || slot >= j->depth || !N) return fail(SUBG_ERR_ARG, "Input parsing error.");
     JoinSlot &sl = j->slot[slot];
-    SUBG_CUDA(cudaEventSynchronize(sl.done));
+    DeviceGuard guard(j->s->device);
+    SUBG_CUDA(cudaMemcpyAsync(sl.tot_pin, sl.tot_dev, 2 * sizeof(long long), cudaMemcpyDeviceToHost, sl.last_stream));
+    SUBG_CUDA(cudaStreamSynchronize(sl.last_stream));
     if (sl.tot_pin[1]) return fail(SUBG_ERR_ARG, "query node id outside the SpG");
     *N = sl.tot_pin[0];
     if (sl.tot_pin[0] > j->cap_rows) return fail(SUBG_ERR_MEM, "joiner: rows of the batch exceed the slot capacity");

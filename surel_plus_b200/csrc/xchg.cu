@@ -448,6 +448,10 @@ int xchg_assemble_impl(Xchg *x, const int64_t *headers, const void *const *srcs,
     }
     ma.coff[W] = c_sum;
 
+    HostProf prof;
+    auto pmark = [&](const char *what) {  // SUBG_PROFILE_HOST: per-phase wall time (adds a stream sync per phase)
+        if (prof.on) { cudaStreamSynchronize(st); prof.mark(what); }
+    };
     SpG *s = new SpG();
     s->tag.last = st;
     s->device = x->device; s->n = n_tot; s->T = T_tot; s->ncol = ncol; s->M = M; s->shift = shift; s->value_kind = 0;
@@ -478,6 +482,7 @@ int xchg_assemble_impl(Xchg *x, const int64_t *headers, const void *const *srcs,
         CKX(dmalloc(&d_cnt, 2, st));
         CKX(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(uint32_t), st));
         s->extent = ext_tot; s->cap = ext_tot + 16;
+        pmark("xchg:alloc");
         if (c_sum > 0) {
             uint32_t cap = 1024;
             while (cap < 4u * (uint32_t)c_sum) cap <<= 1;
@@ -494,6 +499,7 @@ int xchg_assemble_impl(Xchg *x, const int64_t *headers, const void *const *srcs,
             CKX(cudaGetLastError());
             count_launch(3);
         }
+        pmark("xchg:merge");
         if (ext_tot > 0 || n_tot > 0) {
             pa.indices = s->indices; pa.data = (int32_t *)s->data; pa.rowbeg = (long long *)s->rowbeg; pa.nsize = s->nsize; pa.gmap = gmap;
             int per_region = std::max(1, (int)env_blocks_per_region(s->num_sms, W));
@@ -503,6 +509,7 @@ int xchg_assemble_impl(Xchg *x, const int64_t *headers, const void *const *srcs,
             CKX(cudaGetLastError());
             count_launch(1);
         }
+        pmark("xchg:pull");
         CKX(cudaMemcpyAsync(x->host_words, d_cnt, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CKX(cudaStreamSynchronize(st));
         s->c = (int32_t)((uint32_t *)x->host_words)[0];

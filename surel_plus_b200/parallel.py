@@ -292,17 +292,30 @@ def sharded_sample(graph, query, num_walks=100, num_steps=3, bucket=-1, seed=111
     h = C.c_void_p()
     rmode = _capi.SUBG_RNG_PHILOX if rng_mode is None else rng_mode
     _capi.check(lib.subg_gset_sample_shard(graph._h, _ptr(q), n, lo, hi, int(num_walks), int(num_steps), int(bucket),
-                                           int(seed) & 0xFFFFFFFFFFFFFFFF, int(rmode), None, _capi.SAMPLE_NO_RANKS,
-                                           st, C.byref(h)))
+                                           int(seed) & 0xFFFFFFFFFFFFFFFF, int(rmode), None,
+                                           _capi.SAMPLE_NO_RANKS | _capi.SAMPLE_NO_COMPACT, st, C.byref(h)))
     shard = SpG(h, graph.device, n_nodes=graph.N, num_walks=num_walks)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     ev[0].record()
+    prof = os.environ.get("SUBG_PROFILE_HOST") is not None   # per-phase wall times (adds a device sync per phase)
+    marks, t_last = [], time.perf_counter()
+
+    def mark(name):
+        nonlocal t_last
+        if prof:
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            marks.append(f"{name}={1e3 * (t - t_last):.2f}")
+            t_last = t
+    mark("sync-after-sample")
     hdr = np.zeros(8, np.int64)
     _capi.check(lib.subg_xchg_pack(xc._h, shard._h, graph.N, hdr.ctypes.data, st))
+    mark("pack")
     # the header all-gather is the barrier: when it completes here, every peer's pack kernel has completed
     allh = torch.empty((world, 8), dtype=torch.int64, device=tdev)
     dist.all_gather_into_tensor(allh, torch.from_numpy(hdr).to(tdev), group=group)
     headers = np.ascontiguousarray(allh.cpu().numpy())
+    mark("headers")
     if (headers[:, H_FMT] < 0).any():
         shard.close()
         raise MemoryError("a shard did not fit its exchange slab")
@@ -314,12 +327,18 @@ def sharded_sample(graph, query, num_walks=100, num_steps=3, bucket=-1, seed=111
         dist.all_gather_into_tensor(staging, xc.slab_view(stride), group=group)
         srcs = (C.c_void_p * world)(*[staging.data_ptr() + r * stride for r in range(world)])
     fh = C.c_void_p()
+    mark("staging" if staging is not None else "-")
     _capi.check(lib.subg_xchg_assemble(xc._h, headers.ctypes.data, srcs, int(num_walks), int(num_steps) + 1, st, C.byref(fh)))
+    mark("assemble")
     if xc.mode == "peer" and world > 1:
         # nobody may re-pack its slab before every peer has pulled it
         dist.all_reduce(torch.zeros(1, dtype=torch.int32, device=tdev), group=group)
+    mark("end-barrier")
     shard.close()
     full = SpG(fh, graph.device, n_nodes=graph.N, num_walks=num_walks)
+    mark("close-shard")
+    if prof and rank == 0:
+        print("[subg host ms] sharded_sample: " + " ".join(marks), file=sys.stderr, flush=True)
     ev[1].record()
     received = int(headers[:, H_BYTES].sum() - headers[rank, H_BYTES])
     full.exchange_mode = xc.mode
@@ -335,8 +354,8 @@ def sharded_subg_matrix(G, train_idx, num_walks=200, num_steps=4, device=None, s
     from .spg import DeviceGraph
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device())
-    graph = DeviceGraph.from_scipy(G, device)
-    world, _, _ = _group_info(group)
+    world, _, backend = _group_info(group)
+    graph = DeviceGraph.from_scipy_sharded(G, device, group) if (world > 1 and backend == "nccl") else DeviceGraph.from_scipy(G, device)
     deg = np.diff(G.indptr)
     idx = np.asarray(train_idx)
     w = 0.5 * num_walks * (num_steps - 1) + 1.5 * np.minimum(deg[idx], num_walks)   # set-size estimate per seed

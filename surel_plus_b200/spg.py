@@ -57,7 +57,10 @@ class _PinnedPool:
     numpy array built over it (and every view of it) is garbage collected.  Blocks are 12.5 % larger than
     asked so that the next call, whose sizes differ slightly, still fits."""
 
-    def __init__(self, keep_bytes: int = int(os.environ.get("SUBG_PINNED_POOL_BYTES", 6 << 30))):
+    def __init__(self, keep_bytes: int | None = None):
+        if keep_bytes is None:  # default 6 GiB per node, shared by the ranks of a torchrun job (one process per GPU)
+            local_world = max(int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1), 1)
+            keep_bytes = int(os.environ.get("SUBG_PINNED_POOL_BYTES", (6 << 30) // local_world))
         self._free: list[tuple[int, int]] = []  # (capacity, address)
         self._keep = keep_bytes
         self._lib = None
@@ -70,11 +73,19 @@ class _PinnedPool:
                 b = min(fit)
                 self._free.remove(b)
                 return b
-        self._lib = self._lib or _capi.load()
+        with self._lock:
+            self._lib = self._lib or _capi.load()
         cap = max(4096, ((nbytes + (nbytes >> 3) + (1 << 21) - 1) >> 21) << 21) if nbytes > (1 << 20) else max(nbytes, 64)
         p = C.c_void_p()
         _capi.check(self._lib.subg_host_alloc(C.byref(p), cap))
         return cap, p.value
+
+    def trim(self, keep_bytes: int = 0) -> None:
+        """Return pooled blocks to the driver until at most keep_bytes stay page-locked."""
+        with self._lock:
+            while self._free and sum(b[0] for b in self._free) > keep_bytes:
+                c, a = self._free.pop(0)
+                self._lib.subg_host_free(C.c_void_p(a))
 
     def give(self, cap: int, addr: int) -> None:
         try:
@@ -94,18 +105,52 @@ class _PinnedBlock:
     """Owner of one pooled block; numpy arrays reference it through __array_interface__."""
 
     def __init__(self, shape, dtype):
+        self.cap = self.addr = None   # __del__ runs even if take() raises
         self.shape, self.dtype = tuple(int(x) for x in shape), np.dtype(dtype)
         nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
         self.cap, self.addr = _pinned.take(nbytes)
         self.__array_interface__ = {"shape": self.shape, "typestr": self.dtype.str, "data": (self.addr, False), "version": 3}
 
     def __del__(self):
-        _pinned.give(self.cap, self.addr)
+        if self.addr is not None:
+            _pinned.give(self.cap, self.addr)
 
 
 def pinned_empty(shape, dtype) -> np.ndarray:
     """Uninitialised numpy array over pooled page-locked memory (asynchronous D2H target)."""
     return np.asarray(_PinnedBlock(shape, dtype))
+
+
+_copy_pool = None
+
+
+def staged_h2d(arr: np.ndarray, device) -> torch.Tensor:
+    """Pageable host array -> device tensor through pooled page-locked staging: worker threads copy 8 MB chunks into the
+    pinned block (numpy releases the GIL for plain copies) while the chunks that are ready are already on their way
+    over PCIe.  A plain cudaMemcpy from pageable memory runs at roughly a quarter of the link rate (one driver thread
+    bouncing through its own staging)."""
+    global _copy_pool
+    from concurrent.futures import ThreadPoolExecutor
+    a = np.ascontiguousarray(arr)
+    dev = torch.device("cuda", _dev_index(device))
+    out = torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype, device=dev)
+    flat = a.reshape(-1).view(np.uint8)
+    if flat.size < (32 << 20):
+        out.copy_(torch.from_numpy(a))
+        return out
+    if _copy_pool is None:
+        _copy_pool = ThreadPoolExecutor(max_workers=min(6, max(2, (os.cpu_count() or 4) // 2)))
+    stage = pinned_empty((flat.size,), np.uint8)
+    stage_t = torch.from_numpy(stage)
+    dst = out.reshape(-1).view(torch.uint8)
+    CH = 8 << 20
+    futs = [(lo, min(lo + CH, flat.size), _copy_pool.submit(np.copyto, stage[lo:min(lo + CH, flat.size)], flat[lo:min(lo + CH, flat.size)]))
+            for lo in range(0, flat.size, CH)]
+    for lo, hi, f in futs:
+        f.result()
+        dst[lo:hi].copy_(stage_t[lo:hi], non_blocking=True)
+    torch.cuda.current_stream(dev).synchronize()   # the staging block goes back to the pool when `stage` dies
+    return out
 
 
 class DeviceGraph:
@@ -116,6 +161,10 @@ class DeviceGraph:
         self._lib = _capi.load()
         self.device = _dev_index(device)
         self._h = C.c_void_p()
+        if isinstance(indices, np.ndarray) and indices.dtype == np.int32 and indices.nbytes >= (32 << 20) \
+                and isinstance(indptr, np.ndarray) and indptr.dtype in (np.int32, np.int64):
+            # large pageable arrays: pipelined upload through pinned staging (staged_h2d)
+            indptr, indices = staged_h2d(indptr, self.device), staged_h2d(indices, self.device)
         if isinstance(indptr, torch.Tensor):
             if indptr.dtype not in (torch.int32, torch.int64) or indices.dtype != torch.int32:
                 raise TypeError("indptr must be int32/int64 and indices int32")
@@ -142,6 +191,28 @@ class DeviceGraph:
     @classmethod
     def from_scipy(cls, G, device="cuda"):
         return cls(G.indptr, G.indices, device)
+
+    @classmethod
+    def from_scipy_sharded(cls, G, device, group=None):
+        """Same graph on every rank of `group`, uploaded cooperatively: every rank copies only its 1/world slice of the
+        column array from host memory and the slices are all-gathered over NVLink (NCCL), instead of `world` processes
+        pushing the whole CSR through the host's memory system at once.  Every rank must hold the same G."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        dev = torch.device("cuda", _dev_index(device))
+        indices = np.ascontiguousarray(G.indices, dtype=np.int32)
+        E = indices.size
+        chunk = max((E + world - 1) // world, 1)
+        lo, hi = min(rank * chunk, E), min((rank + 1) * chunk, E)
+        mine = torch.zeros(chunk, dtype=torch.int32, device=dev)
+        if hi > lo:
+            mine[:hi - lo].copy_(torch.from_numpy(indices[lo:hi]))
+        full = torch.empty(world * chunk, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(full, mine, group=group)
+        indptr = torch.from_numpy(np.ascontiguousarray(G.indptr)).to(dev)
+        if indptr.dtype not in (torch.int32, torch.int64):
+            indptr = indptr.to(torch.int64)
+        return cls(indptr, full[:E], dev)
 
     @classmethod
     def from_edges(cls, row, col, num_nodes=None, symmetrize=False, drop_self_loops=False, device="cuda"):

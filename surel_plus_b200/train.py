@@ -166,10 +166,11 @@ class JoinStream:
     `xz` of submit has `capacity` rows; rows [0, nrows[0]) are the join, in the order and layout of gather; the segment
     pointer `indptr` (int64 [2B+1], or [4B+1] for triplets) addresses only those.  The buffers of a submit are reused
     `depth` submits later: consume them on the same stream before that.  segid=True also returns the per-row segment id
-    (gather's ptr=False / hgather's `ind`)."""
+    (gather's ptr=False / hgather's `ind`).  Batches are queued on the CUDA stream that was current when the JoinStream was
+    built (or `stream=`)."""
 
     def __init__(self, x, batch_size: int, device="cuda", encode=None, arity: int = 2, capacity: int | None = None,
-                 segid: bool = False, depth: int = 3):
+                 segid: bool = False, depth: int = 3, stream=None):
         from .spg import _view
         self._view = _view
         self.spg = _as_spg(x, device)
@@ -198,6 +199,8 @@ class JoinStream:
         _capi.check(self._lib.subg_joiner_create(self.spg._h, self.B, self.arity, self.table.data_ptr() if self.table is not None else None,
                                                  self.k, self.capacity, int(self.want_segid), self.depth, C.byref(self._h)))
         self._last_slot = -1
+        # the stream the batches are queued on: the one current at construction (or `stream`); looked up once, not per batch
+        self._st = (stream if stream is not None else torch.cuda.current_stream(dev)).cuda_stream
         self._views: dict = {}
         self._outv = [C.c_void_p() for _ in range(4)]
         self._out = tuple(C.byref(x) for x in self._outv)
@@ -215,8 +218,7 @@ class JoinStream:
                 raise TypeError(f"this JoinStream joins batches of {self.B} queries")
         out, indptr, segid, nrows = self._out
         dev = self.spg.device
-        rc = self._submit(self._h, eptr, int(on_dev), torch.cuda.current_stream(dev).cuda_stream, out, indptr, segid, nrows,
-                          self._slot_ref)
+        rc = self._submit(self._h, eptr, int(on_dev), self._st, out, indptr, segid, nrows, self._slot_ref)
         if rc:
             _capi.check(rc)
         q = self._slot.value

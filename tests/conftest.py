@@ -14,13 +14,33 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "reference: needs the reference tree at /root/reference (this container only)")
 
 
+def _gpu_ready() -> str:
+    """'' when the gpu-marked tests can run here, else the reason they are skipped."""
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            return "no CUDA device"
+    except Exception as ex:  # pragma: no cover
+        return f"torch unavailable: {ex!r}"
+    from surel_plus_b200 import _capi
+    if not os.path.exists(_capi.LIB_PATH):
+        return f"{_capi.LIB_PATH} not built (python -m surel_plus_b200.build)"
+    return ""
+
+
 def pytest_collection_modifyitems(config, items):
     from oracle import reference as ref
     have_tree = ref.have_reference_tree()
     skip_ref = pytest.mark.skip(reason="reference tree not present (GPU box)")
+    why = None
     for item in items:
         if "reference" in item.keywords and not have_tree:
             item.add_marker(skip_ref)
+        if "gpu" in item.keywords:
+            if why is None:
+                why = _gpu_ready()
+            if why:  # a plain `pytest tests` on a CPU host skips the GPU suite instead of failing it
+                item.add_marker(pytest.mark.skip(reason=why))
 
 
 @pytest.fixture(scope="session")

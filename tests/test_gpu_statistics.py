@@ -145,3 +145,147 @@ def test_philox_path_matches_reference_sampling_law(small_graph):
     pooled = np.concatenate([tab[:, common], tab[:, ~common].sum(1, keepdims=True)], axis=1)
     stat, p, dof, _ = chi2_contingency(pooled)
     assert p > ALPHA, f"LP-row histogram differs: chi2={stat:.1f} dof={dof} p={p:.2e}"
+
+
+def test_philox_lean_kernel_statistics_on_collab_shape():
+    """The same statement at the size SURVEY.md 8c gives it: the ogbl-collab-shape graph (235 868 nodes), M = 200 walks of
+    m = 2 steps (the reference's collab setting), >= 2 000 seeds stratified by degree (0, 1, 2..M, > M), R = 32 runs of
+    ours (Philox, the LEAN kernel bench.py times: no ranks) against R = 32 runs of the reference's rand_r stream.
+      (i)   exact per run: root column, column sums, the first-hop law (round robin for deg <= M, M distinct
+            neighbours for deg > M);
+      (ii)  chi-square goodness of fit of the step-2 landing counts against R M (p1 P), per seed, for ours and for the
+            reference stream (Bonferroni over the seeds);
+      (iii) KS on the set sizes per stratum and chi-square homogeneity of the LP-row histograms, ours vs reference."""
+    import scipy.sparse as sp
+    from scipy.stats import chi2, chi2_contingency, ks_2samp
+    from surel_plus_b200 import DeviceGraph, SpG, _capi
+    from surel_plus_b200.graphs import named_graph
+    Mw, mw, Rr = 200, 2, 32
+    A = named_graph("collab")
+    N = A.shape[0]
+    deg = np.diff(A.indptr)
+    rng = np.random.default_rng(11)
+    strata = {"deg0": np.flatnonzero(deg == 0), "deg1": np.flatnonzero(deg == 1),
+              "deg2..M": np.flatnonzero((deg >= 2) & (deg <= Mw)), "deg>M": np.flatnonzero(deg > Mw)}
+    quota = {"deg0": 100, "deg1": 300, "deg2..M": 1800, "deg>M": 400}   # the graph has 24 / 236 / 235 564 / 44 nodes in the strata
+    q = np.concatenate([rng.choice(v, min(len(v), quota[k]), replace=False) for k, v in strata.items()]).astype(np.int32)
+    q = q[rng.permutation(len(q))]
+    n = len(q)
+    assert n >= 2000 and all(len(v) > 0 for v in strata.values())
+    dq = deg[q]
+
+    g = DeviceGraph.from_scipy(A, "cuda:0")
+
+    def ours_run(seed):
+        spg = SpG.sample(g, q, Mw, mw, seed=int(seed), rng_mode=_capi.SUBG_RNG_PHILOX, first_visit_ranks=False)
+        v = spg.views()
+        ip, ind = v["indptr"].cpu().numpy(), v["indices"].cpu().numpy()
+        raw = v["enc"].cpu().numpy()[v["data"].cpu().numpy() - 1]
+        spg.close()
+        return np.diff(ip).astype(np.int32), ind, raw
+
+    def ref_run(seed):
+        nsize, remap, enc, raw = po.gset_sampler_replay(A.indptr, A.indices, q, Mw, mw, -1, int(seed), debug=1)
+        return nsize, remap[0], raw
+
+    ours = [ours_run(s) for s in 5000 + np.arange(Rr)]
+    refs = [ref_run(s) for s in np.random.default_rng(1).integers(1, 2 ** 31 - 1, Rr)]
+
+    # (i) exact invariants of every run
+    first = sp.csr_matrix((np.ones(0), (np.zeros(0, int), np.zeros(0, int))), shape=(n, N))
+    for nsize, nodes, raw in ours + refs:
+        seg = np.repeat(np.arange(n), nsize)
+        root = raw[:, 0] == Mw
+        assert root.sum() == n and np.array_equal(nodes[root][np.argsort(seg[root])][dq > 0], q[dq > 0])
+        for j in (1, 2):
+            assert np.array_equal(np.bincount(seg, weights=raw[:, j], minlength=n), np.full(n, Mw))
+    for nsize, nodes, raw in ours[:4] + refs[:4]:
+        seg = np.repeat(np.arange(n), nsize)
+        c1 = sp.csr_matrix((raw[:, 1].astype(np.float64), (seg, nodes)), shape=(n, N))
+        for i in rng.choice(n, 300, replace=False):
+            d = dq[i]
+            row = c1.getrow(i)
+            if d == 0:
+                continue
+            nb = A.indices[A.indptr[q[i]]:A.indptr[q[i] + 1]]
+            got = np.asarray(row[:, nb].todense()).ravel()
+            if d <= Mw:
+                assert np.array_equal(got, np.bincount(np.arange(Mw) % d, minlength=d))       # subg_acc.c:793-796
+            else:
+                assert got.sum() == Mw and got.max() == 1                                      # subg_acc.c:763-776
+
+    # (ii) goodness of fit of step 2 against R M (p1 P)
+    live = deg > 0
+    inv = np.zeros(N)
+    inv[live] = 1.0 / deg[live]
+    P = sp.diags(inv) @ A.astype(np.float64) + sp.diags((~live).astype(np.float64))
+    rows, cols, vals = [], [], []
+    for i in range(n):
+        d, u = dq[i], q[i]
+        if d == 0:
+            rows.append([i]); cols.append([u]); vals.append([1.0])
+            continue
+        nb = A.indices[A.indptr[u]:A.indptr[u + 1]]
+        w = np.bincount(np.arange(Mw) % d, minlength=d) / Mw if d <= Mw else np.full(d, 1.0 / d)
+        rows.append(np.full(d, i)); cols.append(nb); vals.append(w)
+    p1 = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, N))
+    expd = (p1 @ P).tocsr() * (Rr * Mw)
+
+    def gof(runs):
+        obs = sp.csr_matrix((n, N))
+        for nsize, nodes, raw in runs:
+            seg = np.repeat(np.arange(n), nsize)
+            obs = obs + sp.csr_matrix((raw[:, 2].astype(np.float64), (seg, nodes)), shape=(n, N))
+        pv = []
+        for i in range(n):
+            if dq[i] == 0:
+                continue
+            e_row, o_row = expd.getrow(i), obs.getrow(i)
+            assert abs(o_row.sum() - Rr * Mw) < 1e-6
+            e = np.asarray(e_row.todense()).ravel()
+            o = np.asarray(o_row.todense()).ravel()
+            nz = np.flatnonzero((e > 0) | (o > 0))
+            e, o = e[nz], o[nz]
+            assert not o[e == 0].any(), "landing on an unreachable node"
+            big = e >= 5
+            ce = list(e[big]) + ([e[~big].sum()] if e[~big].sum() > 0 else [])
+            co = list(o[big]) + ([o[~big].sum()] if e[~big].sum() > 0 else [])
+            if len(ce) < 2:
+                continue
+            ce, co = np.array(ce), np.array(co)
+            pv.append(chi2.sf(float(((co - ce) ** 2 / ce).sum()), len(ce) - 1))
+        return np.array(pv)
+
+    for name, runs in (("ours", ours), ("reference stream", refs)):
+        p = gof(runs)
+        assert len(p) > 1500
+        assert p.min() > ALPHA / len(p), f"{name}: chi-square GOF rejected (min p {p.min():.2e} over {len(p)} seeds)"
+        assert (p < 0.05).mean() < 0.07, f"{name}: {(p < 0.05).mean():.3f} of the per-seed GOF tests below 0.05"
+
+    # (iii-a) set sizes per stratum
+    for name, idx in strata.items():
+        mask = np.isin(q, idx)
+        a = np.concatenate([r[0][mask] for r in ours])
+        b = np.concatenate([r[0][mask] for r in refs])
+        if name == "deg0":
+            assert (a == 1).all() and (b == 1).all()
+            continue
+        pval = ks_2samp(a, b).pvalue
+        assert pval > ALPHA / len(strata), f"set-size KS rejected in stratum {name}: p={pval:.2e}"
+
+    # (iii-b) LP-row histograms
+    def hist(runs):
+        h = {}
+        for _, _, raw in runs:
+            keys, cts = np.unique(raw, axis=0, return_counts=True)
+            for k, v in zip(map(tuple, keys.tolist()), cts.tolist()):
+                h[k] = h.get(k, 0) + v
+        return h
+    ha, hb = hist(ours), hist(refs)
+    keys = sorted(set(ha) | set(hb))
+    tab = np.array([[ha.get(k, 0) for k in keys], [hb.get(k, 0) for k in keys]], np.float64)
+    common = tab.sum(0) >= 40
+    pooled = np.concatenate([tab[:, common], tab[:, ~common].sum(1, keepdims=True)], axis=1)
+    stat, pval, dof, _ = chi2_contingency(pooled)
+    assert pval > ALPHA, f"LP-row histogram differs: chi2={stat:.1f} dof={dof} p={pval:.2e}"
+    g.close()
