@@ -493,6 +493,9 @@ def bench_sharded(c):
         _capi.timing_enable(False)
         x_ms = c.max_over_ranks(float(np.mean([a.elapsed_time(b) for a, b in x_ev])))
         pull_ms = c.max_over_ranks(p_ms / max(p_n, 1))
+        if os.environ.get("BENCH_PER_RANK"):
+            log(f"[bench] rank {c.rank} mode {mode}: pull {p_ms / max(p_n, 1):.2f} ms, sampler kernel {k_ms / max(k_n, 1):.2f} ms, "
+                f"exchange {float(np.mean([a.elapsed_time(b) for a, b in x_ev])):.2f} ms")
         recv = float(spg.exchange_received)
         info = {"mode": spg.exchange_mode, "ms_per_pass": ms / steps, "seeds_per_s": c.n / (ms / steps / 1e3),
                 "sampler_kernel_ms": c.max_over_ranks(k_ms / max(k_n, 1)),
@@ -511,6 +514,9 @@ def bench_sharded(c):
     # ---- the sharded result must BE the single-GPU SpG (indices are global; LP ids in global first-occurrence order)
     parity_err = None
     try:
+        torch.cuda.synchronize()
+        _capi.trim_cache()           # the check holds a second full SpG: give the cached blocks back first
+        torch.cuda.empty_cache()
         ref = SpG.sample(c.graph, c.q_dev, num_walks=M, num_steps=m, seed=111413 + c.args.steps - 1, rng_mode=_capi.SUBG_RNG_PHILOX,
                          first_visit_ranks=False)
         same = (ref.n, ref.T, ref.c, ref.max_set) == (spg.n, spg.T, spg.c, spg.max_set) and np.array_equal(ref.enc_table(), spg.enc_table())

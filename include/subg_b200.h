@@ -349,6 +349,11 @@ int subg_timing_enable(int enable);
 int subg_timing_read(int which, double *ms, int64_t *launches);
 int64_t subg_launch_count(void);
 
+/* The library keeps freed device blocks of 64 MB and more (SpG row arrays, sampler staging) in a per-process cache and
+ * hands them out again (SUBG_BLOCK_CACHE_BYTES caps it, default 45 % of the device memory).  subg_trim_cache returns
+ * every cached block to the driver and reports the bytes released. */
+int64_t subg_trim_cache(void);
+
 /* pinned host memory helpers (so numpy arrays handed back by the Python shim can be
  * filled with asynchronous copies) */
 int subg_host_alloc(void **ptr, int64_t bytes);

@@ -30,7 +30,7 @@ SYMBOLS = [
     "subg_ppr_topk", "subg_spg_encode", "subg_spg_pushes",
     "subg_walk_sample", "subg_walkset_info", "subg_walkset_export", "subg_walkset_views", "subg_walkset_free", "subg_walk_join",
     "subg_timing_enable", "subg_timing_read", "subg_launch_count",
-    "subg_host_alloc", "subg_host_free",
+    "subg_trim_cache", "subg_host_alloc", "subg_host_free",
 ]
 
 _lib = None
@@ -106,12 +106,14 @@ def load() -> C.CDLL:
     L.subg_timing_read.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(i64)]
     L.subg_launch_count.restype = i64
     L.subg_launch_count.argtypes = []
+    L.subg_trim_cache.restype = i64
+    L.subg_trim_cache.argtypes = []
     L.subg_host_alloc.argtypes = [C.POINTER(vp), i64]
     L.subg_host_free.argtypes = [vp]
     L.subg_host_free.restype = None
     for name in SYMBOLS:
         fn = getattr(L, name)
-        if fn.restype is C.c_int and name not in ("subg_abi_version",):
+        if fn.restype is C.c_int and name not in ("subg_abi_version", "subg_trim_cache"):
             fn.restype = C.c_int
     _lib = L
     return L
@@ -126,6 +128,11 @@ def timing_read(which: int):
     ms, cnt = C.c_double(0), C.c_int64(0)
     load().subg_timing_read(which, C.byref(ms), C.byref(cnt))
     return ms.value, cnt.value
+
+
+def trim_cache() -> int:
+    """Release the library's cache of large device blocks (subg_trim_cache); returns the bytes released."""
+    return int(load().subg_trim_cache())
 
 
 def launch_count() -> int:

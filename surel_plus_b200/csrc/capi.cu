@@ -149,6 +149,17 @@ bool big_free(void *p, cudaStream_t st) {
     return true;
 }
 
+// give every cached large block back to the driver (all devices); returns the bytes released
+long long big_trim() {
+    std::lock_guard<std::mutex> lk(g_big_mutex);
+    long long freed = 0;
+    while (!g_big_free.empty()) {
+        freed += (long long)g_big_free[0].bytes;
+        big_release_locked(0);
+    }
+    return freed;
+}
+
 bool is_device_ptr(const void *p) {
     if (!p) return false;
     cudaPointerAttributes at;
@@ -582,6 +593,8 @@ int subg_walk_join(const int32_t *walks_hd, int64_t n, int64_t stride, const int
     if (int rc = init_device(device)) return rc;
     return walk_join_impl(walks_hd, n, stride, key_off_hd, key_ids_hd, query_hd, Q, out_hd, xq_hd, device, (cudaStream_t)stream);
 }
+
+int64_t subg_trim_cache(void) { return (int64_t)big_trim(); }
 
 int subg_host_alloc(void **ptr, int64_t bytes) {
     if (!ptr || bytes < 0) return fail(SUBG_ERR_ARG, "bad host allocation request");

@@ -268,6 +268,290 @@ __global__ void __launch_bounds__(kPprWarps * 32) ppr_push_kernel(const PprArgs 
     if (lane == 0 && pushes) atomicAdd(a.counter + 1, pushes);
 }
 
+
+// ------------------------------------------------------------------ forward push, fast path
+// Same algorithm and the same floating-point operations in the same order as ppr_push_kernel (pprgo.py:9-38), with the
+// per-seed state split by how it is accessed ("the common small supports would fit in shared memory"):
+//   shared memory (per warp)  the LIFO queue (index + node id, so a pop needs no dependent global load before the
+//                             row pointer is fetched) and the p-list: (node, p) of the nodes popped so far, in
+//                             insertion order -- a few hundred entries; the top-k selection then scans THIS list instead
+//                             of every touched record (3 000 records vs 160 popped nodes on the citation2 shape);
+//   global memory (L2-warm)   one record per touched node: node id, residual r, flags (p-list index, in-queue bit), and
+//                             the open-addressing hash node -> record whose entries carry a 16-bit epoch: a new seed
+//                             bumps the epoch instead of clearing 3 000 scattered slots.
+// Seeds that outgrow the queue, the p-list or the record array are flagged and redone by the general kernel.
+constexpr int kFastQ = 512;    // queue entries per warp
+constexpr int kFastP = 384;    // popped nodes per warp
+
+struct PprFastArgs {
+    const void *rowptr;
+    int rowptr64;
+    const int32_t *col;
+    const int32_t *seeds;
+    int64_t nwork;
+    float alpha, alpha_eps;
+    double one_minus_alpha;
+    int topk;
+    int R;           // records per warp (<= 65535)
+    uint32_t hmask;
+    unsigned long long *htab;   // [warp][hmask + 1]: node << 32 | epoch << 16 | record index
+    int32_t *node;
+    float *r;
+    uint32_t *flag;             // low 16 bits: p-list index + 1 (0 = never popped); bit 31: in the queue
+    uint32_t *epoch;            // [warp]: current epoch (persists across launches)
+    unsigned long long *counter;  // [0] next work item, [1] pushes, [2] failed seeds
+    uint8_t *fail;
+    int32_t *st_node;
+    float *st_val;
+    int32_t *cnt;
+};
+
+__global__ void __launch_bounds__(kPprWarps * 32) ppr_push_fast_kernel(const PprFastArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    const int per_warp = 8 * kFastQ + 8 * kFastP + 1024 + 8 * a.topk;
+    unsigned char *wsm = smem_raw + (size_t)wib * per_warp;
+    int32_t *q_idx = (int32_t *)wsm;
+    int32_t *q_node = q_idx + kFastQ;
+    int32_t *p_node = q_node + kFastQ;
+    float *p_val = (float *)(p_node + kFastP);
+    uint32_t *hist = (uint32_t *)(p_val + kFastP);
+    int32_t *sel_node = (int32_t *)(hist + 256);
+    float *sel_val = (float *)(sel_node + a.topk);
+
+    const int64_t gw = (int64_t)blockIdx.x * kPprWarps + wib;
+    unsigned long long *htab = a.htab + gw * ((int64_t)a.hmask + 1);
+    int32_t *node = a.node + gw * a.R;
+    float *r = a.r + gw * a.R;
+    uint32_t *flag = a.flag + gw * a.R;
+    uint32_t epoch = a.epoch[gw];
+    unsigned long long pushes = 0;
+
+    for (;;) {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(a.counter, 1ull);
+        t = __shfl_sync(FULL, t, 0);
+        if ((int64_t)t >= a.nwork) break;
+        const int64_t i = (int64_t)t;
+        const int32_t s = __ldg(a.seeds + i);
+        // a new epoch invalidates every entry of the previous seed; on wrap-around the table is really cleared
+        epoch++;
+        if (epoch >= 0xffffu) {
+            for (uint32_t h = lane; h <= a.hmask; h += 32) htab[h] = 0ull;
+            epoch = 1;
+            __syncwarp();
+        }
+        const unsigned long long etag = (unsigned long long)epoch << 16;
+
+        // p = {s: 0}; r = {s: alpha}; q = [s]                          pprgo.py:12-16
+        int nrec = 1, np = 0, qlen = 1;
+        if (lane == 0) {
+            htab[hash_node((uint32_t)s, a.hmask)] = ((unsigned long long)(uint32_t)s << 32) | etag | 0ull;
+            node[0] = s; r[0] = a.alpha; flag[0] = 0x80000000u;
+            q_idx[0] = 0; q_node[0] = s;
+        }
+        __syncwarp();
+        bool overflow = false;
+        unsigned long long seed_pushes = 0;
+        while (qlen > 0) {
+            qlen--;
+            const int ui = q_idx[qlen];      // q.pop()                  pprgo.py:18
+            const int32_t u = q_node[qlen];
+            const float res = __ldcg(r + ui);
+            const uint32_t fl = __ldcg(flag + ui);
+            const int64_t rp0 = ld_rowptr(a.rowptr, a.rowptr64, u);
+            const int64_t d = ld_rowptr(a.rowptr, a.rowptr64, (int64_t)u + 1) - rp0;
+            int pi = (int)(fl & 0xffffu);    // p-list index + 1
+            if (pi == 0) {                   // first pop of u: p[u] = res      pprgo.py:21-24
+                if (np >= kFastP) { overflow = true; break; }
+                pi = ++np;
+                if (lane == 0) { p_node[pi - 1] = u; p_val[pi - 1] = res; }
+            } else if (lane == 0) {
+                p_val[pi - 1] += res;
+            }
+            if (lane == 0) {
+                flag[ui] = (uint32_t)pi;     // out of the queue
+                r[ui] = 0.f;                 // pprgo.py:25
+            }
+            // (1 - alpha) * res / deg[u]: float64 arithmetic rounded to float32 (pprgo.py:8,27)
+            const float val = (float)(a.one_minus_alpha * (double)res / (double)d);
+            __syncwarp();
+            for (int64_t j0 = 0; j0 < d; j0 += 32) {
+                const int64_t j = j0 + lane;
+                const bool act = j < d;
+                int32_t v = -1;
+                int idx = -1;
+                uint32_t h = 0;
+                unsigned long long seen = 0ull;
+                int64_t dv = 0;
+                if (act) {
+                    v = __ldg(a.col + rp0 + j);
+                    h = hash_node((uint32_t)v, a.hmask);
+                    dv = ld_rowptr(a.rowptr, a.rowptr64, (int64_t)v + 1) - ld_rowptr(a.rowptr, a.rowptr64, v);
+                }
+                // lookup: probe until the node or a free (stale / never used) slot; the loop ends on a warp vote
+                bool look = act;
+                while (__any_sync(FULL, look)) {
+                    if (look) {
+                        seen = __ldcg(htab + h);
+                        if ((seen & 0xffff0000ull) != etag) look = false;                       // free slot: v is new
+                        else if ((int32_t)(uint32_t)(seen >> 32) == v) { idx = (int)(seen & 0xffffu); look = false; }
+                        else h = (h + 1) & a.hmask;
+                    }
+                }
+                const bool isnew = act && idx < 0;
+                const uint32_t newm = __ballot_sync(FULL, isnew);
+                const int nnew = __popc(newm);
+                if (nrec + nnew > a.R) { overflow = true; break; }
+                float rv = 0.f;
+                uint32_t vflag = 0u;
+                if (isnew) {
+                    idx = nrec + __popc(newm & lt);
+                } else if (act) {
+                    rv = __ldcg(r + idx);
+                    vflag = __ldcg(flag + idx);
+                }
+                // insert the new nodes (distinct columns: no two lanes insert the same node, but they may want the same slot)
+                {
+                    const unsigned long long ent = ((unsigned long long)(uint32_t)v << 32) | etag | (unsigned long long)(uint32_t)idx;
+                    bool ins = isnew;
+                    while (__any_sync(FULL, ins)) {
+                        if (ins) {
+                            if ((seen & 0xffff0000ull) == etag) {       // taken by another lane meanwhile: next slot
+                                h = (h + 1) & a.hmask;
+                                seen = __ldcg(htab + h);
+                            } else {
+                                const unsigned long long old = atomicCAS(htab + h, seen, ent);
+                                if (old == seen) ins = false;
+                                else seen = old;
+                            }
+                        }
+                    }
+                }
+                nrec += nnew;
+                rv = isnew ? val : rv + val;                             // pprgo.py:28-31
+                bool push = false;
+                if (act) {
+                    // res_vnode >= alpha_eps * deg[vnode] (float32 product widened, pprgo.py:33-34); vnode not in q
+                    push = ((double)rv >= (double)a.alpha_eps * (double)dv) && (isnew || (vflag & 0x80000000u) == 0u);
+                }
+                const uint32_t pm = __ballot_sync(FULL, push);
+                if (qlen + __popc(pm) > kFastQ) { overflow = true; break; }
+                if (act) {
+                    r[idx] = rv;
+                    if (isnew) node[idx] = v;
+                    if (push) {                                          // pprgo.py:35-36, CSR order
+                        const int at = qlen + __popc(pm & lt);
+                        q_idx[at] = idx;
+                        q_node[at] = v;
+                    }
+                    if (push || isnew) flag[idx] = (isnew ? 0u : (vflag & 0xffffu)) | (push ? 0x80000000u : 0u);
+                }
+                qlen += __popc(pm);
+                __syncwarp();
+            }
+            if (overflow) break;
+            seed_pushes++;
+        }
+
+        if (overflow) {
+            if (lane == 0) {
+                a.fail[i] = 1;
+                a.cnt[i] = 0;
+                atomicAdd(a.counter + 2, 1ull);
+            }
+            __syncwarp();
+            continue;
+        }
+        pushes += seed_pushes;
+        __syncwarp();
+        // ---- top-k of the p-list by (score, insertion rank): argsort(val)[-topk:], ties at the k-th score towards
+        // later insertion (pprgo.py:59) -- the same radix selection as ppr_push_kernel, over shared memory
+        unsigned long long thr = 0ull;
+        if (np > a.topk) {
+            unsigned long long prefix = 0ull;
+            int want = a.topk;
+            for (int pass = 7; pass >= 0; pass--) {
+                for (int b = lane; b < 256; b += 32) hist[b] = 0u;
+                __syncwarp();
+                for (int t0 = lane; t0 < np; t0 += 32) {
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(p_val[t0]) << 32) | (uint32_t)t0;
+                    if (pass == 7 || (key >> (8 * (pass + 1))) == prefix) atomicAdd(&hist[(key >> (8 * pass)) & 255u], 1u);
+                }
+                __syncwarp();
+                uint32_t mine = 0;
+#pragma unroll
+                for (int b = 0; b < 8; b++) mine += hist[lane * 8 + b];
+                uint32_t incl = mine;
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) {
+                    const uint32_t o = __shfl_down_sync(FULL, incl, dd);
+                    if (lane + dd < 32) incl += o;
+                }
+                const uint32_t above = incl - mine;
+                const bool here = above < (uint32_t)want && incl >= (uint32_t)want;
+                const int owner = __ffs(__ballot_sync(FULL, here)) - 1;
+                int digit = 0, rem = 0, binc = 0;
+                if (lane == owner) {
+                    uint32_t acc = above;
+                    for (int b = 7; b >= 0; b--) {
+                        const uint32_t c = hist[lane * 8 + b];
+                        if (acc + c >= (uint32_t)want) { digit = lane * 8 + b; rem = want - (int)acc; binc = (int)c; break; }
+                        acc += c;
+                    }
+                }
+                digit = __shfl_sync(FULL, digit, owner);
+                rem = __shfl_sync(FULL, rem, owner);
+                binc = __shfl_sync(FULL, binc, owner);
+                prefix = (prefix << 8) | (unsigned long long)digit;
+                want = rem;
+                __syncwarp();
+                if (binc == want) {
+                    thr = prefix << (8 * pass);
+                    break;
+                }
+                thr = prefix;
+            }
+        }
+        int nsel = 0;
+        for (int t0 = 0; t0 < np; t0 += 32) {
+            const int t = t0 + lane;
+            bool keep = false;
+            float pv = 0.f;
+            if (t < np) {
+                pv = p_val[t];
+                keep = (((unsigned long long)__float_as_uint(pv) << 32) | (uint32_t)t) >= thr;
+            }
+            const uint32_t km = __ballot_sync(FULL, keep);
+            if (keep) {
+                const int o = nsel + __popc(km & lt);
+                sel_node[o] = p_node[t];
+                sel_val[o] = pv;
+            }
+            nsel += __popc(km);
+        }
+        __syncwarp();
+        const int64_t row = i * (int64_t)a.topk;
+        for (int t = lane; t < nsel; t += 32) {
+            const int32_t me = sel_node[t];
+            int rank = 0;
+            for (int o = 0; o < nsel; o++) rank += sel_node[o] < me;
+            a.st_node[row + rank] = me;
+            a.st_val[row + rank] = sel_val[t];
+        }
+        if (lane == 0) {
+            a.cnt[i] = nsel;
+            a.fail[i] = 0;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        a.epoch[gw] = epoch;
+        if (pushes) atomicAdd(a.counter + 1, pushes);
+    }
+}
+
 // ------------------------------------------------------------------ CSR assembly + normalisation
 // pprgo.py:87-106: 'sym' sqrt(max(deg_u,1e-12)) * p * (1/sqrt(max(deg_w,1e-12))), 'col' deg_u * p * (1/max(deg_w,1e-12)),
 // evaluated left to right in float64; 'row' keeps p.  deg = adj.sum(1) (caller-supplied, else the row length).
@@ -656,39 +940,70 @@ int ppr_topk_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, float alph
         CKG(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ppr_push_kernel, kPprWarps * 32, smem));
         per_sm = std::max(per_sm, 1);
 
-        // pass 0: all seeds, small workspaces; pass 1: the seeds that overflowed, workspaces sized by the
-        // push bound  #records <= 1 + deg(seed) + sum_pushes deg(u) <= ~ 1/(alpha*eps) + max_deg  (capped by N)
+        // pass 0 (fast kernel): all seeds, queue and p-list in shared memory, records capped; pass 1 (general kernel): the
+        // seeds that outgrew one of those; pass 2: what is left, with workspaces sized by the push bound
+        //   #records <= 1 + deg(seed) + sum_pushes deg(u) <= ~ 1/(alpha*eps) + max_deg  (capped by N)
         int64_t nwork = n;
-        for (int pass = 0; pass < 2 && nwork > 0; pass++) {
+        const bool use_fast = env_i64("SUBG_PPR_FAST", 1) != 0;
+        for (int pass = use_fast ? 0 : 1; pass < 3 && nwork > 0; pass++) {
+            const bool fast = pass == 0;
             int64_t R;
-            if (pass == 0) R = std::min<int64_t>(env_i64("SUBG_PPR_RECORDS", 8192), g->N + 1);
+            if (pass < 2) R = std::min<int64_t>(env_i64("SUBG_PPR_RECORDS", 8192), g->N + 1);
             else R = g->N + 1;  // a record per node can never overflow
             R = std::max<int64_t>(R, 64);
+            if (fast) R = std::min<int64_t>(R, 65535);
             uint32_t H = 64;
             while ((int64_t)H < 2 * R) H <<= 1;
-            int64_t blocks = (int64_t)g->num_sms * per_sm;
+            int smem_k = smem, per_sm_k = per_sm;
+            if (fast) {
+                smem_k = kPprWarps * (8 * kFastQ + 8 * kFastP + 1024 + 8 * topk);
+                if (smem_k > 220 * 1024) continue;   // top-k buffers too large: general kernel only
+                CKG(cudaFuncSetAttribute(ppr_push_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_k));
+                CKG(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_k, ppr_push_fast_kernel, kPprWarps * 32, smem_k));
+                per_sm_k = std::max(per_sm_k, 1);
+                const int64_t capb = env_i64("SUBG_PPR_BLOCKS", 0);
+                if (capb > 0) per_sm_k = (int)std::min<int64_t>(per_sm_k, capb);
+            }
+            int64_t blocks = (int64_t)g->num_sms * per_sm_k;
             blocks = std::min<int64_t>(blocks, (nwork + kPprWarps - 1) / kPprWarps);
-            const int64_t bytes_per_warp = (int64_t)H * 8 + R * 25;
+            const int64_t bytes_per_warp = (int64_t)H * 8 + R * (fast ? 12 : 25);
             const int64_t budget = env_i64("SUBG_PPR_WORKSPACE_BYTES", 24ll << 30);
             blocks = std::max<int64_t>(1, std::min<int64_t>(blocks, budget / (bytes_per_warp * kPprWarps)));
             const int64_t nw = blocks * kPprWarps;
             CKG(dmalloc(&ws.htab, (size_t)nw * H, st));
-            CKG(dmalloc(&ws.node, (size_t)nw * R, st)); CKG(dmalloc(&ws.pord, (size_t)nw * R, st));
-            CKG(dmalloc(&ws.hslot, (size_t)nw * R, st)); CKG(dmalloc(&ws.q, (size_t)nw * R, st));
-            CKG(dmalloc(&ws.r, (size_t)nw * R, st)); CKG(dmalloc(&ws.p, (size_t)nw * R, st));
-            CKG(dmalloc(&ws.inq, (size_t)nw * R, st));
+            CKG(dmalloc(&ws.node, (size_t)nw * R, st));
+            CKG(dmalloc(&ws.r, (size_t)nw * R, st));
+            CKG(dmalloc(&ws.pord, (size_t)(fast ? nw * R : nw * R), st));   // fast: the flag words
+            if (!fast) {
+                CKG(dmalloc(&ws.hslot, (size_t)nw * R, st)); CKG(dmalloc(&ws.q, (size_t)nw * R, st));
+                CKG(dmalloc(&ws.p, (size_t)nw * R, st));
+                CKG(dmalloc(&ws.inq, (size_t)nw * R, st));
+            } else {
+                CKG(dmalloc(&ws.q, (size_t)nw, st));                        // fast: the per-warp epochs
+                CKG(cudaMemsetAsync(ws.q, 0, (size_t)nw * 4, st));
+            }
             fill_empty_kernel<<<8 * g->num_sms, 256, 0, st>>>(ws.htab, nw * (int64_t)H);
             CKG(cudaMemsetAsync(counter, 0, 4 * sizeof(unsigned long long), st));
-            PprArgs a{};
-            a.rowptr = g->rowptr; a.rowptr64 = g->rowptr64 ? 1 : 0; a.col = g->col; a.seeds = s->seeds;
-            a.work = pass == 0 ? nullptr : work; a.nwork = nwork;
-            a.alpha = alpha; a.alpha_eps = alpha_eps; a.one_minus_alpha = 1.0 - (double)alpha;
-            a.topk = topk; a.R = (int)R; a.hmask = H - 1;
-            a.htab = ws.htab; a.node = ws.node; a.pord = ws.pord; a.hslot = ws.hslot; a.q = ws.q;
-            a.r = ws.r; a.p = ws.p; a.inq = ws.inq; a.counter = counter; a.fail = fail_d;
-            a.st_node = st_node; a.st_val = st_val; a.cnt = cnt;
             timing_begin(SUBG_TIMING_PPR, st);
-            ppr_push_kernel<<<(unsigned)blocks, kPprWarps * 32, smem, st>>>(a);
+            if (fast) {
+                PprFastArgs a{};
+                a.rowptr = g->rowptr; a.rowptr64 = g->rowptr64 ? 1 : 0; a.col = g->col; a.seeds = s->seeds; a.nwork = nwork;
+                a.alpha = alpha; a.alpha_eps = alpha_eps; a.one_minus_alpha = 1.0 - (double)alpha;
+                a.topk = topk; a.R = (int)R; a.hmask = H - 1;
+                a.htab = ws.htab; a.node = ws.node; a.r = ws.r; a.flag = (uint32_t *)ws.pord; a.epoch = (uint32_t *)ws.q;
+                a.counter = counter; a.fail = fail_d; a.st_node = st_node; a.st_val = st_val; a.cnt = cnt;
+                ppr_push_fast_kernel<<<(unsigned)blocks, kPprWarps * 32, smem_k, st>>>(a);
+            } else {
+                PprArgs a{};
+                a.rowptr = g->rowptr; a.rowptr64 = g->rowptr64 ? 1 : 0; a.col = g->col; a.seeds = s->seeds;
+                a.work = work; a.nwork = nwork;   // work == nullptr: every seed (no earlier pass ran)
+                a.alpha = alpha; a.alpha_eps = alpha_eps; a.one_minus_alpha = 1.0 - (double)alpha;
+                a.topk = topk; a.R = (int)R; a.hmask = H - 1;
+                a.htab = ws.htab; a.node = ws.node; a.pord = ws.pord; a.hslot = ws.hslot; a.q = ws.q;
+                a.r = ws.r; a.p = ws.p; a.inq = ws.inq; a.counter = counter; a.fail = fail_d;
+                a.st_node = st_node; a.st_val = st_val; a.cnt = cnt;
+                ppr_push_kernel<<<(unsigned)blocks, kPprWarps * 32, smem, st>>>(a);
+            }
             timing_end(SUBG_TIMING_PPR, st);
             CKG(cudaGetLastError());
             count_launch(2);
@@ -699,7 +1014,7 @@ int ppr_topk_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, float alph
             s->pushes += (int64_t)hc[1];
             const int64_t nfail = (int64_t)hc[2];
             if (nfail == 0) break;
-            if (pass == 1) { rc = fail(SUBG_ERR_MEM, "PPR push workspace overflow in the full-size pass"); goto done; }
+            if (pass == 2) { rc = fail(SUBG_ERR_MEM, "PPR push workspace overflow in the full-size pass"); goto done; }
             hfail.resize((size_t)n);
             CKG(cudaMemcpyAsync(hfail.data(), fail_d, (size_t)n, cudaMemcpyDeviceToHost, st));
             CKG(cudaStreamSynchronize(st));
@@ -707,9 +1022,11 @@ int ppr_topk_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, float alph
             for (int64_t i = 0; i < n; i++)
                 if (hfail[i]) hwork.push_back(i);
             nwork = (int64_t)hwork.size();
+            dfree(work, st);
+            work = nullptr;
             CKG(dmalloc(&work, (size_t)nwork, st));
             CKG(cudaMemcpyAsync(work, hwork.data(), (size_t)nwork * 8, cudaMemcpyHostToDevice, st));
-            s->status |= SUBG_STATUS_PPR_SECOND_PASS;
+            if (pass >= 1) s->status |= SUBG_STATUS_PPR_SECOND_PASS;
         }
 
         // ---- CSR assembly

@@ -167,14 +167,80 @@ __device__ __forceinline__ void lane_sort(K (&k)[EPL]) {
 }
 
 // Sorts the 32*EPL keys of a warp ascending.  In: lane L holds elements [L*EPL, (L+1)*EPL) of any
-// order.  Out: the same blocked layout, globally sorted.  buf: 32*EPL + 32 keys of shared memory owned by
+// order.  Out: the same blocked layout, globally sorted.  buf: 32*EPL + 64 keys of shared memory owned by
 // the warp.  Keys are distinct except for the padding (~0 - 1); ~0 itself never occurs in the data: it is the
 // sentinel that follows every run in shared memory, so the serial merge reads without bounds tests (an exhausted
 // run presents ~0, which loses against every key including the padding).
+#ifndef SUBG_MERGE_BIDIR
+#define SUBG_MERGE_BIDIR 1
+#endif
 template <typename K, int EPL>
 __device__ __forceinline__ void warp_merge_sort(K (&k)[EPL], K *buf, int lane) {
     constexpr K SENT = ~(K)0;
     lane_sort<K, EPL>(k);
+#if SUBG_MERGE_BIDIR
+    // Every lane merges its EPL outputs from both ends at once: the first half forwards from its own merge-path point,
+    // the second half backwards from the next lane's point (one shuffle) -- two independent chains of dependent
+    // shared-memory loads instead of one.  Run q occupies buf[q * (L + 2) + 1 ..] between a 0 slot (an exhausted run
+    // presents the minimum to the backward chain) and a ~0 slot (the maximum, for the forward chain).  The only key that
+    // can equal 0 is the root of node 0, which is output position 0 of the whole sort: forward territory.
+    constexpr int HF = (EPL + 1) / 2;
+#pragma unroll 1
+    for (int r = 0; r < 5; r++) {
+        const int L = EPL << r;
+        const int rl = lane & ((1 << r) - 1);    // lane index inside its run
+        const int own = lane * EPL + 2 * (lane >> r) + 1;
+#pragma unroll
+        for (int j = 0; j < EPL; j++) buf[own + j] = k[j];
+        if (rl == 0) buf[own - 1] = (K)0;
+        if (rl == (1 << r) - 1) buf[own + EPL] = SENT;
+        __syncwarp();
+        const int t = lane & ((2 << r) - 1);     // lane index inside the pair of runs
+        const int a0 = (lane - t) * EPL + 2 * ((lane - t) >> r) + 1;   // first key of run A; run B starts L + 2 later
+        const K *A = buf + a0;
+        const K *B = A + L + 2;
+        const int diag = t * EPL;
+        int lo = diag > L ? diag - L : 0;
+        int hi = diag < L ? diag : L;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (A[mid] <= B[diag - 1 - mid]) lo = mid + 1;
+            else hi = mid;
+        }
+        // the next lane's split is where this lane's outputs end; the last lane of the pair ends at (L, L)
+        int lo_n = __shfl_down_sync(FULL, lo, 1);
+        if (t == (2 << r) - 1) lo_n = L;
+        int pa = a0 + lo, pb = a0 + L + 2 + diag - lo;
+        int qa = a0 + lo_n - 1, qb = a0 + L + 2 + (diag + EPL - lo_n) - 1;
+        K ka = buf[pa], kb = buf[pb];
+        K la = buf[qa], lb = buf[qb];
+#pragma unroll
+        for (int j = 0; j < HF; j++) {
+            const bool ta = ka <= kb;
+            k[j] = ta ? ka : kb;
+            if (j + 1 < HF) {
+                pa += ta ? 1 : 0;
+                pb += ta ? 0 : 1;
+                const K v = buf[ta ? pa : pb];
+                ka = ta ? v : ka;
+                kb = ta ? kb : v;
+            }
+            const int jb = EPL - 1 - j;
+            if (jb >= HF) {
+                const bool tb = la > lb;         // the larger tail goes last; ties (padding only) take B
+                k[jb] = tb ? la : lb;
+                if (jb - 1 >= HF) {
+                    qa -= tb ? 1 : 0;
+                    qb -= tb ? 0 : 1;
+                    const K v = buf[tb ? qa : qb];
+                    la = tb ? v : la;
+                    lb = tb ? lb : v;
+                }
+            }
+        }
+        __syncwarp();
+    }
+#else
 #pragma unroll 1
     for (int r = 0; r < 5; r++) {
         const int L = EPL << r;                  // run length; run q occupies buf[q * (L + 1) ..] + one sentinel slot
@@ -213,6 +279,7 @@ __device__ __forceinline__ void warp_merge_sort(K (&k)[EPL], K *buf, int lane) {
         }
         __syncwarp();
     }
+#endif
 }
 
 template <typename T>
@@ -269,7 +336,7 @@ __device__ __forceinline__ uint32_t intern_key(const SamplerArgs &a, unsigned lo
 template <typename K, int EPL>
 constexpr int sampler_min_blocks() {
     constexpr int W = (int)sizeof(K) / 4;
-    constexpr int smem_warp = ((int)sizeof(K) + 4) * 32 * EPL + 32 * (int)sizeof(K) + 256;
+    constexpr int smem_warp = ((int)sizeof(K) + 4) * 32 * EPL + 64 * (int)sizeof(K) + 256;
     constexpr int by_smem = 232448 / (kWarpsPerBlock * smem_warp);
     constexpr int by_regs = 65536 / (kWarpsPerBlock * 32 * (EPL * W + 52));
     constexpr int b = by_smem < by_regs ? by_smem : by_regs;

@@ -318,7 +318,7 @@ static int make_plan(const Graph *g, int M, int m, int bucket, SamplePlan *p) {
     // region 2: member LP rows; Fisher-Yates permutation + hash values during the first hop
     p->lp64 = m * shift + 1 > 32;
     const int fy_half = 4 * M + 4 * fc;
-    p->lp_off = (std::max(ksz * (32 * p->EPL + 32), fy_half) + 15) & ~15;  // keys + one merge sentinel per run
+    p->lp_off = (std::max(ksz * (32 * p->EPL + 64), fy_half) + 15) & ~15;  // keys + two merge sentinels per run
     p->bitmap_off = (p->lp_off + std::max((p->lp64 ? 8 : 4) * (int)Kt, fy_half) + 15) & ~15;
     p->smem_per_warp = (p->bitmap_off + 8 * p->nbw + 15) & ~15;
     return SUBG_OK;

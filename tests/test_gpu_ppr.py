@@ -145,3 +145,32 @@ def test_ppr_errors(small_graph):
         encoding(x, A, "SPD")          # SPD needs idx = arange(N)
     with pytest.raises(NotImplementedError):
         encoding(x, A, "DEG")
+
+
+@pytest.mark.parametrize("alpha,eps,topk", [(0.1, 1e-4, 100), (0.15, 1e-6, 50), (0.05, 3e-6, 500)])
+def test_fast_push_kernel_equals_general_kernel(mid_graph, alpha, eps, topk, monkeypatch):
+    """ppr_push_fast_kernel (queue + p-list in shared memory, epoch-tagged hash) against ppr_push_kernel (all state in the
+    global workspace): same indices, same float32 scores bit for bit, same push count -- including seeds that outgrow the
+    shared-memory queue / p-list (eps = 1e-6: supports of thousands of nodes) and are redone by the general kernel, and a
+    record cap small enough that both kernels overflow and the full-size pass finishes the seeds."""
+    from surel_plus_b200 import DeviceGraph
+    from surel_plus_b200.pprgo import topk_ppr_matrix
+    A = mid_graph
+    n = A.shape[0]
+    idx = np.random.default_rng(5).permutation(n)[:3000].astype(np.int32)
+    g = DeviceGraph.from_scipy(A)
+    outs = {}
+    for fast, rec in ((0, 8192), (1, 8192), (1, 300)):
+        monkeypatch.setenv("SUBG_PPR_FAST", str(fast))
+        monkeypatch.setenv("SUBG_PPR_RECORDS", str(rec))
+        x = topk_ppr_matrix(g, alpha, eps, idx, topk, "row")
+        v = x.views()
+        outs[(fast, rec)] = (v["indptr"].cpu().numpy(), v["indices"].cpu().numpy(), v["data"].cpu().numpy(), x.pushes)
+        x.close()
+    ref = outs[(0, 8192)]
+    for key in ((1, 8192), (1, 300)):
+        got = outs[key]
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]), key
+        assert np.array_equal(got[2], ref[2]), key          # float64 holding the float32 scores: identical bits
+        assert got[3] == ref[3], key
+    g.close()
