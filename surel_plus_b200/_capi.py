@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libsubg_b200.so")
+#: SUBG_LIB: an experiment build of the same library (surel_plus_b200.build --tag); measurement only
+LIB_PATH = os.environ.get("SUBG_LIB") or os.path.join(_HERE, "_lib", "libsubg_b200.so")
 
 SUBG_RNG_PHILOX, SUBG_RNG_RAND_R, SUBG_RNG_TRACE = 0, 1, 2
 STATUS_BUCKET_OVERFLOW, STATUS_DEAD_END, STATUS_PPR_SECOND_PASS = 1, 2, 4

@@ -37,12 +37,16 @@ def _headers():
     return hs + [os.path.join(inc, n) for n in sorted(os.listdir(inc))]
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Incremental: an object is recompiled when its .cu, any header or the flags changed."""
+def build(force: bool = False, verbose: bool = False, tag: str = "", defs: tuple = ()) -> str:
+    """Incremental: an object is recompiled when its .cu, any header or the flags changed.
+    tag / defs: an experiment variant (libsubg_b200_<tag>.so compiled with -D<def> ...), picked up at run time through
+    SUBG_LIB=<path>; the product library is the untagged one."""
     os.makedirs(LIBDIR, exist_ok=True)
-    objdir = os.path.join(LIBDIR, "obj")
+    objdir = os.path.join(LIBDIR, "obj" + ("_" + tag if tag else ""))
     os.makedirs(objdir, exist_ok=True)
     headers = _headers()
+    FLAGS = list(globals()["FLAGS"]) + [f"-D{d}" for d in defs]
+    LIB = os.path.join(LIBDIR, f"libsubg_b200_{tag}.so") if tag else globals()["LIB"]
     flags = " ".join(FLAGS)
 
     def compile_one(src):
@@ -121,6 +125,8 @@ def sass_summary(out_path: str | None = None) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    tag = sys.argv[sys.argv.index("--tag") + 1] if "--tag" in sys.argv else ""
+    defs = tuple(a[2:] for a in sys.argv if a.startswith("-D"))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, tag=tag, defs=defs))
     if "--sass" in sys.argv:
         print(sass_summary())

@@ -271,19 +271,25 @@ __global__ void __launch_bounds__(kPprWarps * 32) ppr_push_kernel(const PprArgs 
 
 // ------------------------------------------------------------------ forward push, fast path
 // Same algorithm and the same floating-point operations in the same order as ppr_push_kernel (pprgo.py:9-38), with the
-// per-seed state split by how it is accessed ("the common small supports would fit in shared memory"):
-//   shared memory (per warp)  the LIFO queue (index + node id, so a pop needs no dependent global load before the
-//                             row pointer is fetched) and the p-list: (node, p) of the nodes popped so far, in
-//                             insertion order -- a few hundred entries; the top-k selection then scans THIS list instead
-//                             of every touched record (3 000 records vs 160 popped nodes on the citation2 shape);
-//   global memory (L2-warm)   one record per touched node: node id, residual r, flags (p-list index, in-queue bit), and
-//                             the open-addressing hash node -> record whose entries carry a 16-bit epoch: a new seed
-//                             bumps the epoch instead of clearing 3 000 scattered slots.
-// Seeds that outgrow the queue, the p-list or the record array are flagged and redone by the general kernel.
+// per-seed state arranged so that a push costs three dependent memory round trips instead of five:
+//   shared memory (per warp)  the LIFO queue (node ids) and the p-list: (node, p) of the nodes popped so far, in
+//                             insertion order -- a few hundred entries; the top-k selection scans THIS list instead of
+//                             every touched node (3 000 touched vs 160 popped nodes on the citation2 shape) and compacts
+//                             it in place; its histogram aliases the queue, which is empty by then.  4.5 KB per warp:
+//                             six CTAs (48 warps) per SM.
+//   global memory             one open-addressing table per warp whose 16-byte slot IS the record:
+//                               x node id | y degree | z epoch << 16 | in-queue bit 15 | p-list index + 1 | w residual r
+//                             one vector load answers "seen?", r, the queue flag and the degree; an update is one 4- or
+//                             8-byte store into the same sector.  A new seed bumps the epoch instead of clearing slots.
+// Inserts need no atomics: the lanes of a warp hold distinct neighbours, so only the target SLOT can collide, and
+// __match_any_sync elects one writer per slot; the losers probe on after a __syncwarp.  The degree of every neighbour is
+// fetched (row info, 8 bytes, L2 resident) together with its first probe, not after it.
+// Seeds that outgrow the queue, the p-list or the table are flagged and redone by the general kernel.
 constexpr int kFastQ = 512;    // queue entries per warp
-constexpr int kFastP = 384;    // popped nodes per warp
+constexpr int kFastPDefault = 320;    // popped nodes per warp (SUBG_PPR_FAST_P)
 
 struct PprFastArgs {
+    const unsigned long long *rowinfo;  // [N] row start (low 40 bits) | degree (high 24 bits, 0xFFFFFF = read rowptr)
     const void *rowptr;
     int rowptr64;
     const int32_t *col;
@@ -292,12 +298,10 @@ struct PprFastArgs {
     float alpha, alpha_eps;
     double one_minus_alpha;
     int topk;
-    int R;           // records per warp (<= 65535)
+    int R;           // touched nodes per seed (<= half the slots)
+    int P;           // p-list capacity per warp
     uint32_t hmask;
-    unsigned long long *htab;   // [warp][hmask + 1]: node << 32 | epoch << 16 | record index
-    int32_t *node;
-    float *r;
-    uint32_t *flag;             // low 16 bits: p-list index + 1 (0 = never popped); bit 31: in the queue
+    uint4 *htab;                // [warp][hmask + 1]
     uint32_t *epoch;            // [warp]: current epoch (persists across launches)
     unsigned long long *counter;  // [0] next work item, [1] pushes, [2] failed seeds
     uint8_t *fail;
@@ -306,25 +310,41 @@ struct PprFastArgs {
     int32_t *cnt;
 };
 
+__device__ __forceinline__ uint4 ld_slot(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+// the row info (8 B per node, tens of MB) is what the L2 should keep; the tables stream through it
+__device__ __forceinline__ unsigned long long ld_rowinfo(const PprFastArgs &a, uint32_t v, uint64_t keep) {
+    unsigned long long q;
+    asm("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(q) : "l"(a.rowinfo + v), "l"(keep));
+    return q;
+}
+__device__ __forceinline__ void row_of(const PprFastArgs &a, uint32_t v, uint64_t keep, int64_t &start, uint32_t &deg) {
+    const unsigned long long q = ld_rowinfo(a, v, keep);
+    start = (int64_t)(q & 0xffffffffffull);
+    deg = (uint32_t)(q >> 40);
+    if (deg == 0xFFFFFFu) deg = (uint32_t)min(ld_rowptr(a.rowptr, a.rowptr64, (int64_t)v + 1) - start, (int64_t)0xffffffffll);
+}
+
 __global__ void __launch_bounds__(kPprWarps * 32) ppr_push_fast_kernel(const PprFastArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t lt = (1u << lane) - 1u;
-    const int per_warp = 8 * kFastQ + 8 * kFastP + 1024 + 8 * a.topk;
+    const int per_warp = 4 * kFastQ + 8 * a.P;
     unsigned char *wsm = smem_raw + (size_t)wib * per_warp;
-    int32_t *q_idx = (int32_t *)wsm;
-    int32_t *q_node = q_idx + kFastQ;
+    int32_t *q_node = (int32_t *)wsm;
     int32_t *p_node = q_node + kFastQ;
-    float *p_val = (float *)(p_node + kFastP);
-    uint32_t *hist = (uint32_t *)(p_val + kFastP);
-    int32_t *sel_node = (int32_t *)(hist + 256);
-    float *sel_val = (float *)(sel_node + a.topk);
+    float *p_val = (float *)(p_node + a.P);
+    uint32_t *hist = (uint32_t *)wsm;               // the queue is empty when the selection runs
+    int32_t *sel_node = p_node;                     // the selection compacts the p-list in place
+    float *sel_val = p_val;
+    uint64_t keep;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
 
     const int64_t gw = (int64_t)blockIdx.x * kPprWarps + wib;
-    unsigned long long *htab = a.htab + gw * ((int64_t)a.hmask + 1);
-    int32_t *node = a.node + gw * a.R;
-    float *r = a.r + gw * a.R;
-    uint32_t *flag = a.flag + gw * a.R;
+    uint4 *htab = a.htab + gw * ((int64_t)a.hmask + 1);
     uint32_t epoch = a.epoch[gw];
     unsigned long long pushes = 0;
 
@@ -335,118 +355,113 @@ __global__ void __launch_bounds__(kPprWarps * 32) ppr_push_fast_kernel(const Ppr
         if ((int64_t)t >= a.nwork) break;
         const int64_t i = (int64_t)t;
         const int32_t s = __ldg(a.seeds + i);
-        // a new epoch invalidates every entry of the previous seed; on wrap-around the table is really cleared
+        // a new epoch invalidates every slot of the previous seed; on wrap-around the table is really cleared
         epoch++;
         if (epoch >= 0xffffu) {
-            for (uint32_t h = lane; h <= a.hmask; h += 32) htab[h] = 0ull;
+            for (uint32_t h = lane; h <= a.hmask; h += 32) htab[h] = make_uint4(0u, 0u, 0u, 0u);
             epoch = 1;
-            __syncwarp();
         }
-        const unsigned long long etag = (unsigned long long)epoch << 16;
+        const uint32_t etag = epoch << 16;
+        __syncwarp();
 
         // p = {s: 0}; r = {s: alpha}; q = [s]                          pprgo.py:12-16
         int nrec = 1, np = 0, qlen = 1;
         if (lane == 0) {
-            htab[hash_node((uint32_t)s, a.hmask)] = ((unsigned long long)(uint32_t)s << 32) | etag | 0ull;
-            node[0] = s; r[0] = a.alpha; flag[0] = 0x80000000u;
-            q_idx[0] = 0; q_node[0] = s;
+            int64_t rs;
+            uint32_t ds;
+            row_of(a, (uint32_t)s, keep, rs, ds);
+            const uint32_t h = hash_node((uint32_t)s, a.hmask);
+            htab[h] = make_uint4((uint32_t)s, ds, etag | 0x8000u, __float_as_uint(a.alpha));
+            q_node[0] = s;
         }
         __syncwarp();
         bool overflow = false;
         unsigned long long seed_pushes = 0;
         while (qlen > 0) {
             qlen--;
-            const int ui = q_idx[qlen];      // q.pop()                  pprgo.py:18
-            const int32_t u = q_node[qlen];
-            const float res = __ldcg(r + ui);
-            const uint32_t fl = __ldcg(flag + ui);
-            const int64_t rp0 = ld_rowptr(a.rowptr, a.rowptr64, u);
-            const int64_t d = ld_rowptr(a.rowptr, a.rowptr64, (int64_t)u + 1) - rp0;
-            int pi = (int)(fl & 0xffffu);    // p-list index + 1
+            const int32_t u = q_node[qlen];  // q.pop()                  pprgo.py:18
+            const unsigned long long urow = ld_rowinfo(a, (uint32_t)u, keep);
+            uint32_t uh = hash_node((uint32_t)u, a.hmask);   // u is in the table: almost always at its first slot
+            uint4 us = ld_slot(htab + uh);
+            while (us.x != (uint32_t)u || (us.z & 0xffff0000u) != etag) {
+                uh = (uh + 1) & a.hmask;
+                us = ld_slot(htab + uh);
+            }
+            const float res = __uint_as_float(us.w);
+            const int64_t rp0 = (int64_t)(urow & 0xffffffffffull);
+            const int64_t d = (int64_t)us.y;
+            int pi = (int)(us.z & 0x7fffu);  // p-list index + 1
             if (pi == 0) {                   // first pop of u: p[u] = res      pprgo.py:21-24
-                if (np >= kFastP) { overflow = true; break; }
+                if (np >= a.P) { overflow = true; break; }
                 pi = ++np;
                 if (lane == 0) { p_node[pi - 1] = u; p_val[pi - 1] = res; }
             } else if (lane == 0) {
                 p_val[pi - 1] += res;
             }
-            if (lane == 0) {
-                flag[ui] = (uint32_t)pi;     // out of the queue
-                r[ui] = 0.f;                 // pprgo.py:25
-            }
+            if (lane == 0)                   // out of the queue, r[u] = 0      pprgo.py:25
+                *(uint2 *)((uint32_t *)(htab + uh) + 2) = make_uint2(etag | (uint32_t)pi, 0u);
             // (1 - alpha) * res / deg[u]: float64 arithmetic rounded to float32 (pprgo.py:8,27)
             const float val = (float)(a.one_minus_alpha * (double)res / (double)d);
             __syncwarp();
             for (int64_t j0 = 0; j0 < d; j0 += 32) {
                 const int64_t j = j0 + lane;
                 const bool act = j < d;
-                int32_t v = -1;
-                int idx = -1;
-                uint32_t h = 0;
-                unsigned long long seen = 0ull;
-                int64_t dv = 0;
+                uint32_t v = 0xffffffffu, h = 0xffffff00u + (uint32_t)lane, dv = 0;
+                uint4 sl = make_uint4(0u, 0u, 0u, 0u);
                 if (act) {
-                    v = __ldg(a.col + rp0 + j);
-                    h = hash_node((uint32_t)v, a.hmask);
-                    dv = ld_rowptr(a.rowptr, a.rowptr64, (int64_t)v + 1) - ld_rowptr(a.rowptr, a.rowptr64, v);
+                    v = (uint32_t)__ldg(a.col + rp0 + j);
+                    h = hash_node(v, a.hmask);
+                    sl = ld_slot(htab + h);
+                    int64_t rs;
+                    row_of(a, v, keep, rs, dv);   // wanted for new nodes only, but asked for before the probe answers
                 }
                 // lookup: probe until the node or a free (stale / never used) slot; the loop ends on a warp vote
-                bool look = act;
+                bool look = act, isnew = false;
                 while (__any_sync(FULL, look)) {
                     if (look) {
-                        seen = __ldcg(htab + h);
-                        if ((seen & 0xffff0000ull) != etag) look = false;                       // free slot: v is new
-                        else if ((int32_t)(uint32_t)(seen >> 32) == v) { idx = (int)(seen & 0xffffu); look = false; }
-                        else h = (h + 1) & a.hmask;
-                    }
-                }
-                const bool isnew = act && idx < 0;
-                const uint32_t newm = __ballot_sync(FULL, isnew);
-                const int nnew = __popc(newm);
-                if (nrec + nnew > a.R) { overflow = true; break; }
-                float rv = 0.f;
-                uint32_t vflag = 0u;
-                if (isnew) {
-                    idx = nrec + __popc(newm & lt);
-                } else if (act) {
-                    rv = __ldcg(r + idx);
-                    vflag = __ldcg(flag + idx);
-                }
-                // insert the new nodes (distinct columns: no two lanes insert the same node, but they may want the same slot)
-                {
-                    const unsigned long long ent = ((unsigned long long)(uint32_t)v << 32) | etag | (unsigned long long)(uint32_t)idx;
-                    bool ins = isnew;
-                    while (__any_sync(FULL, ins)) {
-                        if (ins) {
-                            if ((seen & 0xffff0000ull) == etag) {       // taken by another lane meanwhile: next slot
-                                h = (h + 1) & a.hmask;
-                                seen = __ldcg(htab + h);
-                            } else {
-                                const unsigned long long old = atomicCAS(htab + h, seen, ent);
-                                if (old == seen) ins = false;
-                                else seen = old;
-                            }
+                        if ((sl.z & 0xffff0000u) != etag) { isnew = true; look = false; }     // free slot: v is new
+                        else if (sl.x == v) look = false;
+                        else {
+                            h = (h + 1) & a.hmask;
+                            sl = ld_slot(htab + h);
                         }
                     }
                 }
-                nrec += nnew;
-                rv = isnew ? val : rv + val;                             // pprgo.py:28-31
-                bool push = false;
-                if (act) {
-                    // res_vnode >= alpha_eps * deg[vnode] (float32 product widened, pprgo.py:33-34); vnode not in q
-                    push = ((double)rv >= (double)a.alpha_eps * (double)dv) && (isnew || (vflag & 0x80000000u) == 0u);
-                }
+                const uint32_t newm = __ballot_sync(FULL, isnew);
+                if (nrec + __popc(newm) > a.R) { overflow = true; break; }
+                nrec += __popc(newm);
+                const float rv = isnew ? val : __uint_as_float(sl.w) + val;            // pprgo.py:28-31
+                const uint32_t fl = isnew ? 0u : (sl.z & 0xffffu);
+                if (!isnew) dv = sl.y;
+                // res_vnode >= alpha_eps * deg[vnode] (float32 product widened, pprgo.py:33-34); vnode not in q
+                const bool push = act && ((double)rv >= (double)a.alpha_eps * (double)dv) && (fl & 0x8000u) == 0u;
                 const uint32_t pm = __ballot_sync(FULL, push);
                 if (qlen + __popc(pm) > kFastQ) { overflow = true; break; }
-                if (act) {
-                    r[idx] = rv;
-                    if (isnew) node[idx] = v;
-                    if (push) {                                          // pprgo.py:35-36, CSR order
-                        const int at = qlen + __popc(pm & lt);
-                        q_idx[at] = idx;
-                        q_node[at] = v;
+                const uint32_t tagw = etag | fl | (push ? 0x8000u : 0u);
+                if (act && !isnew) {
+                    if (push) *(uint2 *)((uint32_t *)(htab + h) + 2) = make_uint2(tagw, __float_as_uint(rv));
+                    else ((uint32_t *)(htab + h))[3] = __float_as_uint(rv);
+                }
+                // insert the new nodes: distinct columns, so only the slot can collide; one writer per slot and round
+                bool ins = isnew;
+                while (__any_sync(FULL, ins)) {
+                    const uint32_t grp = __match_any_sync(FULL, ins ? h : (0xffffff00u + (uint32_t)lane));
+                    const bool win = ins && (__ffs((int)grp) - 1) == lane;
+                    if (win) {
+                        htab[h] = make_uint4(v, dv, tagw, __float_as_uint(rv));
+                        ins = false;
                     }
-                    if (push || isnew) flag[idx] = (isnew ? 0u : (vflag & 0xffffu)) | (push ? 0x80000000u : 0u);
+                    __syncwarp();
+                    if (ins) {                                   // lost the slot: probe on (sees this round's writes)
+                        for (;;) {
+                            h = (h + 1) & a.hmask;
+                            if ((ld_slot(htab + h).z & 0xffff0000u) != etag) break;
+                        }
+                    }
+                }
+                if (push) {                                              // pprgo.py:35-36, CSR order
+                    const int at = qlen + __popc(pm & lt);
+                    q_node[at] = (int32_t)v;
                 }
                 qlen += __popc(pm);
                 __syncwarp();
@@ -519,14 +534,16 @@ __global__ void __launch_bounds__(kPprWarps * 32) ppr_push_fast_kernel(const Ppr
             const int t = t0 + lane;
             bool keep = false;
             float pv = 0.f;
+            int32_t pn = 0;
             if (t < np) {
                 pv = p_val[t];
+                pn = p_node[t];
                 keep = (((unsigned long long)__float_as_uint(pv) << 32) | (uint32_t)t) >= thr;
             }
-            const uint32_t km = __ballot_sync(FULL, keep);
+            const uint32_t km = __ballot_sync(FULL, keep);   // every read of this batch precedes its in-place writes (o <= t)
             if (keep) {
                 const int o = nsel + __popc(km & lt);
-                sel_node[o] = p_node[t];
+                sel_node[o] = pn;
                 sel_val[o] = pv;
             }
             nsel += __popc(km);
@@ -954,10 +971,10 @@ int ppr_topk_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, float alph
             if (fast) R = std::min<int64_t>(R, 65535);
             uint32_t H = 64;
             while ((int64_t)H < 2 * R) H <<= 1;
-            int smem_k = smem, per_sm_k = per_sm;
+            int smem_k = smem, per_sm_k = per_sm, fast_p = 0;
             if (fast) {
-                smem_k = kPprWarps * (8 * kFastQ + 8 * kFastP + 1024 + 8 * topk);
-                if (smem_k > 220 * 1024) continue;   // top-k buffers too large: general kernel only
+                fast_p = (int)std::min<int64_t>(std::max<int64_t>(env_i64("SUBG_PPR_FAST_P", kFastPDefault), 32), 2048);
+                smem_k = kPprWarps * (4 * kFastQ + 8 * fast_p);
                 CKG(cudaFuncSetAttribute(ppr_push_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_k));
                 CKG(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_k, ppr_push_fast_kernel, kPprWarps * 32, smem_k));
                 per_sm_k = std::max(per_sm_k, 1);
@@ -966,31 +983,33 @@ int ppr_topk_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, float alph
             }
             int64_t blocks = (int64_t)g->num_sms * per_sm_k;
             blocks = std::min<int64_t>(blocks, (nwork + kPprWarps - 1) / kPprWarps);
-            const int64_t bytes_per_warp = (int64_t)H * 8 + R * (fast ? 12 : 25);
+            const int64_t bytes_per_warp = fast ? (int64_t)H * 16 : (int64_t)H * 8 + R * 25;
             const int64_t budget = env_i64("SUBG_PPR_WORKSPACE_BYTES", 24ll << 30);
             blocks = std::max<int64_t>(1, std::min<int64_t>(blocks, budget / (bytes_per_warp * kPprWarps)));
             const int64_t nw = blocks * kPprWarps;
-            CKG(dmalloc(&ws.htab, (size_t)nw * H, st));
-            CKG(dmalloc(&ws.node, (size_t)nw * R, st));
-            CKG(dmalloc(&ws.r, (size_t)nw * R, st));
-            CKG(dmalloc(&ws.pord, (size_t)(fast ? nw * R : nw * R), st));   // fast: the flag words
+            CKG(dmalloc(&ws.htab, (size_t)nw * H * (fast ? 2 : 1), st));     // fast: 16-byte slots
             if (!fast) {
+                CKG(dmalloc(&ws.node, (size_t)nw * R, st));
+                CKG(dmalloc(&ws.r, (size_t)nw * R, st));
+                CKG(dmalloc(&ws.pord, (size_t)nw * R, st));
                 CKG(dmalloc(&ws.hslot, (size_t)nw * R, st)); CKG(dmalloc(&ws.q, (size_t)nw * R, st));
                 CKG(dmalloc(&ws.p, (size_t)nw * R, st));
                 CKG(dmalloc(&ws.inq, (size_t)nw * R, st));
+                fill_empty_kernel<<<8 * g->num_sms, 256, 0, st>>>(ws.htab, nw * (int64_t)H);
             } else {
                 CKG(dmalloc(&ws.q, (size_t)nw, st));                        // fast: the per-warp epochs
                 CKG(cudaMemsetAsync(ws.q, 0, (size_t)nw * 4, st));
+                CKG(cudaMemsetAsync(ws.htab, 0, (size_t)nw * H * 16, st));  // epoch 0 = never written
             }
-            fill_empty_kernel<<<8 * g->num_sms, 256, 0, st>>>(ws.htab, nw * (int64_t)H);
             CKG(cudaMemsetAsync(counter, 0, 4 * sizeof(unsigned long long), st));
             timing_begin(SUBG_TIMING_PPR, st);
             if (fast) {
                 PprFastArgs a{};
+                a.rowinfo = (const unsigned long long *)g->rowinfo;
                 a.rowptr = g->rowptr; a.rowptr64 = g->rowptr64 ? 1 : 0; a.col = g->col; a.seeds = s->seeds; a.nwork = nwork;
                 a.alpha = alpha; a.alpha_eps = alpha_eps; a.one_minus_alpha = 1.0 - (double)alpha;
-                a.topk = topk; a.R = (int)R; a.hmask = H - 1;
-                a.htab = ws.htab; a.node = ws.node; a.r = ws.r; a.flag = (uint32_t *)ws.pord; a.epoch = (uint32_t *)ws.q;
+                a.topk = topk; a.R = (int)R; a.P = fast_p; a.hmask = H - 1;
+                a.htab = (uint4 *)ws.htab; a.epoch = (uint32_t *)ws.q;
                 a.counter = counter; a.fail = fail_d; a.st_node = st_node; a.st_val = st_val; a.cnt = cnt;
                 ppr_push_fast_kernel<<<(unsigned)blocks, kPprWarps * 32, smem_k, st>>>(a);
             } else {

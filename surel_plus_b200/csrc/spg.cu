@@ -340,6 +340,10 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
     DeviceGuard guard(g->device);
     const bool want_slot = !(flags & SUBG_SAMPLE_NO_RANKS);
     const bool want_rank = want_slot || pl.stride < pl.Kt;
+    if (!want_rank) {  // no first-visit ranks: the order bitmap is never touched, its shared memory buys a resident CTA on ppa
+        pl.nbw = 0;
+        pl.smem_per_warp = (pl.bitmap_off + 15) & ~15;
+    }
 
     g->tag.use_on(st);
     SpG *s = new SpG();

@@ -163,45 +163,62 @@ __global__ void __launch_bounds__(kPlanTile) join_plan_offsets_kernel(const int3
     if (g == nseg - 1) seg_ptr[nseg] = tot[0];
 }
 // Plan of a small batch in ONE launch (segments <= kPlanOneMax): a single block sizes every segment and scans them.
+// Phase 1 walks the segments with a stride of the block (a warp reads 256 contiguous bytes of the edge array, which may be
+// pinned HOST memory read over PCIe: one request per warp and round, all rounds in flight before the first is used) and
+// leaves the sizes in shared memory; phase 2 gives every thread `per` consecutive segments of that array for the scan.
 constexpr int kPlanOneThreads = 1024;
-constexpr int kPlanOneItems = 16;
+constexpr int kPlanOneItems = 8;
 constexpr int kPlanOneMax = kPlanOneThreads * kPlanOneItems;
-// edge may be pinned host memory (read once over PCIe); edge_out (nullable) receives the device copy the join kernel reads
-__global__ void __launch_bounds__(kPlanOneThreads) join_plan_one_kernel(const long long *rowbeg, const int32_t *nsize, int64_t n_rows,
-                                                                       const long long *edge, long long *edge_out, int64_t B,
-                                                                       int arity, int nseg, long long *seg_ptr, long long *tot) {
+// edge_out (nullable) receives the device copy the join kernel reads
+__global__ void __launch_bounds__(kPlanOneThreads) join_plan_one_kernel(const long long *__restrict__ rowbeg, const int32_t *__restrict__ nsize,
+                                                                       int64_t n_rows, const long long *__restrict__ edge,
+                                                                       long long *__restrict__ edge_out, int64_t B, int arity, int nseg,
+                                                                       long long *__restrict__ seg_ptr, long long *__restrict__ tot) {
     __shared__ long long ws[32];
-    const int per = (nseg + kPlanOneThreads - 1) / kPlanOneThreads;   // consecutive segments per thread, <= kPlanOneItems
-    const int first = threadIdx.x * per;
-    int32_t sz[kPlanOneItems];
-    long long sum = 0;
+    __shared__ int32_t ssz[kPlanOneMax];
+    long long node[kPlanOneItems];
+    int64_t at[kPlanOneItems];
     bool bad = false;
 #pragma unroll
     for (int q = 0; q < kPlanOneItems; q++) {
-        sz[q] = 0;
-        const int g = first + q;
-        if (q < per && g < nseg) {
-            long long node;
-            int64_t at = g;
+        const int g = threadIdx.x + q * kPlanOneThreads;
+        node[q] = -1;
+        at[q] = g;
+        if (g < nseg) {
             if (arity != 2) {
                 const int blk = g / (int)B, qq = g - blk * (int)B;
-                at = (int64_t)(blk == 0 ? 0 : (blk == 2 ? 1 : 2)) * B + qq;  // u, w, v, w
+                at[q] = (int64_t)(blk == 0 ? 0 : (blk == 2 ? 1 : 2)) * B + qq;  // u, w, v, w
             }
-            node = edge[at];
-            if (edge_out) edge_out[at] = node;
-            if (node < 0 || node >= n_rows) bad = true;
-            else sz[q] = nsize ? nsize[node] : (int32_t)(rowbeg[node + 1] - rowbeg[node]);
-            sum += sz[q];
+            node[q] = edge[at[q]];
         }
     }
+#pragma unroll
+    for (int q = 0; q < kPlanOneItems; q++) {
+        const int g = threadIdx.x + q * kPlanOneThreads;
+        if (g < nseg) {
+            int32_t sz = 0;
+            if (node[q] < 0 || node[q] >= n_rows) bad = true;
+            else sz = nsize ? nsize[node[q]] : (int32_t)(rowbeg[node[q] + 1] - rowbeg[node[q]]);
+            ssz[g] = sz;
+            if (edge_out) edge_out[at[q]] = node[q];
+        }
+    }
+    const int any_bad = __syncthreads_or(bad ? 1 : 0);
+    const int per = (nseg + kPlanOneThreads - 1) / kPlanOneThreads;   // consecutive segments per thread, <= kPlanOneItems
+    const int first = threadIdx.x * per;
+    long long sum = 0;
+#pragma unroll
+    for (int q = 0; q < kPlanOneItems; q++)
+        if (q < per && first + q < nseg) sum += ssz[first + q];
     long long total;
     long long ex = block_excl_scan(sum, &total, ws);
-    const int any_bad = __syncthreads_or(bad ? 1 : 0);
 #pragma unroll
     for (int q = 0; q < kPlanOneItems; q++) {
         const int g = first + q;
-        if (q < per && g < nseg) seg_ptr[g] = ex;
-        ex += sz[q];
+        if (q < per && g < nseg) {
+            seg_ptr[g] = ex;
+            ex += ssz[g];
+        }
     }
     if (threadIdx.x == 0) {
         seg_ptr[nseg] = total;
@@ -666,6 +683,13 @@ struct Joiner {
     size_t row_bytes = 0;
     const float *enc = nullptr;
     cudaStream_t cap_stream = nullptr;
+    // Host-edge batches alternate between two internal streams, so that the plan kernel of batch k+1 (and the PCIe read of
+    // its edges) runs beside the join kernel of batch k; the caller's stream is made to wait for each batch (see submit).
+    cudaStream_t lane[2] = {nullptr, nullptr};
+    cudaEvent_t ev_user = nullptr;   // the caller's stream at the previous submit
+    bool ev_user_set = false;
+    int lanes = 2;
+    unsigned seq = 0;
     std::vector<JoinSlot> slot;
 };
 
@@ -684,6 +708,9 @@ void joiner_free_impl(Joiner *j) {
         if (q.edge_pin) cudaFreeHost(q.edge_pin);
         if (q.tot_pin) cudaFreeHost(q.tot_pin);
     }
+    for (int l = 0; l < 2; l++)
+        if (j->lane[l]) { cudaStreamSynchronize(j->lane[l]); cudaStreamDestroy(j->lane[l]); }
+    if (j->ev_user) cudaEventDestroy(j->ev_user);
     if (j->cap_stream) cudaStreamDestroy(j->cap_stream);
     cudaGetLastError();
     delete j;
@@ -731,6 +758,9 @@ int joiner_create_impl(const SpG *s, int64_t B, int arity, const float *enc_tabl
     j->slot.resize(depth);
     cudaError_t e = cudaStreamCreateWithFlags(&j->cap_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) s->tag.last = j->cap_stream;  // no cross-stream event inside the capture (everything has completed)
+    if (const char *v = getenv("SUBG_JOIN_LANES")) j->lanes = atoi(v) >= 2 ? 2 : 1;
+    for (int l = 0; l < j->lanes && e == cudaSuccess; l++) e = cudaStreamCreateWithFlags(&j->lane[l], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&j->ev_user, cudaEventDisableTiming);
     int rc = SUBG_OK;
     for (int q = 0; q < depth && e == cudaSuccess && rc == SUBG_OK; q++) {
         JoinSlot &sl = j->slot[q];
@@ -787,13 +817,30 @@ int joiner_submit_impl(Joiner *j, const int64_t *edge_hd, int edge_on_device, cu
     if (edge_on_device < 0) edge_on_device = is_device_ptr(edge_hd) ? 1 : 0;
     if (edge_on_device) {
         if (int rc = joiner_enqueue(j, sl, st, (const long long *)edge_hd)) return rc;
+        SUBG_CUDA(cudaEventRecord(sl.done, st));
+        sl.last_stream = st;
     } else {
         SUBG_CUDA(cudaEventSynchronize(sl.done));  // the slot's previous batch has read its staging (long ago, unless the ring is lapped)
         memcpy(sl.edge_pin, edge_hd, eb);
-        SUBG_CUDA(cudaGraphLaunch(sl.exec, st));
+        if (j->lanes < 2) {
+            SUBG_CUDA(cudaGraphLaunch(sl.exec, st));
+            SUBG_CUDA(cudaEventRecord(sl.done, st));
+            sl.last_stream = st;
+        } else {
+            // The batch runs on an internal stream behind the caller's stream AS OF THE PREVIOUS SUBMIT: that point covers
+            // the consumer's reads of this slot's last contents (queued at least depth - 1 submits ago) but not the wait
+            // for the previous batch, so two batches are in flight.  The caller's stream then waits for this batch.
+            cudaStream_t is = j->lane[j->seq++ & 1];
+            if (!j->ev_user_set) SUBG_CUDA(cudaEventRecord(j->ev_user, st));   // first batch: behind everything queued so far
+            SUBG_CUDA(cudaStreamWaitEvent(is, j->ev_user, 0));
+            SUBG_CUDA(cudaGraphLaunch(sl.exec, is));
+            SUBG_CUDA(cudaEventRecord(sl.done, is));
+            SUBG_CUDA(cudaEventRecord(j->ev_user, st));
+            j->ev_user_set = true;
+            SUBG_CUDA(cudaStreamWaitEvent(st, sl.done, 0));
+            sl.last_stream = is;
+        }
     }
-    SUBG_CUDA(cudaEventRecord(sl.done, st));
-    sl.last_stream = st;
     count_launch(j->launches);
     if (out_dev) *out_dev = sl.out_dev;
     if (indptr_dev) *indptr_dev = (int64_t *)sl.indptr_dev;

@@ -206,13 +206,15 @@ struct PullArgs {
     long long *rowbeg;
     int32_t *nsize;
     const int32_t *gmap;
+    unsigned long long *ticket;   // nullable: [world] chunk counters (windowed pull)
 };
 
 constexpr int kPullThreads = 256;
 constexpr int kPullUnroll = 4;
+constexpr int64_t kPullChunk = 4096;   // 16-byte words per ticket (64 KB of packed entries)
 
 template <int E>
-__device__ __forceinline__ void pull_region(const PullArgs &a, int r, int64_t first, int64_t step) {
+__device__ __forceinline__ void pull_region(const PullArgs &a, int r, int64_t first, int64_t step, int64_t limit) {
     const uint4 *word = (const uint4 *)(a.src[r] + a.word_off[r]);
     const unsigned char *extra = a.src[r] + a.extra_off[r];
     const int nb = a.nb[r];
@@ -221,7 +223,7 @@ __device__ __forceinline__ void pull_region(const PullArgs &a, int r, int64_t fi
     const int32_t *gmap = a.gmap + a.gmap_off[r];
     int4 *out_i = (int4 *)(a.indices + a.dst_off[r]);
     int4 *out_d = (int4 *)(a.data + a.dst_off[r]);
-    const int64_t n4 = a.e4[r] >> 2;
+    const int64_t n4 = limit;
     for (int64_t i0 = first; i0 < n4; i0 += step * kPullUnroll) {
         uint4 w[kPullUnroll], x[kPullUnroll];
 #pragma unroll
@@ -268,16 +270,40 @@ __device__ __forceinline__ void pull_region(const PullArgs &a, int r, int64_t fi
 }
 
 // grid = world x blocks_per_region; block b works on region (rank + b % world) % world, so every GPU reads from all of
-// its peers at once and no two GPUs start on the same peer
+// its peers at once and no two GPUs start on the same peer.  Two schedules inside a region:
+//   grid-stride   block j of the region takes words j, j + nblk, ... (in units of a block's 4 KB): all blocks advance in
+//                 lock step only as long as they run at the same speed;
+//   windowed      (a.ticket) blocks take 64 KB chunks of the region in order from a counter: however far the blocks drift
+//                 apart in time, the addresses in flight stay inside a window of nblk x 64 KB per region -- at the twitter
+//                 size (2.5 GB per region, 20 GB per GPU) that is what keeps the peer mappings inside the TLB reach.
 __global__ void __launch_bounds__(kPullThreads) xchg_pull_kernel(const PullArgs a) {
     const int r = (a.rank + (int)(blockIdx.x % a.world)) % a.world;
     const int64_t jb = blockIdx.x / a.world, nblk = gridDim.x / a.world;
     const int64_t first = jb * kPullThreads + threadIdx.x, step = nblk * kPullThreads;
-    switch (a.extra[r]) {
-        case 0: pull_region<0>(a, r, first, step); break;
-        case 1: pull_region<1>(a, r, first, step); break;
-        case 2: pull_region<2>(a, r, first, step); break;
-        default: pull_region<4>(a, r, first, step); break;
+    const int64_t n4 = a.e4[r] >> 2;
+    if (a.ticket) {
+        __shared__ unsigned long long s_chunk;
+        for (;;) {
+            if (threadIdx.x == 0) s_chunk = atomicAdd(a.ticket + r, 1ull);
+            __syncthreads();
+            const int64_t lo = (int64_t)s_chunk * kPullChunk;
+            __syncthreads();
+            if (lo >= n4) break;
+            const int64_t hi = lo + kPullChunk < n4 ? lo + kPullChunk : n4;
+            switch (a.extra[r]) {
+                case 0: pull_region<0>(a, r, lo + threadIdx.x, kPullThreads, hi); break;
+                case 1: pull_region<1>(a, r, lo + threadIdx.x, kPullThreads, hi); break;
+                case 2: pull_region<2>(a, r, lo + threadIdx.x, kPullThreads, hi); break;
+                default: pull_region<4>(a, r, lo + threadIdx.x, kPullThreads, hi); break;
+            }
+        }
+    } else {
+        switch (a.extra[r]) {
+            case 0: pull_region<0>(a, r, first, step, n4); break;
+            case 1: pull_region<1>(a, r, first, step, n4); break;
+            case 2: pull_region<2>(a, r, first, step, n4); break;
+            default: pull_region<4>(a, r, first, step, n4); break;
+        }
     }
     // row offsets and set sizes of the region
     const long long *rb = (const long long *)(a.src[r] + a.rowbeg_off[r]);
@@ -289,9 +315,11 @@ __global__ void __launch_bounds__(kPullThreads) xchg_pull_kernel(const PullArgs 
 }
 
 // ------------------------------------------------------------------ host side
-// blocks of the pull kernel per region: together about 8 CTAs per SM (SUBG_XCHG_BLOCKS overrides the total)
-static int64_t env_blocks_per_region(int num_sms, int world) {
-    int64_t total = 8ll * num_sms;
+// blocks of the pull kernel per region: together about 8 CTAs per SM, 2 per SM for large exchanges (measured at the twitter
+// size on 8 GPUs: 1184 blocks pull 203 GB/s per GPU, 296 blocks 444 GB/s; at the ppa size 1184 blocks reach 616 GB/s;
+// profiles/r2p_exchange_twitter8.txt).  SUBG_XCHG_BLOCKS overrides the total.
+static int64_t env_blocks_per_region(int num_sms, int world, bool large) {
+    int64_t total = (large ? 2ll : 8ll) * num_sms;
     if (const char *v = getenv("SUBG_XCHG_BLOCKS")) total = std::max<int64_t>(atoll(v), 1);
     return (total + world - 1) / world;
 }
@@ -460,6 +488,7 @@ int xchg_assemble_impl(Xchg *x, const int64_t *headers, const void *const *srcs,
     unsigned long long *tab_key = nullptr, *tab_pos = nullptr;
     int32_t *rank_of_slot = nullptr, *gmap = nullptr;
     uint32_t *d_cnt = nullptr;
+    unsigned long long *d_ticket = nullptr;
     int rc = SUBG_OK;
 #define CKX(call)                                                                                  \
     do {                                                                                           \
@@ -502,7 +531,18 @@ int xchg_assemble_impl(Xchg *x, const int64_t *headers, const void *const *srcs,
         pmark("xchg:merge");
         if (ext_tot > 0 || n_tot > 0) {
             pa.indices = s->indices; pa.data = (int32_t *)s->data; pa.rowbeg = (long long *)s->rowbeg; pa.nsize = s->nsize; pa.gmap = gmap;
-            int per_region = std::max(1, (int)env_blocks_per_region(s->num_sms, W));
+            // windowed schedule and fewer blocks for large exchanges (SUBG_XCHG_TICKET = 0 / 1 overrides; default: more
+            // than 4 GB pulled)
+            int64_t pulled = 0;
+            for (int r = 0; r < W; r++) pulled += 4 * pa.e4[r];
+            int per_region = std::max(1, (int)env_blocks_per_region(s->num_sms, W, pulled > (4ll << 30)));
+            const char *tkv = getenv("SUBG_XCHG_TICKET");
+            const int64_t tk = tkv ? atoll(tkv) : -1;
+            if (tk > 0 || (tk < 0 && pulled > (4ll << 30))) {
+                CKX(dmalloc(&d_ticket, (size_t)kMaxWorld, st));
+                CKX(cudaMemsetAsync(d_ticket, 0, kMaxWorld * sizeof(unsigned long long), st));
+                pa.ticket = d_ticket;
+            }
             timing_begin(SUBG_TIMING_EXCHANGE, st);
             xchg_pull_kernel<<<(unsigned)(W * per_region), kPullThreads, 0, st>>>(pa);
             timing_end(SUBG_TIMING_EXCHANGE, st);
@@ -516,7 +556,7 @@ int xchg_assemble_impl(Xchg *x, const int64_t *headers, const void *const *srcs,
     }
 done:
 #undef CKX
-    dfree(tab_key, st); dfree(tab_pos, st); dfree(rank_of_slot, st); dfree(gmap, st); dfree(d_cnt, st);
+    dfree(tab_key, st); dfree(tab_pos, st); dfree(rank_of_slot, st); dfree(gmap, st); dfree(d_cnt, st); dfree(d_ticket, st);
     if (rc != SUBG_OK) {
         spg_free_impl(s);
         return rc;

@@ -164,8 +164,11 @@ class JoinStream:
         xz, indptr = js.gather(edge)                 # same result with the reference's exact shapes (one sync)
 
     `xz` of submit has `capacity` rows; rows [0, nrows[0]) are the join, in the order and layout of gather; the segment
-    pointer `indptr` (int64 [2B+1], or [4B+1] for triplets) addresses only those.  The buffers of a submit are reused
-    `depth` submits later: consume them on the same stream before that.  segid=True also returns the per-row segment id
+    pointer `indptr` (int64 [2B+1], or [4B+1] for triplets) addresses only those.  Host-edge batches alternate between two
+    internal streams (the plan of batch k+1 runs beside the join of batch k; SUBG_JOIN_LANES=1 turns that off) and the
+    caller's stream waits for each batch, so consumers just use the tensors on that stream.  The buffers of a submit are
+    reused `depth` submits later: queue the work that reads them before the (depth-1)-th following submit (with the default
+    depth of 3: submit(k), consume(k), or one batch of prefetch).  segid=True also returns the per-row segment id
     (gather's ptr=False / hgather's `ind`).  Batches are queued on the CUDA stream that was current when the JoinStream was
     built (or `stream=`)."""
 
