@@ -625,7 +625,7 @@ def bench_ppr(c):
     k_avg = k_ms / max(k_n, 1)
     per_launch = alg / max(k_n / steps, 1)
     ach = per_launch / (k_avg / 1e3) / 1e9
-    roof = {"bound": "hbm", "kernel": "ppr_push_kernel", "achieved": ach, "peak": c.peaks["hbm_gbs"], "unit": "GB/s",
+    roof = {"bound": "hbm", "kernel": "ppr_push_fast_kernel (+ ppr_push_kernel for the seeds that outgrow its shared-memory queue / p-list)", "achieved": ach, "peak": c.peaks["hbm_gbs"], "unit": "GB/s",
             "frac": ach / c.peaks["hbm_gbs"], "traffic": load_traffic("ppr_push", args), "peak_source": c.peaks["source"],
             "algorithmic_bytes_per_launch": per_launch, "kernel_ms_per_launch": k_avg, "kernel_launches_per_step": k_n / steps,
             "kernel_share_of_step": k_ms / ms_total, "pushes_per_step": pushes / steps, "pushes_per_s": pushes / (k_ms / 1e3),

@@ -285,6 +285,9 @@ __global__ void __launch_bounds__(kPprWarps * 32) ppr_push_kernel(const PprArgs 
 // __match_any_sync elects one writer per slot; the losers probe on after a __syncwarp.  The degree of every neighbour is
 // fetched (row info, 8 bytes, L2 resident) together with its first probe, not after it.
 // Seeds that outgrow the queue, the p-list or the table are flagged and redone by the general kernel.
+#ifndef SUBG_PPR_LAZY_DEG
+#define SUBG_PPR_LAZY_DEG 1   // 1: fetch a neighbour's degree only once the probe says it is new (half the row-info requests; 197 vs 201 ms on citation2), 0: with the first probe
+#endif
 constexpr int kFastQ = 512;    // queue entries per warp
 constexpr int kFastPDefault = 320;    // popped nodes per warp (SUBG_PPR_FAST_P)
 
@@ -412,8 +415,10 @@ __global__ void __launch_bounds__(kPprWarps * 32) ppr_push_fast_kernel(const Ppr
                     v = (uint32_t)__ldg(a.col + rp0 + j);
                     h = hash_node(v, a.hmask);
                     sl = ld_slot(htab + h);
+#if !SUBG_PPR_LAZY_DEG
                     int64_t rs;
                     row_of(a, v, keep, rs, dv);   // wanted for new nodes only, but asked for before the probe answers
+#endif
                 }
                 // lookup: probe until the node or a free (stale / never used) slot; the loop ends on a warp vote
                 bool look = act, isnew = false;
@@ -432,6 +437,12 @@ __global__ void __launch_bounds__(kPprWarps * 32) ppr_push_fast_kernel(const Ppr
                 nrec += __popc(newm);
                 const float rv = isnew ? val : __uint_as_float(sl.w) + val;            // pprgo.py:28-31
                 const uint32_t fl = isnew ? 0u : (sl.z & 0xffffu);
+#if SUBG_PPR_LAZY_DEG
+                if (isnew) {
+                    int64_t rs;
+                    row_of(a, v, keep, rs, dv);
+                }
+#endif
                 if (!isnew) dv = sl.y;
                 // res_vnode >= alpha_eps * deg[vnode] (float32 product widened, pprgo.py:33-34); vnode not in q
                 const bool push = act && ((double)rv >= (double)a.alpha_eps * (double)dv) && (fl & 0x8000u) == 0u;

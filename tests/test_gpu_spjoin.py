@@ -208,3 +208,39 @@ def test_join_stream_graph_replay_equals_gather(mid_graph, arity, B):
     for x in (js, js_raw, tiny):
         if x is not None:
             x.close()
+
+
+@pytest.mark.parametrize("B,arity", [(1024, 2), (2048, 3)])
+def test_join_stream_prefetch_pattern_two_lanes(mid_graph, B, arity):
+    """The training-loop pattern at the reference's batch sizes (train.py:121-127 B = 1024, main_horder.py:33 B = 2048):
+    batch k+1 is submitted BEFORE batch k is consumed, nothing is synchronised in between, host-edge batches alternate
+    between the joiner's two internal streams.  Every batch's rows, consumed on the caller's stream (a clone queued
+    there), equal gather / hgather."""
+    from surel_plus_b200 import DeviceGraph, JoinStream, SpG, gather, hgather
+    A = mid_graph
+    n, M = A.shape[0], 40
+    g = DeviceGraph.from_scipy(A)
+    spg = SpG.sample(g, np.arange(n), M, 2, seed=5, first_visit_ranks=False)
+    xpe = torch.from_numpy(spg.enc_table()).float().cuda() / M
+    rng = np.random.default_rng(100 + B)
+    edges = [rng.integers(0, n, (arity, B)) for _ in range(12)]
+    js = JoinStream(spg, B, "cuda", encode=xpe, arity=arity, segid=True, depth=3)
+    got = []
+    pending = js.submit(edges[0])
+    for k in range(len(edges)):
+        nxt = js.submit(edges[k + 1]) if k + 1 < len(edges) else None      # prefetch
+        xz, indptr, nrows, segid = pending
+        got.append((xz.clone(), indptr.clone(), nrows.clone(), segid.clone()))   # the consumer, on the current stream
+        pending = nxt
+    torch.cuda.synchronize()
+    for edge, (xz, indptr, nrows, segid) in zip(edges, got):
+        N = int(nrows[0].item())
+        if arity == 2:
+            want_xz, want_ptr = gather(edge, spg, "cuda", True, xpe)
+            _, want_seg = gather(edge, spg, "cuda", False, xpe)
+            assert torch.equal(indptr, want_ptr)
+        else:
+            want_xz, want_seg = hgather(edge, spg, "cuda", xpe)
+        assert N == want_xz.shape[0] and int(nrows[1].item()) == 0
+        assert torch.equal(xz[:N], want_xz) and torch.equal(segid[:N], want_seg)
+    js.close()
