@@ -405,11 +405,22 @@ def sampler_roofline(c, deg, M, m, T_avg, n_seeds, k_ms, k_launches, b_ms, steps
     alg_bytes = seed_algorithmic_bytes(deg, M, m, T_avg)
     k_avg_ms = k_ms / max(k_launches, 1)
     achieved = alg_bytes / (k_avg_ms / 1e3) / 1e9
+    # what explains `frac`: the walk is random 4-byte gathers, so the kernel is compared with the measured
+    # rate of that access pattern (profiles/r1_gather_micro.txt: plain random gathers over an array of the CSR's size, one B200)
+    live = int((deg > 0).sum())
+    visits = float(live) * M * m + n_seeds
+    csr_mb = (4.0 * float(c.graph.E) + 8.0 * float(c.graph.N)) / 2 ** 20
+    ceiling = 285e9 if csr_mb <= 100 else (78e9 if csr_mb <= 400 else 42e9)
+    gather = {"visits_per_s": visits / (k_avg_ms / 1e3), "csr_MB": csr_mb, "random_gather_rate_measured": ceiling,
+              "frac_of_gather_rate": visits / (k_avg_ms / 1e3) / ceiling,
+              "regime": "instruction issue (CSR inside the L2)" if csr_mb <= 100 else "random DRAM sector gathers",
+              "source": "profiles/r1_gather_micro.txt (L2-resident 285 G/s, 243 MB 78 G/s, 1 GB 42 G/s)"}
     return {"bound": "hbm", "kernel": "gset_sample_kernel", "achieved": achieved, "peak": c.peaks["hbm_gbs"],
             "unit": "GB/s", "frac": achieved / c.peaks["hbm_gbs"], "traffic": load_traffic("gset_sample", c.args),
             "peak_source": c.peaks["source"], "algorithmic_bytes_per_launch": alg_bytes,
             "kernel_ms_per_launch": k_avg_ms, "kernel_share_of_step": k_ms / ms_total,
-            "spg_build_ms_per_step": b_ms / steps, "avg_set_size": T_avg / max(n_seeds, 1), "unique_lp_rows": int(lp_rows)}
+            "spg_build_ms_per_step": b_ms / steps, "avg_set_size": T_avg / max(n_seeds, 1), "unique_lp_rows": int(lp_rows),
+            "gather": gather}
 
 
 def bench_single(c, with_clocks=True):
@@ -622,8 +633,10 @@ def bench_ppr(c):
     d = c.deg[c.deg > 0].astype(np.float64)
     deg_push = float((d * d).sum() / d.sum())
     alg = pushes / steps * (8 + 8 * deg_push) + 8.0 * x.T
-    k_avg = k_ms / max(k_n, 1)
-    per_launch = alg / max(k_n / steps, 1)
+    # one launch of ppr_push_fast_kernel takes every seed of the step; the general kernel's one or two small relaunches (the
+    # handful of seeds that outgrew the fast path) are counted into the same time
+    k_avg = k_ms / steps
+    per_launch = alg
     ach = per_launch / (k_avg / 1e3) / 1e9
     roof = {"bound": "hbm", "kernel": "ppr_push_fast_kernel (+ ppr_push_kernel for the seeds that outgrow its shared-memory queue / p-list)", "achieved": ach, "peak": c.peaks["hbm_gbs"], "unit": "GB/s",
             "frac": ach / c.peaks["hbm_gbs"], "traffic": load_traffic("ppr_push", args), "peak_source": c.peaks["source"],

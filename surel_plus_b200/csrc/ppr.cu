@@ -1067,7 +1067,7 @@ int ppr_topk_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, float alph
         CKG(cudaStreamSynchronize(st));
         s->T = T; s->rowbeg = s->indptr; s->extent = T; s->cap = T;
         CKG(dmalloc(&s->indices, (size_t)T + 16, st));
-        CKG(cudaMallocAsync(&s->data, ((size_t)T + 16) * 8, st));
+        CKG(dmalloc((unsigned char **)&s->data, ((size_t)T + 16) * 8, st));   // multi-GB at full size: the block cache, not the driver pool
         if (n > 0) {
             const int64_t blocks = std::min<int64_t>((n * 32 + 255) / 256, 8 * (int64_t)g->num_sms);
             ppr_assemble_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), 256, 0, st>>>(
@@ -1116,7 +1116,7 @@ int spg_encode_impl(const Graph *g, const SpG *x, int encoder, cudaStream_t st, 
             // x.data = (x.data + 0.1) / (x.data.max() + 0.1)                      utils.py:36
             CKG(dmalloc(&s->indptr, (size_t)n + 1, st));
             CKG(dmalloc(&s->indices, (size_t)T + 16, st));
-            CKG(cudaMallocAsync(&s->data, ((size_t)T + 16) * 8, st));
+            CKG(dmalloc((unsigned char **)&s->data, ((size_t)T + 16) * 8, st));   // multi-GB at full size: the block cache, not the driver pool
             CKG(dmalloc(&mx_bits, 1, st));
             CKG(cudaMemsetAsync(mx_bits, 0, 8, st));
             CKG(cudaMemcpyAsync(s->indptr, x->indptr, ((size_t)n + 1) * 8, cudaMemcpyDeviceToDevice, st));
@@ -1164,7 +1164,7 @@ int spg_encode_impl(const Graph *g, const SpG *x, int encoder, cudaStream_t st, 
             CKG(cudaMemcpyAsync(&To, s->indptr + n, 8, cudaMemcpyDeviceToHost, st));
             CKG(cudaStreamSynchronize(st));
             CKG(dmalloc(&s->indices, (size_t)To + 16, st));
-            CKG(cudaMallocAsync(&s->data, ((size_t)To + 16) * 8, st));
+            CKG(dmalloc((unsigned char **)&s->data, ((size_t)To + 16) * 8, st));
             a.o_indptr = (const long long *)s->indptr; a.o_indices = s->indices; a.o_data = (double *)s->data;
             spd_fill_kernel<<<blocks, 128, smem, st>>>(a);
             CKG(cudaGetLastError());

@@ -835,7 +835,7 @@ int spg_from_csr_impl(const int64_t *indptr_hd, const int32_t *indices_hd, const
     const size_t vb = value_kind ? 8 : 4;
     cudaError_t e = dmalloc(&s->indptr, (size_t)n_rows + 1, st);
     if (e == cudaSuccess) e = dmalloc(&s->indices, (size_t)nnz + 16, st);
-    if (e == cudaSuccess) e = cudaMallocAsync(&s->data, ((size_t)nnz + 16) * vb, st);
+    if (e == cudaSuccess) e = dmalloc((unsigned char **)&s->data, ((size_t)nnz + 16) * vb, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(s->indptr, indptr_hd, ((size_t)n_rows + 1) * 8, cudaMemcpyDefault, st);
     if (e == cudaSuccess && nnz > 0) e = cudaMemcpyAsync(s->indices, indices_hd, (size_t)nnz * 4, cudaMemcpyDefault, st);
     if (e == cudaSuccess && nnz > 0) e = cudaMemcpyAsync(s->data, data_hd, (size_t)nnz * vb, cudaMemcpyDefault, st);
