@@ -253,7 +253,11 @@ int subg_spjoin(const subg_spg *s, const int64_t *edge_hd, int64_t B, int arity,
  *   out_dev     rows [0, N) of the layout of subg_spjoin_run; rows beyond N are not written
  *   indptr_dev  int64[nseg+1] segment pointers (train.py:21-30)      segid_dev  int64 rows' segment ids (want_segid)
  *   nrows_dev   int64[2] on the device: {N, bad-node flag}
- * A slot is reused after `depth` submits: consume (or copy) its buffers on the same stream before that.
+ * Host-edge batches alternate between two streams owned by the joiner (the plan kernel of batch k+1 and the PCIe read of
+ * its edges run beside the join kernel of batch k; SUBG_JOIN_LANES=1 keeps everything on `stream`); each runs behind
+ * `stream` as of the PREVIOUS submit, and `stream` is made to wait for the batch, so consumers simply use the buffers on
+ * `stream`.  A slot is reused after `depth` submits: queue the work that reads its buffers on `stream` before the
+ * (depth - 1)-th following submit (depth 3: submit(k), consume(k), or one batch of prefetch).
  * rows waits for the slot's last batch and returns N; SUBG_ERR_MEM if N exceeded capacity_rows (the batch was not
  * joined: run it through subg_spjoin), SUBG_ERR_ARG if a node id was outside the SpG.
  * The SpG must outlive the joiner and must not be compacted (subg_spg_views) while it exists. */

@@ -35,7 +35,7 @@ constexpr uint64_t kEmptyKey = ~0ull;
 constexpr uint32_t kStatusTableFull = 1u << 31;  // internal status bits
 constexpr uint32_t kStatusBadSeed = 1u << 30;
 constexpr int kFirstHopCap = 1000000;  // NEBMAX, subg_acc.c:13,750
-constexpr int kGW = 8;                 // walks advanced together per lane
+constexpr int kGW = 8;                 // walks advanced together per lane (template GW: 8, or 4 when num_walks <= 128)
 constexpr int kCtrCursor = 16, kCtrTotal = 32, kCtrWords = 48;
 
 struct SamplerArgs {
@@ -349,7 +349,10 @@ constexpr int sampler_min_blocks() {
 // LEAN = true: additionally no first-visit ranks, no bucket cap (stride >= M*m+1) and LP rows of at most 32 bits -- the
 // configuration subg_matrix runs in -- with those paths compiled out (the kernel is bound by instruction issue and
 // fetch: every kilobyte of SASS that is not executed still competes for the instruction caches).
-template <typename K, int EPL, bool PARITY, bool LEAN>
+// GW: walks a lane advances together.  A lane owns ceil(M / 32) walks; with M <= 128 the slots 4..7 of a group of 8 would
+// never hold a walk but would still run their share of the Philox calls and address arithmetic (dblp / twitter shapes,
+// M = 100: a quarter of the kernel's instructions).  The Philox counters do not depend on GW: same walks either way.
+template <typename K, int EPL, bool PARITY, bool LEAN, int GW = kGW>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL>()) gset_sample_kernel(const SamplerArgs a) {
     using Acc = std::conditional_t<LEAN, uint32_t, unsigned long long>;   // packed landing counts of one member
     const int stop_after = LEAN ? 0 : a.stop_after;                      // the measurement hooks are not in the lean kernel
@@ -471,14 +474,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
                 calls0 += M;
             }
 
-            // Walks are advanced in groups of kGW per lane: all loads of one hop of a group are
-            // issued back to back (kGW x 32 gathers in flight per warp).
+            // Walks are advanced in groups of GW per lane: all loads of one hop of a group are
+            // issued back to back (GW x 32 gathers in flight per warp).
             const int rstep = d > 0 ? 32 % d : 0;   // w % d for w = lane + 32 t, kept incrementally
             int rr0 = d > 0 ? lane % d : 0;
-            for (int g = 0; g * 32 < M; g += kGW) {
-                uint32_t cur[kGW];
+            for (int g = 0; g * 32 < M; g += GW) {
+                uint32_t cur[GW];
 #pragma unroll
-                for (int tt = 0; tt < kGW; tt++) {
+                for (int tt = 0; tt < GW; tt++) {
                     const int w = lane + 32 * (g + tt);
                     cur[tt] = (uint32_t)u;
                     if (w < M && d > 0) {
@@ -495,22 +498,22 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
                     }
                 }
                 // ---- later hops, uniform with replacement (subg_acc.c:802-809)
-                uint32_t rst[kGW];
+                uint32_t rst[GW];
                 if (replay && m > 1) {
 #pragma unroll
-                    for (int tt = 0; tt < kGW; tt++) {
+                    for (int tt = 0; tt < GW; tt++) {
                         const int w = lane + 32 * (g + tt);
                         rst[tt] = lcg_jump(a.rng_lo, 3u * (uint32_t)(calls0 + (int64_t)w * (m - 1)));
                     }
                 }
                 for (int s = 1; s < m; s++) {
-                    uint2 raw[kGW];
+                    uint2 raw[GW];
 #pragma unroll
-                    for (int tt = 0; tt < kGW; tt++) raw[tt] = load_row_raw(a, pol, cur[tt]);
-                    uint32_t draw[kGW];
+                    for (int tt = 0; tt < GW; tt++) raw[tt] = load_row_raw(a, pol, cur[tt]);
+                    uint32_t draw[GW];
                     if (!replay) {  // one Philox call = this hop of four walks
 #pragma unroll
-                        for (int c = 0; c < kGW / 4; c++) {
+                        for (int c = 0; c < GW / 4; c++) {
                             const uint4 r4 = philox4x32_10(
                                 make_uint4(gi_lo, gi_hi, (uint32_t)(lane + 8 * g + 32 * c) | ((uint32_t)s << 16), 0x57414c4bu),
                                 make_uint2(a.rng_lo, a.rng_hi));
@@ -518,7 +521,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
                         }
                     }
 #pragma unroll
-                    for (int tt = 0; tt < kGW; tt++) {
+                    for (int tt = 0; tt < GW; tt++) {
                         const int w = lane + 32 * (g + tt);
                         if (w < M) {
                             int64_t rp;
