@@ -282,6 +282,70 @@ __device__ __forceinline__ void warp_merge_sort(K (&k)[EPL], K *buf, int lane) {
 #endif
 }
 
+// Power-of-two EPL: bitonic sort of the 32*EPL keys entirely in registers -- in-lane compare-exchanges for strides below
+// EPL, one shuffle per key for the strides that cross lanes.  Written in the all-ascending form (the first step of every
+// merge pairs i with i ^ (size - 1), the later steps i with i ^ stride), so no comparator needs a direction flag: the lower
+// index keeps the minimum (a predicated VIMNMX).  Same blocked layout in and out as warp_merge_sort, no shared memory, no
+// searches: at 8 keys per lane 36 steps of 8 two-instruction operations against five merge-path rounds (binary search +
+// serial merge each).  The steps that cross lanes differ only in the lane mask, so they are ROLLED loops over one code
+// block each (fully unrolled, the 16-key network alone is 24 KB of SASS and the kernel waits on instruction fetch:
+// stalled_no_instruction 4.5, profiles/r3a_sampler_collab.txt); only the in-lane steps are unrolled.
+template <typename K, int EPL>
+__device__ __forceinline__ void bitonic_inlane_halving(K (&k)[EPL], int first_stride) {
+#pragma unroll
+    for (int stride = EPL / 2; stride >= 1; stride >>= 1) {
+        if (stride <= first_stride) {
+#pragma unroll
+            for (int j = 0; j < EPL; j++) {
+                const int p = j ^ stride;
+                if (p > j) cswap(k[j], k[p]);
+            }
+        }
+    }
+}
+template <typename K, int EPL>
+__device__ __forceinline__ void warp_bitonic_sort(K (&k)[EPL], int lane) {
+    static_assert((EPL & (EPL - 1)) == 0, "EPL must be a power of two");
+    // merges of size 2 .. EPL stay inside the lane
+#pragma unroll
+    for (int size = 2; size <= EPL; size <<= 1) {
+#pragma unroll
+        for (int j = 0; j < EPL; j++) {
+            const int p = j ^ (size - 1);
+            if (p > j) cswap(k[j], k[p]);
+        }
+        bitonic_inlane_halving<K, EPL>(k, size / 4);
+    }
+    // merges of size 2 EPL .. 32 EPL: lanes per merge lm2 = 2, 4, .., 32
+#pragma unroll 1
+    for (int lm2 = 2; lm2 <= 32; lm2 <<= 1) {
+        {   // flip step: lane ^ (lm2 - 1), register EPL - 1 - j
+            const bool lower = (lane & (lm2 >> 1)) == 0;
+            K o[EPL];
+#pragma unroll
+            for (int j = 0; j < EPL; j++) o[j] = __shfl_xor_sync(FULL, k[EPL - 1 - j], lm2 - 1);
+#pragma unroll
+            for (int j = 0; j < EPL; j++) {
+                const K mn = k[j] < o[j] ? k[j] : o[j];
+                const K mx = k[j] < o[j] ? o[j] : k[j];
+                k[j] = lower ? mn : mx;
+            }
+        }
+#pragma unroll 1
+        for (int lm = lm2 >> 2; lm >= 1; lm >>= 1) {   // halving steps that cross lanes: lane ^ lm, same register
+            const bool lower = (lane & lm) == 0;
+#pragma unroll
+            for (int j = 0; j < EPL; j++) {
+                const K o = __shfl_xor_sync(FULL, k[j], lm);
+                const K mn = k[j] < o ? k[j] : o;
+                const K mx = k[j] < o ? o : k[j];
+                k[j] = lower ? mn : mx;
+            }
+        }
+        bitonic_inlane_halving<K, EPL>(k, EPL / 2);
+    }
+}
+
 template <typename T>
 __device__ __forceinline__ T warp_incl_scan_acc(T v) {
 #pragma unroll
@@ -551,7 +615,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
 #pragma unroll
         for (int r = 0; r < EPL; r++) k[r] = keys[lane * EPL + r];
         __syncwarp();
-        warp_merge_sort<K, EPL>(k, keys, lane);
+        if constexpr ((EPL & (EPL - 1)) == 0 && sizeof(K) == 4) warp_bitonic_sort<K, EPL>(k, lane);
+        else warp_merge_sort<K, EPL>(k, keys, lane);
         if (stop_after == 2) {
             if (k[0] == 1 && lane == 33) a.nsize[i] = 0;  // keep the sort alive
             continue;

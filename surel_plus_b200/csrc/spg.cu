@@ -39,6 +39,11 @@ static cudaError_t launch_gset_sample_k64(const SamplerArgs &a, int EPL, int num
     return launch_gset_sample_k64d(a, EPL, num_sms, st);
 }
 static const int kEplList[] = {3, 5, 7, 9, 11, 13, 15, 17, 19, 21, 25, 29, 33, 41, 49, 63};
+// keys per lane that are a power of two sort with the register bitonic network instead of the merge path; taken when the
+// seed's keys fit 128 / 256 slots (SUBG_SAMPLER_POW2=0: measurement only).  Measured (profiles/r2_sampler_sweeps.txt): dblp
+// shape, 201 keys: EPL 8 bitonic 4.15 ms against EPL 7 merge path 4.89 ms; collab shape, 401 keys: EPL 16 bitonic 1.22 ms
+// against EPL 13 merge path 1.02 ms (the padding to 512 slots eats the saving), so 16 is not offered.
+static const int kEplPow2[] = {4, 8};
 
 static int ceil_log2(uint64_t x) {
     int b = 0;
@@ -307,6 +312,11 @@ static int make_plan(const Graph *g, int M, int m, int bucket, SamplePlan *p) {
     const uint32_t max_ord = ((uint32_t)M << p->LS) | (uint32_t)(m - 1);
     p->OB = ceil_log2((uint64_t)max_ord + 1);
     p->key64 = !((uint64_t)g->N <= (1ull << (32 - p->OB)) - 1ull);
+    // 32-bit keys that fit 128 / 256 slots: a power-of-two EPL sorts with the register bitonic network (64-bit keys
+    // cost two shuffles and a multi-instruction compare per step: twitter shape 168 -> 243 ms, so they keep the merge path)
+    if (!p->key64 && Kt > 96 && env_i64("SUBG_SAMPLER_POW2", 1) != 0)
+        for (int e : kEplPow2)
+            if (32 * e >= Kt) { p->EPL = e; break; }
     const int ksz = p->key64 ? 8 : 4;
     p->stride = bucket < 0 ? (int)Kt : bucket;
     p->rowcap = (std::min(p->stride, (int)Kt) + 3) & ~3;

@@ -139,11 +139,12 @@ def staged_h2d(arr: np.ndarray, device) -> torch.Tensor:
         out.copy_(torch.from_numpy(a))
         return out
     if _copy_pool is None:
-        _copy_pool = ThreadPoolExecutor(max_workers=min(6, max(2, (os.cpu_count() or 4) // 2)))
+        nthr = int(os.environ.get("SUBG_COPY_THREADS", "0")) or min(6, max(2, (os.cpu_count() or 4) // 2))
+        _copy_pool = ThreadPoolExecutor(max_workers=nthr)
     stage = pinned_empty((flat.size,), np.uint8)
     stage_t = torch.from_numpy(stage)
     dst = out.reshape(-1).view(torch.uint8)
-    CH = 8 << 20
+    CH = int(os.environ.get("SUBG_COPY_CHUNK_MB", "8")) << 20
     futs = [(lo, min(lo + CH, flat.size), _copy_pool.submit(np.copyto, stage[lo:min(lo + CH, flat.size)], flat[lo:min(lo + CH, flat.size)]))
             for lo in range(0, flat.size, CH)]
     for lo, hi, f in futs:
