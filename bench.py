@@ -411,8 +411,12 @@ def sampler_roofline(c, deg, M, m, T_avg, n_seeds, k_ms, k_launches, b_ms, steps
     visits = float(live) * M * m + n_seeds
     csr_mb = (4.0 * float(c.graph.E) + 8.0 * float(c.graph.N)) / 2 ** 20
     ceiling = 285e9 if csr_mb <= 100 else (78e9 if csr_mb <= 400 else 42e9)
-    gather = {"visits_per_s": visits / (k_avg_ms / 1e3), "csr_MB": csr_mb, "random_gather_rate_measured": ceiling,
-              "frac_of_gather_rate": visits / (k_avg_ms / 1e3) / ceiling,
+    later = float(live) * M * (m - 1)   # hops 2..m: row info of a random node, then a uniformly random entry of its row
+    gather = {"visits_per_s": visits / (k_avg_ms / 1e3), "random_column_gathers_per_s": later / (k_avg_ms / 1e3),
+              "csr_MB": csr_mb, "random_gather_rate_measured": ceiling,
+              "frac_of_gather_rate": later / (k_avg_ms / 1e3) / ceiling,
+              "what": "gathers of the later hops only (the first hop reads the seed's own row) over the rate of plain random "
+                      "4-byte gathers from an array of the CSR's size with nothing else in the kernel",
               "regime": "instruction issue (CSR inside the L2)" if csr_mb <= 100 else "random DRAM sector gathers",
               "source": "profiles/r1_gather_micro.txt (L2-resident 285 G/s, 243 MB 78 G/s, 1 GB 42 G/s)"}
     return {"bound": "hbm", "kernel": "gset_sample_kernel", "achieved": achieved, "peak": c.peaks["hbm_gbs"],

@@ -353,6 +353,15 @@ int subg_timing_enable(int enable);
 int subg_timing_read(int which, double *ms, int64_t *launches);
 int64_t subg_launch_count(void);
 
+/* Replaces batch_sampler (subg_acc/subg_acc.c:391-507), the serial walk-based mini-batch node sampler: for every query node
+ * in order, up to num_walks walks of num_steps nodes (first hop without replacement, later hops uniform); a seed stops as
+ * soon as the batch holds (i + 1) * thld / n distinct nodes.  One rand_r stream starting at rng_state (the reference seeds
+ * it with seed + getpid(), :423): same state, same batch, bit for bit.  out_hd (host or device, `capacity` entries)
+ * receives the distinct nodes in insertion order, *count_out their number; SUBG_ERR_MEM if capacity was too small (an upper
+ * bound is min(N, n * (num_walks * num_steps + 1))).  One warp replays the stream; synchronises the stream. */
+int subg_batch_sample(const subg_graph *g, const int32_t *seeds_hd, int64_t n, int num_walks, int num_steps, int thld,
+                      uint32_t rng_state, int32_t *out_hd, int64_t capacity, int64_t *count_out, void *stream);
+
 /* The library keeps freed device blocks of 64 MB and more (SpG row arrays, sampler staging) in a per-process cache and
  * hands them out again (SUBG_BLOCK_CACHE_BYTES caps it, default 45 % of the device memory).  subg_trim_cache returns
  * every cached block to the driver and reports the bytes released. */

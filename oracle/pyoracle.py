@@ -63,6 +63,8 @@ def lib() -> C.CDLL:
     L.orc_walk_join.argtypes = [_i32p, C.c_int64, C.c_int64, _i64p, _i32p, _i32p, C.c_int64, _i32p, _i32p]
     L.orc_rpe_encode.restype = C.c_int64
     L.orc_rpe_encode.argtypes = [_i32p, C.c_int64, C.c_int, C.c_int, _i64p, _i32p, _i32p, C.c_int64]
+    L.orc_batch_sampler.restype = C.c_int64
+    L.orc_batch_sampler.argtypes = [_i64p, _i32p, C.c_int64, _i32p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_uint32, _i32p, C.c_int64]
     _lib = L
     return L
 
@@ -393,3 +395,17 @@ def encoding_spd(x, adj):
     out = out.tocsr()
     out.sort_indices()
     return out
+
+
+def batch_sampler(ptr, neighs, query, num_walks=200, num_steps=8, thld=1000, seed=111413, pid=0):
+    """batch_sampler (subg_acc.c:391-507): distinct nodes, in insertion order, of the serial walk-based mini-batch
+    sampler; the rand_r stream starts at seed + pid (the reference adds getpid(), :423)."""
+    ptr = _c(ptr, np.int64)
+    neighs = _c(neighs, np.int32)
+    query = _c(np.asarray(query).reshape(-1), np.int32)
+    N = len(ptr) - 1
+    cap = int(min(N, len(query) * (num_walks * num_steps + 1))) + 1
+    out = np.empty(cap, np.int32)
+    cnt = lib().orc_batch_sampler(ptr, neighs, N, query, len(query), num_walks, num_steps, thld, (seed + pid) & 0xFFFFFFFF, out, cap)
+    assert cnt >= 0, cnt
+    return out[:cnt].copy()

@@ -700,3 +700,77 @@ int orc_walk_join(const int32_t *walks, int64_t n, int64_t stride, const int64_t
     idmap_free(&members);
     return 0;
 }
+
+/* ------------------------------------------------------------------------- */
+/* batch_sampler (subg_acc.c:391-507): the serial mini-batch node sampler.    */
+/* One rand_r stream (the reference seeds it with seed + getpid(), :423; the  */
+/* caller passes that sum).  For every query node in order: a partial Fisher- */
+/* Yates over its neighbours if it has more than num_walks of them (:430-441; */
+/* num_walks draws, before any walk), the node itself joins the batch (:443), */
+/* then up to num_walks walks of num_steps nodes each (first hop w % deg or   */
+/* the shuffled pick, later hops uniform with replacement, a hop from a node  */
+/* without neighbours is skipped without a draw, :445-470); after every walk  */
+/* the seed stops as soon as the batch holds (i + 1) * thld / n distinct      */
+/* nodes (:472-473, int arithmetic).  Output: the distinct nodes in insertion */
+/* order (uthash iterates in insertion order, :484-490).  N = node count      */
+/* (sizes the seen map).  Returns the count, or -1 if it exceeds cap.         */
+/* ------------------------------------------------------------------------- */
+int64_t orc_batch_sampler(const int64_t *rowptr, const int32_t *col, int64_t N,
+                          const int32_t *query, int64_t n, int num_walks, int num_steps, int thld,
+                          uint32_t state, int32_t *out, int64_t cap)
+{
+    unsigned char *seen = (unsigned char *)calloc((size_t)(N > 0 ? N : 1), 1);
+    int32_t *rseq = NULL;
+    int64_t rcap = 0, count = 0;
+    int overflow = 0;
+    if (!seen) return -2;
+#define ORC_ADD(v)                                         \
+    do {                                                   \
+        const int32_t _v = (v);                            \
+        if (!seen[_v]) {                                   \
+            seen[_v] = 1;                                  \
+            if (count < cap) out[count] = _v;              \
+            else overflow = 1;                             \
+            count++;                                       \
+        }                                                  \
+    } while (0)
+    for (int64_t i = 0; i < n; i++) {
+        const int32_t u = query[i];
+        const int64_t hop1 = rowptr[u + 1] - rowptr[u];
+        if (hop1 > num_walks) {
+            if (hop1 > rcap) {
+                free(rseq);
+                rcap = hop1;
+                rseq = (int32_t *)malloc((size_t)rcap * sizeof(int32_t));
+                if (!rseq) { free(seen); return -2; }
+            }
+            for (int64_t j = 0; j < hop1; j++) rseq[j] = (int32_t)j;
+            for (int k = 0; k < num_walks; k++) {
+                const int64_t s = (int64_t)((uint32_t)orc_rand_r(&state) % (uint32_t)(hop1 - k)) + k;
+                const int32_t t = rseq[k];
+                rseq[k] = rseq[s];
+                rseq[s] = t;
+            }
+        }
+        ORC_ADD(u);
+        for (int walk = 0; walk < num_walks; walk++) {
+            int32_t curr = u;
+            if (hop1 < 1) break;
+            else if (hop1 <= num_walks) curr = col[rowptr[curr] + walk % hop1];
+            else curr = col[rowptr[curr] + rseq[walk]];
+            ORC_ADD(curr);
+            for (int step = 1; step < num_steps; step++) {
+                const int64_t nn = rowptr[curr + 1] - rowptr[curr];
+                if (nn > 0) {
+                    curr = col[rowptr[curr] + (int64_t)((uint32_t)orc_rand_r(&state) % (uint32_t)nn)];
+                    ORC_ADD(curr);
+                }
+            }
+            if ((int)count >= (int)((i + 1) * (int64_t)thld / n)) break;
+        }
+    }
+#undef ORC_ADD
+    free(seen);
+    free(rseq);
+    return overflow ? -1 : count;
+}

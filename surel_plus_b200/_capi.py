@@ -29,7 +29,7 @@ SYMBOLS = [
     "subg_spjoin_plan", "subg_spjoin_run", "subg_spjoin",
     "subg_joiner_create", "subg_joiner_submit", "subg_joiner_rows", "subg_joiner_free",
     "subg_ppr_topk", "subg_spg_encode", "subg_spg_pushes",
-    "subg_walk_sample", "subg_walkset_info", "subg_walkset_export", "subg_walkset_views", "subg_walkset_free", "subg_walk_join",
+    "subg_walk_sample", "subg_walkset_info", "subg_walkset_export", "subg_walkset_views", "subg_walkset_free", "subg_walk_join", "subg_batch_sample",
     "subg_timing_enable", "subg_timing_read", "subg_launch_count",
     "subg_trim_cache", "subg_host_alloc", "subg_host_free",
 ]
@@ -103,6 +103,7 @@ def load() -> C.CDLL:
     L.subg_walkset_free.argtypes = [vp]
     L.subg_walkset_free.restype = None
     L.subg_walk_join.argtypes = [vp, i64, i64, vp, vp, vp, i64, vp, vp, i32, vp]
+    L.subg_batch_sample.argtypes = [vp, vp, i64, i32, i32, i32, C.c_uint32, vp, i64, C.POINTER(i64), vp]
     L.subg_timing_enable.argtypes = [i32]
     L.subg_timing_read.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(i64)]
     L.subg_launch_count.restype = i64

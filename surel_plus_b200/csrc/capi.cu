@@ -217,6 +217,8 @@ int walkset_export_impl(const WalkSet *w, int32_t *walks_hd, int64_t *off_hd, in
 int walkset_info_impl(const WalkSet *w, int64_t *n, int64_t *T, int32_t *M, int32_t *ncol, uint32_t *status);
 int walkset_views_impl(const WalkSet *w, const int32_t **walks, const int64_t **off, const int32_t **ids, const int32_t **rpe);
 void walkset_free_impl(WalkSet *w);
+int batch_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, int M, int m, int thld, uint32_t state, int32_t *out_hd,
+                      int64_t cap, int64_t *count_out, cudaStream_t st);
 int walk_join_impl(const int32_t *walks_hd, int64_t n, int64_t stride, const int64_t *key_off_hd, const int32_t *key_ids_hd,
                    const int32_t *query_hd, int64_t Q, int32_t *out_hd, int32_t *xq_hd, int device, cudaStream_t st);
 
@@ -592,6 +594,12 @@ int subg_walk_join(const int32_t *walks_hd, int64_t n, int64_t stride, const int
                    const int32_t *query_hd, int64_t Q, int32_t *out_hd, int32_t *xq_hd, int device, void *stream) {
     if (int rc = init_device(device)) return rc;
     return walk_join_impl(walks_hd, n, stride, key_off_hd, key_ids_hd, query_hd, Q, out_hd, xq_hd, device, (cudaStream_t)stream);
+}
+
+int subg_batch_sample(const subg_graph *g, const int32_t *seeds_hd, int64_t n, int num_walks, int num_steps, int thld,
+                      uint32_t rng_state, int32_t *out_hd, int64_t capacity, int64_t *count_out, void *stream) {
+    return batch_sample_impl(reinterpret_cast<const Graph *>(g), seeds_hd, n, num_walks, num_steps, thld, rng_state, out_hd, capacity,
+                             count_out, (cudaStream_t)stream);
 }
 
 int64_t subg_trim_cache(void) { return (int64_t)big_trim(); }

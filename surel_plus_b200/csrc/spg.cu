@@ -635,8 +635,19 @@ int gset_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n_all, int
         prof.mark("unique_launch");
         // No synchronisation here: the id remap is still in flight; everything that touches the SpG later
         // (SpJoin, export, views, free) is ordered behind it on the stream.
-        // A mostly empty worst-case allocation is not worth keeping
-        if (!s->indptr && !(flags & SUBG_SAMPLE_NO_COMPACT) && cap > s->extent + s->extent / 4 + (16ll << 20)) {
+        // A mostly empty worst-case allocation is compacted only when the slack is a sizeable share of the device (default:
+        // more than 15 % of its memory, SUBG_COMPACT_SLACK_PCT): SpJoin and the exchange read the scattered rows in place, and
+        // the copy costs a pass over the SpG (dblp shape: 0.4 ms of a 5 ms pass for 2.3 GB of slack; twitter shape: 33 ms of
+        // 255 ms for 24 GB of slack on a 180 GB device)
+        static size_t total_by_device[64] = {};   // cudaMemGetInfo costs milliseconds once large blocks are cached: ask once
+        size_t &mem_total = total_by_device[g->device & 63];
+        if (mem_total == 0) {
+            size_t mem_free = 0;
+            cudaMemGetInfo(&mem_free, &mem_total);
+        }
+        const int64_t slack_bytes = (cap - s->extent) * (int64_t)(want_slot ? 10 : 8);
+        const int64_t slack_limit = (int64_t)((double)mem_total * (double)env_i64("SUBG_COMPACT_SLACK_PCT", 15) / 100.0);
+        if (!s->indptr && !(flags & SUBG_SAMPLE_NO_COMPACT) && cap > s->extent + s->extent / 4 + (16ll << 20) && slack_bytes > slack_limit) {
             timing_begin(SUBG_TIMING_BUILD, st);
             const int erc = spg_ensure_csr(s, st);
             timing_end(SUBG_TIMING_BUILD, st);

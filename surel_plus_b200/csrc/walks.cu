@@ -591,6 +591,142 @@ done:
     return rc;
 }
 
+// ------------------------------------------------------------------ batch_sampler (subg_acc.c:391-507)
+// The reference's serial mini-batch node sampler: ONE rand_r stream, and every seed's early exit depends on the running
+// number of distinct nodes over all seeds before it, so the walk order is part of the result.  One warp replays it: lane 0
+// owns the stream and the walks (a chain of dependent draws), all lanes initialise the Fisher-Yates index array of a seed
+// with more than num_walks neighbours.  The batch is a bitmap over the nodes plus the list of distinct nodes in insertion
+// order (what uthash's iteration returns, subg_acc.c:484-490).  No caller in the reference and no parallelism to speak of:
+// provided for drop-in completeness, bit-exact given the stream's start (seed + pid).
+namespace {
+__global__ void batch_sample_kernel(const void *rowptr, int rowptr64, const int32_t *col, const int32_t *seeds, int64_t n, int64_t N,
+                                    int M, int m, int thld, uint32_t state, uint32_t *seen, int32_t *rseq, int32_t *out,
+                                    int64_t cap, long long *result) {
+    const int lane = threadIdx.x;
+    long long count = 0;
+    bool bad = false;
+    auto row = [&](int64_t v) -> int64_t {
+        return rowptr64 ? (int64_t)((const long long *)rowptr)[v] : (int64_t)((const int32_t *)rowptr)[v];
+    };
+    auto add = [&](int32_t v) {   // lane 0 only
+        const uint32_t bit = 1u << (v & 31);
+        if (!(seen[v >> 5] & bit)) {
+            seen[v >> 5] |= bit;
+            if (count < cap) out[count] = v;
+            count++;
+        }
+    };
+    for (int64_t i = 0; i < n; i++) {
+        const int32_t u = seeds[i];
+        if ((uint64_t)(int64_t)u >= (uint64_t)N) { bad = true; break; }
+        const int64_t r0 = row(u);
+        const int64_t hop1 = row((int64_t)u + 1) - r0;
+        if (hop1 > M) {   // partial Fisher-Yates, num_walks draws (subg_acc.c:430-441)
+            for (int64_t j = lane; j < hop1; j += 32) rseq[j] = (int32_t)j;
+            __syncwarp();
+            if (lane == 0) {
+                for (int k = 0; k < M; k++) {
+                    const int64_t sidx = (int64_t)(rand_r_dev(state) % (uint32_t)(hop1 - k)) + k;
+                    const int32_t t = rseq[k];
+                    rseq[k] = rseq[sidx];
+                    rseq[sidx] = t;
+                }
+            }
+        }
+        if (lane == 0) {
+            add(u);
+            for (int walk = 0; walk < M; walk++) {
+                if (hop1 < 1) break;
+                int32_t curr = hop1 <= M ? col[r0 + walk % hop1] : col[r0 + rseq[walk]];
+                add(curr);
+                for (int step = 1; step < m; step++) {
+                    const int64_t c0 = row(curr);
+                    const int64_t nn = row((int64_t)curr + 1) - c0;
+                    if (nn > 0) {
+                        curr = col[c0 + (int64_t)(rand_r_dev(state) % (uint32_t)nn)];
+                        add(curr);
+                    }
+                }
+                if ((int)count >= (int)((i + 1) * (int64_t)thld / n)) break;   // subg_acc.c:472 (int arithmetic)
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        result[0] = count;
+        result[1] = bad ? 1 : 0;
+    }
+}
+__global__ void max_degree_kernel(const void *rowptr, int rowptr64, const int32_t *seeds, int64_t n, int64_t N, unsigned long long *out) {
+    unsigned long long mx = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t u = seeds[i];
+        if (u < 0 || u >= N) continue;
+        const int64_t d = rowptr64 ? ((const long long *)rowptr)[u + 1] - ((const long long *)rowptr)[u]
+                                   : (int64_t)((const int32_t *)rowptr)[u + 1] - ((const int32_t *)rowptr)[u];
+        mx = max(mx, (unsigned long long)d);
+    }
+    if (mx) atomicMax(out, mx);
+}
+}  // namespace
+
+// out_hd: host or device int32[cap]; *count_out = distinct nodes (may exceed cap: then SUBG_ERR_MEM and nothing useful in out)
+int batch_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, int M, int m, int thld, uint32_t state, int32_t *out_hd,
+                      int64_t cap, int64_t *count_out, cudaStream_t st) {
+    if (!g || n < 0 || (n > 0 && !seeds_hd) || M < 1 || m < 1 || cap < 0 || (cap > 0 && !out_hd) || !count_out)
+        return fail(SUBG_ERR_ARG, "Input parsing error.");
+    DeviceGuard guard(g->device);
+    g->tag.use_on(st);
+    *count_out = 0;
+    if (n == 0) return SUBG_OK;
+    int32_t *d_seeds = nullptr, *d_rseq = nullptr, *d_out = nullptr;
+    uint32_t *d_seen = nullptr;
+    long long *d_res = nullptr;
+    unsigned long long *d_mx = nullptr;
+    int rc = SUBG_OK;
+    cudaError_t e = cudaSuccess;
+    long long hres[2] = {0, 0};
+    unsigned long long hmx = 0;
+#define BK(call)                                                                                   \
+    do {                                                                                           \
+        e = (call);                                                                                \
+        if (e != cudaSuccess) {                                                                    \
+            rc = fail(e == cudaErrorMemoryAllocation ? SUBG_ERR_MEM : SUBG_ERR_CUDA,               \
+                      std::string(#call) + ": " + cudaGetErrorString(e));                          \
+            goto done;                                                                             \
+        }                                                                                          \
+    } while (0)
+    BK(dmalloc(&d_seeds, (size_t)n, st));
+    BK(cudaMemcpyAsync(d_seeds, seeds_hd, (size_t)n * 4, cudaMemcpyDefault, st));
+    BK(dmalloc(&d_mx, 1, st));
+    BK(cudaMemsetAsync(d_mx, 0, 8, st));
+    max_degree_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, st>>>(g->rowptr, g->rowptr64 ? 1 : 0, d_seeds, n, g->N, d_mx);
+    BK(cudaMemcpyAsync(&hmx, d_mx, 8, cudaMemcpyDeviceToHost, st));
+    BK(cudaStreamSynchronize(st));
+    BK(dmalloc(&d_rseq, (size_t)std::max<unsigned long long>(hmx, 1), st));
+    BK(dmalloc(&d_seen, (size_t)(g->N / 32 + 1), st));
+    BK(cudaMemsetAsync(d_seen, 0, (size_t)(g->N / 32 + 1) * 4, st));
+    BK(dmalloc(&d_out, (size_t)std::max<int64_t>(cap, 1), st));
+    BK(dmalloc(&d_res, 2, st));
+    batch_sample_kernel<<<1, 32, 0, st>>>(g->rowptr, g->rowptr64 ? 1 : 0, g->col, d_seeds, n, g->N, M, m, thld, state, d_seen, d_rseq,
+                                          d_out, cap, d_res);
+    BK(cudaGetLastError());
+    count_launch(2);
+    BK(cudaMemcpyAsync(hres, d_res, 16, cudaMemcpyDeviceToHost, st));
+    BK(cudaStreamSynchronize(st));
+    if (hres[1]) { rc = fail(SUBG_ERR_ARG, "query contains node ids outside [0, N)"); goto done; }
+    *count_out = hres[0];
+    if (hres[0] > cap) { rc = fail(SUBG_ERR_MEM, "batch_sampler: output capacity too small"); goto done; }
+    if (hres[0] > 0) {
+        BK(cudaMemcpyAsync(out_hd, d_out, (size_t)hres[0] * 4, cudaMemcpyDefault, st));
+        BK(cudaStreamSynchronize(st));
+    }
+done:
+#undef BK
+    dfree(d_seeds, st); dfree(d_rseq, st); dfree(d_seen, st); dfree(d_out, st); dfree(d_res, st); dfree(d_mx, st);
+    return rc;
+}
+
 int walkset_info_impl(const WalkSet *w, int64_t *n, int64_t *T, int32_t *M, int32_t *ncol, uint32_t *status) {
     if (!w) return fail(SUBG_ERR_ARG, "null walk set");
     if (n) *n = w->n;

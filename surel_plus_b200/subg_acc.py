@@ -165,8 +165,28 @@ def walk_join(walk, key, query, nthread=-1, return_idx=-1, device="cuda"):
     return [out, xq] if want else out
 
 
-def batch_sampler(*args, **kwargs):
-    """Serial mini-batch node sampler (subg_acc.c:391-507): no caller in the reference, every seed's early exit
-    depends on the running size of one shared node set, and the stream is seeded with seed + getpid()
-    (subg_acc.c:423), i.e. not reproducible; out of scope."""
-    raise NotImplementedError("batch_sampler is out of scope of the B200 hot path")
+def batch_sampler(ptr, neighs, query, num_walks=200, num_steps=8, thld=1000, nthread=-1, seed=111413, device="cuda", pid=None):
+    """subg_acc.c:391-507 (kwlist :397): the serial walk-based mini-batch node sampler.  Returns the int32 array of the
+    distinct nodes visited, in insertion order.  The reference seeds its single rand_r stream with seed + getpid()
+    (:423) -- so does this (`pid=` overrides the process id for reproducible runs): within one process the result equals
+    the reference's bit for bit (`subg_batch_sample`; one warp replays the stream on the device)."""
+    import ctypes as C
+    from .spg import _stream
+    del nthread  # the reference parses it and never uses it
+    if isinstance(ptr, DeviceGraph):
+        g, own = ptr, False
+    else:
+        g, own = DeviceGraph(np.asarray(ptr), np.asarray(neighs), device), True
+    try:
+        q = np.ascontiguousarray(np.asarray(query).reshape(-1), dtype=np.int32)
+        lib = _capi.load()
+        state = (int(seed) + (os.getpid() if pid is None else int(pid))) & 0xFFFFFFFF
+        cap = int(min(g.N, len(q) * (int(num_walks) * int(num_steps) + 1))) + 1
+        out = np.empty(cap, np.int32)
+        cnt = C.c_int64(0)
+        _capi.check(lib.subg_batch_sample(g._h, q.ctypes.data, len(q), int(num_walks), int(num_steps), int(thld), state,
+                                          out.ctypes.data, cap, C.byref(cnt), _stream(g.device)))
+        return out[:cnt.value].copy()
+    finally:
+        if own:
+            g.close()

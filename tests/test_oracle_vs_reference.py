@@ -147,3 +147,19 @@ def test_walk_join_vs_compiled_reference(subg, mid_graph, M, m, rep):
     out, xq = subg.walk_join(walks, list(obj[:, 0]), qq, return_idx=True)
     o_out, o_xq = po.walk_join(walks, list(obj[:, 0]), qq, return_idx=True)
     assert np.array_equal(out, o_out) and np.array_equal(xq, o_xq)
+
+
+@pytest.mark.parametrize("M,m,thld,nq", [(200, 8, 1000, 50), (20, 3, 100, 30), (5, 4, 400, 200), (300, 2, 50, 10),
+                                         (10, 1, 600, 605), (3, 5, 10 ** 6, 40)])
+def test_batch_sampler_oracle_equals_compiled_reference(small_graph, M, m, thld, nq):
+    """batch_sampler (subg_acc.c:391-507) seeds its stream with seed + getpid(): called in THIS process with the same
+    seed, the unmodified compiled reference and the oracle restatement return the same nodes in the same order
+    (hubs with more than num_walks neighbours, isolated nodes, thresholds that never / always cut the walks short)."""
+    import os
+    R = ref.subg_acc()
+    A = small_graph
+    ptr, nb = A.indptr.astype(np.int32), A.indices.astype(np.int32)
+    q = np.random.default_rng(M + nq).permutation(A.shape[0])[:nq].astype(np.int32)
+    want = R.batch_sampler(ptr, nb, q, num_walks=M, num_steps=m, thld=thld, seed=7)
+    got = po.batch_sampler(ptr, nb, q, M, m, thld, seed=7, pid=os.getpid())
+    assert np.array_equal(got, want)
