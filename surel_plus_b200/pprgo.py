@@ -38,7 +38,13 @@ def topk_ppr_matrix(adj_matrix, alpha, eps, idx, topk, normalization="row", devi
     q = np.ascontiguousarray(np.asarray(idx).astype(np.int32, copy=False))
     ndeg = None
     if not isinstance(adj_matrix, DeviceGraph) and normalization != "row":
-        ndeg = np.ascontiguousarray(np.asarray(adj_matrix.sum(1)).ravel(), dtype=np.float64)  # pprgo.py:89,99
+        # deg = adj.sum(1) (pprgo.py:89,99).  For an unweighted adjacency (every stored entry 1 / True: what the reference's
+        # loaders build) that is the row length, which the device has already; scipy's sum over 61 M entries is 0.3-0.5 s
+        # on the host, half of the whole call on the citation2 shape.  Anything else is summed as the reference does.
+        data = adj_matrix.data
+        uniform = bool(data.all()) if data.dtype == np.bool_ else bool((data == 1).all())
+        if not uniform:
+            ndeg = np.ascontiguousarray(np.asarray(adj_matrix.sum(1)).ravel(), dtype=np.float64)
     h = C.c_void_p()
     _capi.check(lib.subg_ppr_topk(graph._h, _ptr(q), q.size, C.c_float(np.float32(alpha)), C.c_float(np.float32(eps)),
                                   int(topk), _NORMS[normalization], _ptr(ndeg) if ndeg is not None else None,
