@@ -403,7 +403,10 @@ constexpr int sampler_min_blocks() {
     constexpr int smem_warp = ((int)sizeof(K) + 4) * 32 * EPL + 64 * (int)sizeof(K) + 256;
     constexpr int by_smem = 232448 / (kWarpsPerBlock * smem_warp);
     constexpr int by_regs = 65536 / (kWarpsPerBlock * 32 * (EPL * W + 52));
-    constexpr int b = by_smem < by_regs ? by_smem : by_regs;
+#ifndef SUBG_SAMPLER_EXTRA_BLOCK
+#define SUBG_SAMPLER_EXTRA_BLOCK 0   // experiment: ask the compiler for one more resident CTA than the register estimate gives
+#endif
+    constexpr int b = (by_smem < by_regs ? by_smem : by_regs) + SUBG_SAMPLER_EXTRA_BLOCK;
     return b < 1 ? 1 : (b > 8 ? 8 : b);
 }
 
