@@ -402,7 +402,9 @@ constexpr int sampler_min_blocks() {
     constexpr int W = (int)sizeof(K) / 4;
     constexpr int smem_warp = ((int)sizeof(K) + 4) * 32 * EPL + 64 * (int)sizeof(K) + 256;
     constexpr int by_smem = 232448 / (kWarpsPerBlock * smem_warp);
-    constexpr int by_regs = 65536 / (kWarpsPerBlock * 32 * (EPL * W + 52));
+    // registers the compiler is asked to fit: keys + 45 (19 keys per lane -> 64 registers; measured on ppa against 72: same 7
+    // resident CTAs, kernel 5.96 -> 5.79 ms, profiles/r2_sampler_sweeps.txt)
+    constexpr int by_regs = 65536 / (kWarpsPerBlock * 32 * (EPL * W + 45));
 #ifndef SUBG_SAMPLER_EXTRA_BLOCK
 #define SUBG_SAMPLER_EXTRA_BLOCK 0   // experiment: ask the compiler for one more resident CTA than the register estimate gives
 #endif
