@@ -263,7 +263,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "sampled_node_sets_per_sec", "value": val, "unit": "seeds/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_all / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "int32" if W["kind"] == "lp" else "f32", "data": "synthetic",
         "config": dict(workload_config(args, W, A.shape[0], A.nnz), reference_sample=sample),
         "cpu_baseline": {"value": val, "unit": "seeds/s", "cores": cores, "kind": kind, "sample": sample},
@@ -465,7 +465,8 @@ def bench_single(c, with_clocks=True):
     clk = c.clocks.stop() if c.rank == 0 and with_clocks else None
     T_avg = T_sum / args.steps
     roof = sampler_roofline(c, c.deg, M, m, T_avg, c.n, k_ms, k_launches, b_ms, args.steps, ms_total, spg.c)
-    head = {"value": c.world * c.n * args.steps / (ms_total / 1e3), "ms_per_step": ms_total / args.steps, "scaling": "weak",
+    # total work (one pass over all seeds) is the same at every N: the N = 1 point of the strong-scaling series
+    head = {"value": c.world * c.n * args.steps / (ms_total / 1e3), "ms_per_step": ms_total / args.steps, "scaling": "strong",
             "clocks": clk, "gpu_launches": int(launches), "roofline": roof}
     return head, spg
 
@@ -648,7 +649,7 @@ def bench_ppr(c):
             "kernel_share_of_step": k_ms / ms_total, "pushes_per_step": pushes / steps, "pushes_per_s": pushes / (k_ms / 1e3),
             "bytes_model": f"pushes x (8 + 8 x {deg_push:.1f} edge-weighted mean degree) + 8 x nnz"}
     head = {"value": c.n * steps / (ms_total / 1e3), "ms_per_step": ms_total / steps, "steps": steps,
-            "scaling": "strong" if c.world > 1 else "weak", "clocks": clk, "gpu_launches": int(launches), "roofline": roof}
+            "scaling": "strong", "clocks": clk, "gpu_launches": int(launches), "roofline": roof}
     return head, x
 
 
