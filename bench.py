@@ -371,6 +371,15 @@ def run_ours(args):
         spjoin.append({"error": repr(ex)})
         log(f"[bench] SpJoin block failed on rank {c.rank}: {ex!r}")
 
+    # ---- the no-replication alternative: linked shards (remote rows read over NVLink at join time) ------------------
+    linked = None
+    if c.world > 1 and W["kind"] == "lp" and not args.quick and not args.no_linked:
+        try:
+            linked = bench_linked(c)
+        except Exception as ex:  # noqa: BLE001
+            linked = {"error": repr(ex)}
+            log(f"[bench] linked block failed on rank {c.rank}: {ex!r}")
+
     cpu = None
     if c.rank == 0 and c.world == 1 and not args.no_cpu_baseline and not args.quick and c.A is not None:
         cpu = cpu_baseline(c, spg, spjoin)
@@ -392,6 +401,8 @@ def run_ours(args):
         line["spjoin_batches"] = spjoin
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if linked is not None:
+            line["linked"] = linked
         print(json.dumps(line), flush=True)
     if c.world > 1:
         from surel_plus_b200.parallel import close_exchanges
@@ -599,6 +610,53 @@ def row_checksums(torch, spg):
         pos = torch.arange(tot, device=dev) - (off[row_of] - off[a]) + r["rowbeg"][row_of]
         v = r["indices"][pos].long() * 1000003 + r["data"][pos].long() * 7919 + 1
         out.index_add_(0, row_of, v * v)
+    return out
+
+
+def bench_linked(c):
+    """N > 1: one pass with LINKED shards (parallel.linked_sample: no bulk exchange, every rank keeps its rows; the LP
+    tables are merged and 12 bytes of row metadata per seed cross NVLink), and SpJoin on the linked SpG, whose remote rows
+    come over NVLink inside the join kernel.  Reported beside the replicated pass: the trade is pass time against join rate."""
+    torch, args, W = c.torch, c.args, c.W
+    from surel_plus_b200.parallel import linked_exchange, linked_sample, partition_by_work
+    M, m = W["M"], W["m"]
+    bounds = partition_by_work(0.5 * M * m + 1.5 * np.minimum(c.deg, M), c.world)
+    xc = linked_exchange(c.graph, int(np.max(np.diff(bounds))), M, m)   # one slab, re-staged by every pass
+    for i in range(2):
+        lk = linked_sample(c.graph, c.q_dev, num_walks=M, num_steps=m, seed=7 + i, bounds=bounds, exchange=xc)
+        c.barrier()
+        lk.close()
+        c.barrier()
+    steps = max(2, min(args.steps, 5))
+    c.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    lk = None
+    for i in range(steps):
+        if lk is not None:
+            lk.close()
+            c.barrier()
+        lk = linked_sample(c.graph, c.q_dev, num_walks=M, num_steps=m, seed=111413 + i, bounds=bounds, exchange=xc)
+    e1.record()
+    c.barrier()
+    ms = c.max_over_ranks(e0.elapsed_time(e1)) / steps
+    out = {"ms_per_pass": ms, "seeds_per_s": c.n / (ms / 1e3), "unit": "seeds/s",
+           "what": "seed ranges sampled per rank, shards staged unpacked in the IPC-mapped slabs and linked (LP tables merged, ids "
+                   "relabelled in place, row offsets / sizes fetched); rows are NOT copied: SpJoin reads remote rows over NVLink",
+           "spjoin": []}
+    for B in (args.spjoin_batch or W["batches"]):
+        try:
+            b = bench_spjoin(c, lk, int(B))
+            out["spjoin"].append({k: b.get(k) for k in ("batch", "pattern", "value", "unit", "ms_per_batch")}
+                                 | {"stream": (b.get("stream") or {}).get("value"),
+                                    "kernel_ms": (b.get("roofline") or {}).get("kernel_ms_per_launch")})
+        except Exception as ex:  # noqa: BLE001
+            out["spjoin"].append({"batch": int(B), "error": repr(ex)})
+    c.barrier()
+    lk.close()
+    torch.cuda.synchronize()
+    c.barrier()
+    xc.close()
     return out
 
 
@@ -903,6 +961,7 @@ def main():
     ap.add_argument("--quick", action="store_true", help="kernel iteration: the sampling pass only (no e2e, SpJoin, CPU baseline)")
     ap.add_argument("--no-replicas", action="store_true", help="N > 1: skip the secondary independent-replicas number")
     ap.add_argument("--no-exchange-compare", action="store_true", help="N > 1: skip the NCCL-staged exchange comparison")
+    ap.add_argument("--no-linked", action="store_true", help="N > 1: skip the linked-shards (no replication) comparison")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

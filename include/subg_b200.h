@@ -213,6 +213,17 @@ int subg_xchg_slab(const subg_xchg *x, void **slab_dev, int64_t *bytes);
 int subg_xchg_pack(subg_xchg *x, const subg_spg *shard, int64_t num_nodes, int64_t *header, void *stream);
 int subg_xchg_assemble(subg_xchg *x, const int64_t *headers, const void *const *srcs, int num_walks, int ncol,
                        void *stream, subg_spg **out);
+/* The alternative to replicating the SpG: LINKED shards.  stage copies the shard UNPACKED into the slab (a plane of node
+ * ids and a plane of LP ids at the same offsets in every slab; plane_entries = capacity of a plane, the same on every
+ * rank; header as for pack, *header[4] < 0 if it did not fit).  link merges the LP tables, relabels THIS rank's id plane
+ * to the global ids in place, fetches the row offsets / sizes of all shards (12 bytes per seed) and returns an SpG whose
+ * rows stay where they were sampled: indices / data point at the first slab's planes and rowbeg[u] is row u's offset from
+ * there, reaching into the peers' mapped slabs.  SpJoin takes it unchanged and reads remote rows over NVLink at join
+ * time.  The caller must barrier after link (every rank has relabelled its plane) and keep every exchange context alive
+ * while the SpG is in use; the SpG does not own its rows (subg_spg_views makes a local compact copy). */
+int subg_xchg_stage(subg_xchg *x, const subg_spg *shard, int64_t num_nodes, int64_t plane_entries, int64_t *header, void *stream);
+int subg_xchg_link(subg_xchg *x, const int64_t *headers, const void *const *srcs, int num_walks, int ncol, void *stream,
+                   subg_spg **out);
 void subg_xchg_free(subg_xchg *x);
 
 /* ---- SpJoin -------------------------------------------------------------------

@@ -25,7 +25,7 @@ SYMBOLS = [
     "subg_graph_create", "subg_graph_from_edges", "subg_graph_export", "subg_graph_info", "subg_graph_free",
     "subg_gset_sample", "subg_gset_sample_shard", "subg_spg_set_lp_table", "subg_spg_info", "subg_spg_export", "subg_spg_views", "subg_spg_rows", "subg_spg_enc", "subg_spg_walks", "subg_spg_expand_rows",
     "subg_spg_from_csr", "subg_spg_alloc", "subg_spg_seal", "subg_spg_free",
-    "subg_xchg_create", "subg_xchg_export", "subg_xchg_open", "subg_xchg_slab", "subg_xchg_pack", "subg_xchg_assemble", "subg_xchg_free",
+    "subg_xchg_create", "subg_xchg_export", "subg_xchg_open", "subg_xchg_slab", "subg_xchg_pack", "subg_xchg_assemble", "subg_xchg_stage", "subg_xchg_link", "subg_xchg_free",
     "subg_spjoin_plan", "subg_spjoin_run", "subg_spjoin",
     "subg_joiner_create", "subg_joiner_submit", "subg_joiner_rows", "subg_joiner_free",
     "subg_ppr_topk", "subg_spg_encode", "subg_spg_pushes",
@@ -82,6 +82,8 @@ def load() -> C.CDLL:
     L.subg_xchg_slab.argtypes = [vp, C.POINTER(vp), C.POINTER(i64)]
     L.subg_xchg_pack.argtypes = [vp, vp, i64, vp, vp]
     L.subg_xchg_assemble.argtypes = [vp, vp, vp, i32, i32, vp, C.POINTER(vp)]
+    L.subg_xchg_stage.argtypes = [vp, vp, i64, i64, vp, vp]
+    L.subg_xchg_link.argtypes = [vp, vp, vp, i32, i32, vp, C.POINTER(vp)]
     L.subg_xchg_free.argtypes = [vp]
     L.subg_xchg_free.restype = None
     L.subg_spjoin_plan.argtypes = [vp, vp, i64, i32, vp, vp, C.POINTER(i64), vp]

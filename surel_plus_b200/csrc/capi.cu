@@ -209,6 +209,8 @@ int xchg_open_impl(Xchg *x, const void *handles);
 int xchg_slab_impl(const Xchg *x, void **slab_dev, int64_t *bytes);
 int xchg_pack_impl(Xchg *x, const SpG *s, int64_t n_nodes, int64_t *header, cudaStream_t st);
 int xchg_assemble_impl(Xchg *x, const int64_t *headers, const void *const *srcs, int M, int ncol, cudaStream_t st, SpG **out);
+int xchg_stage_impl(Xchg *x, const SpG *s, int64_t n_nodes, int64_t plane_entries, int64_t *header, cudaStream_t st);
+int xchg_link_impl(Xchg *x, const int64_t *headers, const void *const *srcs, int M, int ncol, cudaStream_t st, SpG **out);
 void xchg_free_impl(Xchg *x);
 struct WalkSet;
 int walk_sample_impl(const Graph *g, const int32_t *seeds_hd, int64_t n, int M, int m, uint64_t seed, int rng_mode,
@@ -470,6 +472,15 @@ int subg_xchg_slab(const subg_xchg *x, void **slab_dev, int64_t *bytes) {
 }
 int subg_xchg_pack(subg_xchg *x, const subg_spg *shard, int64_t num_nodes, int64_t *header, void *stream) {
     return xchg_pack_impl(reinterpret_cast<Xchg *>(x), reinterpret_cast<const SpG *>(shard), num_nodes, header, (cudaStream_t)stream);
+}
+int subg_xchg_stage(subg_xchg *x, const subg_spg *shard, int64_t num_nodes, int64_t plane_entries, int64_t *header, void *stream) {
+    return xchg_stage_impl(reinterpret_cast<Xchg *>(x), reinterpret_cast<const SpG *>(shard), num_nodes, plane_entries, header,
+                           (cudaStream_t)stream);
+}
+int subg_xchg_link(subg_xchg *x, const int64_t *headers, const void *const *srcs, int num_walks, int ncol, void *stream,
+                   subg_spg **out) {
+    return xchg_link_impl(reinterpret_cast<Xchg *>(x), headers, srcs, num_walks, ncol, (cudaStream_t)stream,
+                          reinterpret_cast<SpG **>(out));
 }
 int subg_xchg_assemble(subg_xchg *x, const int64_t *headers, const void *const *srcs, int num_walks, int ncol, void *stream,
                        subg_spg **out) {

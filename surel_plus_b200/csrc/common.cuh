@@ -159,6 +159,9 @@ struct SpG {
     int64_t cap = 0;             // entries allocated
     int32_t *indices = nullptr;  // ascending per row
     void *data = nullptr;        // int32 (id+1) or float64
+    // linked SpG (multi-GPU, csrc/xchg.cu): indices / data are NOT owned -- they point into the exchange slabs of this GPU
+    // and of its peers (one address space: rowbeg holds each row's offset from the first slab's plane)
+    bool borrowed = false;
     uint16_t *slot = nullptr;    // first-visit rank (sampler-built SpGs that asked for it)
     int16_t *enc = nullptr;      // [c, ncol]
     // sampler-built LP SpGs keep the 64-bit key of every unique LP row and the stream position of its first occurrence

@@ -228,7 +228,8 @@ __global__ void row_sizes_kernel(const long long *indptr, int64_t n, int32_t *ns
 
 static void free_spg_arrays(SpG *s, cudaStream_t st) {
     if (s->rowbeg && (void *)s->rowbeg != (void *)s->indptr) dfree(s->rowbeg, st);
-    dfree(s->indptr, st); dfree(s->indices, st); dfree(s->data, st); dfree(s->slot, st);
+    dfree(s->indptr, st); dfree(s->slot, st);
+    if (!s->borrowed) { dfree(s->indices, st); dfree(s->data, st); }
     dfree(s->enc, st); dfree(s->nsize, st); dfree(s->seeds, st); dfree(s->lp_key, st); dfree(s->lp_pos, st); dfree(s->walks, st);
     s->walks = nullptr;
     s->indptr = nullptr; s->rowbeg = nullptr; s->indices = nullptr; s->data = nullptr; s->slot = nullptr;
@@ -262,7 +263,9 @@ int spg_ensure_csr(SpG *s, cudaStream_t st) {
     }
     SUBG_CUDA(cudaStreamSynchronize(st));
     dfree(scratch, st);
-    dfree(s->indices, st); dfree(s->data, st); dfree(s->slot, st); dfree(s->rowbeg, st);
+    if (!s->borrowed) { dfree(s->indices, st); dfree(s->data, st); }
+    s->borrowed = false;   // the compact copy is owned (a linked SpG has just pulled its remote rows over NVLink)
+    dfree(s->slot, st); dfree(s->rowbeg, st);
     s->indices = ni; s->data = nd; s->slot = ns;
     s->indptr = indptr; s->rowbeg = indptr;
     s->extent = s->T; s->cap = s->T + 16;
@@ -677,6 +680,7 @@ int spg_set_lp_table_impl(SpG *s, const int32_t *id_map_hd, const int16_t *enc_h
                           cudaStream_t st) {
     if (!s || c_new < 0 || (s->c > 0 && !id_map_hd) || (c_new > 0 && !enc_hd)) return fail(SUBG_ERR_ARG, "Input parsing error.");
     if (s->value_kind != 0) return fail(SUBG_ERR_ARG, "LP table of a value SpG");
+    if (s->borrowed) return fail(SUBG_ERR_ARG, "a linked SpG's rows live in the exchange slabs and are not relabelled");
     if (ncol > 0) s->ncol = ncol;
     if (s->ncol < 1) return fail(SUBG_ERR_ARG, "LP table width unknown");
     DeviceGuard guard(s->device);

@@ -565,6 +565,199 @@ done:
     return SUBG_OK;
 }
 
+// ------------------------------------------------------------------ linked SpG: shards stay where they were sampled
+// The alternative to replicating the SpG: every rank STAGES its shard unpacked in its slab -- a plane
+// of node ids and a plane of LP ids at the same two offsets in every slab -- and the ranks LINK them: the LP tables are
+// merged as in assemble, every rank relabels its OWN id plane to the global ids in place, and only the row metadata
+// (12 bytes per seed) crosses NVLink.  The result is an ordinary scattered SpG whose indices / data pointers are the
+// first slab's planes and whose rowbeg[u] is row u's offset from there -- a 64-bit element offset that reaches into the
+// peers' slabs, because all of them are mapped into this process (one address space).  SpJoin reads such an SpG unchanged:
+// its TMA bulk copies and plain loads take `indices + rowbeg[u]` wherever that lies, so the rows of a query's endpoints
+// come over NVLink at join time.  The pass costs the sampling of 1/N of the seeds and no bulk transfer; the joins pay
+// for it (7/8 of the row bytes are remote at 8 GPUs).  The caller has to barrier after link (all id planes relabelled)
+// and keep the exchange contexts alive for as long as the SpG is used.
+static int64_t plane_round(int64_t e) { return (e + 63) & ~63ll; }
+static int64_t plane_offset(int64_t slab_bytes, int64_t P) { return (slab_bytes - 8 * P) & ~255ll; }
+constexpr int kStagedFormat = 8;   // H_FMT low byte of a staged shard; H_BYTES then holds the plane size in entries
+
+__global__ void xchg_relabel_plane_kernel(int32_t *plane, int64_t e4, const int32_t *__restrict__ gmap, uint32_t c) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (e4 >> 2); i += (int64_t)gridDim.x * blockDim.x) {
+        int4 v = ((int4 *)plane)[i];
+        v.x = __ldg(gmap + clamp_id(v.x, c)); v.y = __ldg(gmap + clamp_id(v.y, c));
+        v.z = __ldg(gmap + clamp_id(v.z, c)); v.w = __ldg(gmap + clamp_id(v.w, c));
+        ((int4 *)plane)[i] = v;
+    }
+}
+struct LinkArgs {
+    const unsigned char *src[kMaxWorld];
+    int64_t nsize_off[kMaxWorld], rowbeg_off[kMaxWorld], n[kMaxWorld], row_off[kMaxWorld];
+    long long delta[kMaxWorld];   // elements from the first slab's plane to this slab's plane
+    int world;
+    long long *rowbeg;
+    int32_t *nsize;
+};
+__global__ void xchg_link_rows_kernel(const LinkArgs a) {
+    for (int r = 0; r < a.world; r++) {
+        const long long *rb = (const long long *)(a.src[r] + a.rowbeg_off[r]);
+        const int32_t *ns = (const int32_t *)(a.src[r] + a.nsize_off[r]);
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n[r]; i += (int64_t)gridDim.x * blockDim.x) {
+            a.rowbeg[a.row_off[r] + i] = (long long)ld_peer_u64(rb + i) + a.delta[r];
+            a.nsize[a.row_off[r] + i] = (int32_t)ld_peer_u32(ns + i);
+        }
+    }
+}
+
+// plane_entries: capacity of a plane in entries, the SAME on every rank (e.g. the largest seed range x the row capacity)
+int xchg_stage_impl(Xchg *x, const SpG *s, int64_t n_nodes, int64_t plane_entries, int64_t *header, cudaStream_t st) {
+    if (!x || !s || !header || n_nodes < 1 || plane_entries < 0) return fail(SUBG_ERR_ARG, "Input parsing error.");
+    if (s->value_kind != 0 || s->device != x->device || s->borrowed) return fail(SUBG_ERR_ARG, "exchange takes a sampler-built LP shard on the context's device");
+    if (s->c > 0 && (!s->lp_key || !s->lp_pos)) return fail(SUBG_ERR_ARG, "shard has no LP keys (not built by subg_gset_sample_shard)");
+    DeviceGuard guard(x->device);
+    x->tag.use_on(st);
+    s->tag.use_on(st);
+    const int nb = std::max(1, ceil_log2_u64((uint64_t)n_nodes));
+    const int64_t P = plane_round(plane_entries + 4);
+    const SlabLayout L = slab_layout(s->n, 0, s->c, 0);
+    const int64_t PI = plane_offset(x->slab_bytes, P);
+    header[H_N] = s->n; header[H_T] = s->T; header[H_EXTENT] = s->extent; header[H_C] = s->c;
+    header[H_FMT] = kStagedFormat | (nb << 8); header[H_MAXSET] = s->max_set; header[H_STATUS] = s->status; header[H_BYTES] = P;
+    const int64_t e4 = (s->extent + 3) & ~3ll;
+    if (PI < L.end || e4 > P || s->extent + 4 > s->cap) {
+        header[H_FMT] = -1;
+        return SUBG_OK;
+    }
+    if (e4 > 0) {
+        SUBG_CUDA(cudaMemcpyAsync(x->slab + PI, s->indices, (size_t)e4 * 4, cudaMemcpyDeviceToDevice, st));
+        SUBG_CUDA(cudaMemcpyAsync(x->slab + PI + 4 * P, s->data, (size_t)e4 * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    if (s->n > 0) {
+        const unsigned blocks = (unsigned)std::min<int64_t>((s->n + 255) / 256, 4 * 148);
+        xchg_rows_kernel<<<blocks, 256, 0, st>>>((const long long *)s->rowbeg, s->nsize, s->n, (long long *)(x->slab + L.rowbeg),
+                                                 (int32_t *)(x->slab + L.nsize));
+        count_launch(1);
+    }
+    if (s->c > 0) {
+        SUBG_CUDA(cudaMemcpyAsync(x->slab + L.key, s->lp_key, (size_t)s->c * 8, cudaMemcpyDeviceToDevice, st));
+        SUBG_CUDA(cudaMemcpyAsync(x->slab + L.pos, s->lp_pos, (size_t)s->c * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    SUBG_CUDA(cudaGetLastError());
+    return SUBG_OK;
+}
+
+int xchg_link_impl(Xchg *x, const int64_t *headers, const void *const *srcs, int M, int ncol, cudaStream_t st, SpG **out) {
+    if (!x || !headers || !out || ncol < 2) return fail(SUBG_ERR_ARG, "Input parsing error.");
+    if (!srcs && !x->opened && x->world > 1) return fail(SUBG_ERR_ARG, "peer slabs are not mapped (subg_xchg_open) and no sources were given");
+    DeviceGuard guard(x->device);
+    x->tag.use_on(st);
+    const int W = x->world;
+    const int m = ncol - 1;
+    int shift = 0;
+    while ((M >> shift) != 0) shift++;
+    MergeArgs ma{};
+    LinkArgs la{};
+    ma.world = W; la.world = W;
+    int64_t n_tot = 0, T_tot = 0, P = -1;
+    int32_t c_sum = 0, max_set = 0;
+    uint32_t status = 0;
+    for (int r = 0; r < W; r++) {
+        const int64_t *h = headers + 8 * r;
+        if (h[H_FMT] < 0) return fail(SUBG_ERR_MEM, "a shard did not fit its exchange slab");
+        if ((h[H_FMT] & 0xff) != kStagedFormat || h[H_N] < 0 || h[H_T] < 0 || h[H_EXTENT] < h[H_T] || h[H_C] < 0)
+            return fail(SUBG_ERR_ARG, "malformed exchange header (link takes staged shards)");
+        if (P < 0) P = h[H_BYTES];
+        if (h[H_BYTES] != P) return fail(SUBG_ERR_ARG, "the ranks staged with different plane sizes");
+        const SlabLayout L = slab_layout(h[H_N], 0, h[H_C], 0);
+        const unsigned char *src = srcs ? (const unsigned char *)srcs[r] : x->peer[r];
+        if (!src) return fail(SUBG_ERR_ARG, "missing slab source");
+        ma.src[r] = src; ma.key_off[r] = L.key; ma.pos_off[r] = L.pos; ma.coff[r] = c_sum;
+        la.src[r] = src; la.nsize_off[r] = L.nsize; la.rowbeg_off[r] = L.rowbeg; la.n[r] = h[H_N]; la.row_off[r] = n_tot;
+        la.delta[r] = (long long)(((intptr_t)src - (intptr_t)(srcs ? (const unsigned char *)srcs[0] : x->peer[0])) / 4);
+        n_tot += h[H_N]; T_tot += h[H_T];
+        if ((int64_t)c_sum + h[H_C] > INT32_MAX) return fail(SUBG_ERR_MEM, "too many unique LP rows");
+        c_sum += (int32_t)h[H_C];
+        max_set = std::max<int32_t>(max_set, (int32_t)h[H_MAXSET]);
+        status |= (uint32_t)h[H_STATUS];
+    }
+    ma.coff[W] = c_sum;
+    const unsigned char *base = srcs ? (const unsigned char *)srcs[0] : x->peer[0];
+    const int64_t PI = plane_offset(x->slab_bytes, P);
+    SpG *s = new SpG();
+    s->tag.last = st;
+    s->device = x->device; s->n = n_tot; s->T = T_tot; s->ncol = ncol; s->M = M; s->shift = shift; s->value_kind = 0;
+    s->max_set = max_set; s->status = status;
+    s->borrowed = true;
+    s->indices = (int32_t *)(base + PI);
+    s->data = (void *)(base + PI + 4 * P);
+    s->extent = T_tot; s->cap = 0;
+    cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, x->device);
+    unsigned long long *tab_key = nullptr, *tab_pos = nullptr;
+    int32_t *rank_of_slot = nullptr, *gmap = nullptr;
+    uint32_t *d_cnt = nullptr;
+    int rc = SUBG_OK;
+#define CKX(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            rc = fail(_e == cudaErrorMemoryAllocation ? SUBG_ERR_MEM : SUBG_ERR_CUDA,              \
+                      std::string(#call) + ": " + cudaGetErrorString(_e));                         \
+            goto done;                                                                             \
+        }                                                                                          \
+    } while (0)
+    {
+        CKX(dmalloc(&s->rowbeg, (size_t)std::max<int64_t>(n_tot, 1), st));
+        CKX(dmalloc(&s->nsize, (size_t)std::max<int64_t>(n_tot, 1), st));
+        CKX(dmalloc(&s->enc, (size_t)std::max(c_sum, 1) * ncol, st));
+        CKX(dmalloc(&s->lp_key, (size_t)std::max(c_sum, 1), st));
+        CKX(dmalloc(&s->lp_pos, (size_t)std::max(c_sum, 1), st));
+        CKX(dmalloc(&gmap, (size_t)std::max(c_sum, 1), st));
+        CKX(dmalloc(&d_cnt, 2, st));
+        CKX(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(uint32_t), st));
+        if (c_sum > 0) {
+            uint32_t cap = 1024;
+            while (cap < 4u * (uint32_t)c_sum) cap <<= 1;
+            CKX(dmalloc(&tab_key, (size_t)cap, st));
+            CKX(dmalloc(&tab_pos, (size_t)cap, st));
+            CKX(dmalloc(&rank_of_slot, (size_t)cap, st));
+            const unsigned fb = (unsigned)std::min<int64_t>((cap + 255) / 256, 4 * s->num_sms);
+            fill_u64x2_kernel<<<fb, 256, 0, st>>>(tab_key, tab_pos, cap, kXEmptyKey, ~0ull);
+            const unsigned mb = (unsigned)std::min<int64_t>((c_sum + 255) / 256, 4 * s->num_sms);
+            merge_insert_kernel<<<mb, 256, 0, st>>>(ma, tab_key, tab_pos, cap - 1);
+            if (int urc = rank_unique_keys(tab_key, tab_pos, cap, (uint32_t)c_sum, false, M, m, shift, rank_of_slot, s->enc, s->lp_key,
+                                           s->lp_pos, d_cnt, s->num_sms, st)) { rc = urc; goto done; }
+            merge_map_kernel<<<mb, 256, 0, st>>>(ma, tab_key, cap - 1, rank_of_slot, gmap);
+            CKX(cudaGetLastError());
+            count_launch(3);
+            // this rank's own id plane -> global ids, in place (the peers do the same with theirs)
+            const int64_t *hme = headers + 8 * x->rank;
+            const int64_t e4 = (hme[H_EXTENT] + 3) & ~3ll;
+            if (e4 > 0 && hme[H_C] > 0) {
+                const unsigned rb = (unsigned)std::min<int64_t>((e4 / 4 + 255) / 256, 16 * (int64_t)s->num_sms);
+                xchg_relabel_plane_kernel<<<rb, 256, 0, st>>>((int32_t *)(x->slab + PI + 4 * P), e4, gmap + ma.coff[x->rank], (uint32_t)hme[H_C]);
+                CKX(cudaGetLastError());
+                count_launch(1);
+            }
+        }
+        if (n_tot > 0) {
+            la.rowbeg = (long long *)s->rowbeg; la.nsize = s->nsize;
+            xchg_link_rows_kernel<<<4 * s->num_sms, 256, 0, st>>>(la);
+            CKX(cudaGetLastError());
+            count_launch(1);
+        }
+        CKX(cudaMemcpyAsync(x->host_words, d_cnt, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CKX(cudaStreamSynchronize(st));
+        s->c = (int32_t)((uint32_t *)x->host_words)[0];
+    }
+done:
+#undef CKX
+    dfree(tab_key, st); dfree(tab_pos, st); dfree(rank_of_slot, st); dfree(gmap, st); dfree(d_cnt, st);
+    if (rc != SUBG_OK) {
+        spg_free_impl(s);
+        return rc;
+    }
+    *out = s;
+    return SUBG_OK;
+}
+
 void xchg_free_impl(Xchg *x) {
     if (!x) return;
     DeviceGuard guard(x->device);

@@ -349,6 +349,73 @@ def sharded_sample(graph, query, num_walks=100, num_steps=3, bucket=-1, seed=111
     return full
 
 
+def linked_exchange(graph, n_seeds_max: int, num_walks: int, num_steps: int, bucket: int = -1, group=None) -> ShardExchange:
+    """A slab (with the peers' mappings) large enough for linked_sample of seed ranges of up to n_seeds_max seeds; pass it
+    as `exchange=` to reuse it over several passes (each pass re-stages it: close the previous linked SpG on every rank
+    first)."""
+    Kt = num_walks * num_steps + 1
+    row_cap = (min(Kt, bucket) if bucket > 0 else Kt) + 3 & ~3
+    need = slab_bytes_needed(int(n_seeds_max), row_cap)
+    xc = ShardExchange(graph.device, int(need * 1.05) + (1 << 20), group, "peer")
+    if xc.mode != "peer":
+        why = xc.why
+        xc.close()
+        raise RuntimeError(f"linked shards need the peers' slabs mapped: {why}")
+    return xc
+
+
+def linked_sample(graph, query, num_walks=100, num_steps=3, bucket=-1, seed=111413, rng_mode=None, group=None,
+                  bounds: Optional[np.ndarray] = None, exchange: Optional[ShardExchange] = None):
+    """The no-replication alternative to sharded_sample: every rank samples its seed range and keeps its rows; the shards
+    are LINKED (csrc/xchg.cu: staged planes in the IPC-mapped slabs, LP tables merged, ids relabelled in place, 12 bytes of
+    row metadata per seed fetched).  Returns an SpG with the same rows, ids and LP table as SpG.sample of one process,
+    whose remote rows are read over NVLink when a query joins them: the pass costs no bulk transfer, the joins do.
+    The SpG keeps its exchange context alive (and with it the slab the peers read): close it on every rank together."""
+    from .spg import SpG, _ptr, _stream
+    lib = _capi.load()
+    world, rank, _ = _group_info(group)
+    q = query if isinstance(query, torch.Tensor) else np.ascontiguousarray(np.asarray(query).astype(np.int32, copy=False))
+    n = q.numel() if isinstance(q, torch.Tensor) else q.size
+    if bounds is None:
+        bounds = np.array([partition(n, world, r)[0] for r in range(world)] + [n], dtype=np.int64)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    Kt = num_walks * num_steps + 1
+    row_cap = (min(Kt, bucket) if bucket > 0 else Kt) + 3 & ~3
+    plane = int(np.max(np.diff(bounds))) * row_cap
+    # the slab is owned by the result (or by the caller who passed `exchange`), never the cache sharded_sample re-packs
+    xc = exchange if exchange is not None else linked_exchange(graph, int(np.max(np.diff(bounds))), num_walks, num_steps, bucket, group)
+    st = _stream(graph.device)
+    tdev = torch.device("cuda", graph.device)
+    h = C.c_void_p()
+    rmode = _capi.SUBG_RNG_PHILOX if rng_mode is None else rng_mode
+    _capi.check(lib.subg_gset_sample_shard(graph._h, _ptr(q), n, lo, hi, int(num_walks), int(num_steps), int(bucket),
+                                           int(seed) & 0xFFFFFFFFFFFFFFFF, int(rmode), None,
+                                           _capi.SAMPLE_NO_RANKS | _capi.SAMPLE_NO_COMPACT, st, C.byref(h)))
+    shard = SpG(h, graph.device, n_nodes=graph.N, num_walks=num_walks)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    hdr = np.zeros(8, np.int64)
+    _capi.check(lib.subg_xchg_stage(xc._h, shard._h, graph.N, plane, hdr.ctypes.data, st))
+    allh = torch.empty((world, 8), dtype=torch.int64, device=tdev)
+    dist.all_gather_into_tensor(allh, torch.from_numpy(hdr).to(tdev), group=group)    # barrier: every shard is staged
+    headers = np.ascontiguousarray(allh.cpu().numpy())
+    if (headers[:, H_FMT] < 0).any():
+        shard.close()
+        if exchange is None:
+            xc.close()
+        raise MemoryError("a shard did not fit its exchange slab")
+    fh = C.c_void_p()
+    _capi.check(lib.subg_xchg_link(xc._h, headers.ctypes.data, None, int(num_walks), int(num_steps) + 1, st, C.byref(fh)))
+    dist.all_reduce(torch.zeros(1, dtype=torch.int32, device=tdev), group=group)      # barrier: every id plane is relabelled
+    shard.close()
+    ev[1].record()
+    full = SpG(fh, graph.device, n_nodes=graph.N, num_walks=num_walks)
+    full._exchange = xc            # the slabs live as long as the SpG
+    full.exchange_mode = "linked"
+    full.exchange_events = ev
+    return full
+
+
 def sharded_subg_matrix(G, train_idx, num_walks=200, num_steps=4, device=None, seed=111413, rng_mode=None, group=None):
     """Multi-GPU subg_matrix (sampler/random_walks.py:74-82): (z, enc) with z the replicated device SpG."""
     from .spg import DeviceGraph

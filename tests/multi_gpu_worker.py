@@ -52,6 +52,23 @@ def main():
     left = whole[ip[lo]:ip[hi]]
     right = whole[ip[B + lo]:ip[B + hi]]
     assert torch.equal(mine, torch.cat([left, right]))
+    # the no-replication alternative: linked shards, remote rows read over NVLink by the join kernel (TMA bulk copies)
+    from surel_plus_b200.parallel import linked_sample
+    for mode in (_capi.SUBG_RNG_RAND_R, _capi.SUBG_RNG_PHILOX):
+        ref = SpG.sample(g, q, 60, 3, seed=5, rng_mode=mode, first_visit_ranks=False)
+        lk = linked_sample(g, q, 60, 3, seed=5, rng_mode=mode)
+        assert (lk.n, lk.T, lk.c, lk.max_set) == (ref.n, ref.T, ref.c, ref.max_set)
+        assert np.array_equal(lk.enc_table(), ref.enc_table())
+        e2 = np.stack([q[:800], q[::-1][:800]]).astype(np.int64)
+        x0, p0 = gather(e2, ref, f"cuda:{local}", True, None)
+        x1, p1 = gather(e2, lk, f"cuda:{local}", True, None)
+        assert torch.equal(x0, x1) and torch.equal(p0, p1)
+        torch.cuda.synchronize()
+        dist.barrier()
+        lk.close()
+        ref.close()
+        dist.barrier()
+    print("LINKED_OK", rank, flush=True)
     dist.barrier()
     print("SHARDED_OK", rank, flush=True)
     dist.destroy_process_group()

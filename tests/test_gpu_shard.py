@@ -139,6 +139,90 @@ def test_exchange_pack_merge_pull(mid_graph, mode_name, cuts, extra, monkeypatch
         assert np.array_equal(reps[0].views()["nsize"].cpu().numpy(), nsize)
 
 
+@pytest.mark.parametrize("mode_name,cuts", [("RAND_R", (0.5,)), ("PHILOX", (0.1, 0.35, 0.9)), ("PHILOX", (0.0, 0.5))])
+def test_linked_shards_join_like_the_single_call_spg(mid_graph, mode_name, cuts):
+    """The no-replication alternative (subg_xchg_stage / subg_xchg_link): the shards stay in their slabs, the LP tables are
+    merged, every 'rank' relabels its own id plane, and the linked SpG -- rows addressed by 64-bit offsets that reach into
+    the other slabs -- joins (pairs, triplets, JoinStream) exactly like the SpG of a single call; views() pulls the rows
+    into a local compact copy equal to the single call's CSR.  One process, one GPU, world = number of shards (on a
+    multi-GPU box the slabs are the peers' IPC mappings: tests/multi_gpu_worker.py)."""
+    from surel_plus_b200 import DeviceGraph, JoinStream, SpG, _capi, gather, hgather
+    from surel_plus_b200 import parallel as par
+    from surel_plus_b200.spg import _ptr, _stream
+    A = mid_graph
+    n = A.shape[0]
+    M, m, seed = 50, 3, 7
+    mode = getattr(_capi, f"SUBG_RNG_{mode_name}")
+    q = np.random.default_rng(1).permutation(n).astype(np.int32)
+    g = DeviceGraph.from_scipy(A)
+    lib = _capi.load()
+    full = SpG.sample(g, q, M, m, seed=seed, rng_mode=mode, first_visit_ranks=False)
+    bounds = [0] + [int(c * n) for c in cuts] + [n]
+    W = len(bounds) - 1
+    shards = []
+    for i in range(W):
+        h = C.c_void_p()
+        _capi.check(lib.subg_gset_sample_shard(g._h, _ptr(q), q.size, bounds[i], bounds[i + 1], M, m, -1, seed, mode,
+                                               None, _capi.SAMPLE_NO_RANKS | _capi.SAMPLE_NO_COMPACT, _stream(g.device), C.byref(h)))
+        shards.append(SpG(h, g.device, n_nodes=g.N, num_walks=M))
+    row_cap = (M * m + 1 + 3) & ~3
+    n_max = max(s.n for s in shards)
+    need = par.slab_bytes_needed(n_max, row_cap, lp_rows=max(max(s.c for s in shards), 1)) + (1 << 16)
+    ctx, slabs = [], []
+    headers = np.zeros((W, 8), np.int64)
+    for r in range(W):
+        h = C.c_void_p()
+        _capi.check(lib.subg_xchg_create(g.device, r, W, need, C.byref(h)))
+        ctx.append(h)
+        _capi.check(lib.subg_xchg_stage(h, shards[r]._h, g.N, n_max * row_cap, headers[r].ctypes.data, _stream(g.device)))
+        p = C.c_void_p()
+        _capi.check(lib.subg_xchg_slab(h, C.byref(p), None))
+        slabs.append(p.value)
+    assert (headers[:, par.H_FMT] >= 0).all() and set((headers[:, par.H_FMT] & 0xff).tolist()) == {8}
+    srcs = (C.c_void_p * W)(*slabs)
+    linked = []
+    for r in range(W):
+        fh = C.c_void_p()
+        _capi.check(lib.subg_xchg_link(ctx[r], headers.ctypes.data, srcs, M, m + 1, _stream(g.device), C.byref(fh)))
+        linked.append(SpG(fh, g.device, n_nodes=g.N, num_walks=M))
+    torch.cuda.synchronize()          # "barrier": every id plane is relabelled
+    for s in shards:
+        s.close()
+    xpe = torch.from_numpy(full.enc_table()).float().cuda() / M
+    rng = np.random.default_rng(0)
+    edge = rng.integers(0, n, (2, 700))
+    hedge = rng.integers(0, n, (3, 300))
+    want_xz, want_ptr = gather(edge, full, "cuda", True, xpe)
+    want_raw, _ = gather(edge, full, "cuda", True, None)
+    want_h, want_hseg = hgather(hedge, full, "cuda", xpe)
+    for rep in linked:
+        assert (rep.n, rep.T, rep.c, rep.max_set) == (full.n, full.T, full.c, full.max_set)
+        assert np.array_equal(rep.enc_table(), full.enc_table())
+        got_xz, got_ptr = gather(edge, rep, "cuda", True, xpe)
+        assert torch.equal(got_xz, want_xz) and torch.equal(got_ptr, want_ptr)
+        got_raw, _ = gather(edge, rep, "cuda", True, None)
+        assert torch.equal(got_raw, want_raw)                       # the LP ids themselves, not only their table rows
+        got_h, got_hseg = hgather(hedge, rep, "cuda", xpe)
+        assert torch.equal(got_h, want_h) and torch.equal(got_hseg, want_hseg)
+    js = JoinStream(linked[0], 700, "cuda", encode=xpe)
+    sxz, sptr = js.gather(edge)
+    assert torch.equal(sxz, want_xz) and torch.equal(sptr, want_ptr)
+    js.close()
+    fv = full.views()
+    rv = linked[-1].views()            # pulls the rows into an owned compact copy
+    for key in ("indptr", "indices", "data"):
+        assert torch.equal(rv[key], fv[key]), key
+    got_xz, _ = gather(edge, linked[-1], "cuda", True, xpe)
+    assert torch.equal(got_xz, want_xz)
+    for rep in linked:
+        rep.close()
+    torch.cuda.synchronize()
+    for h in ctx:
+        lib.subg_xchg_free(h)
+    full.close()
+    g.close()
+
+
 def test_from_device_csr_roundtrip(mid_graph):
     from surel_plus_b200 import DeviceGraph, SpG, gather
     A = mid_graph
