@@ -5,7 +5,7 @@ walks it drew (SUBG_SAMPLE_DUMP_WALKS), the oracle (trace-driven restatement of 
 against the compiled reference) is fed exactly those walks, and everything the kernel produced from them -- set sizes,
 first-visit order, LP counts, 64-bit keys, first-occurrence ids, sorted SpG rows -- must be identical, with and
 without first-visit ranks (the bench runs without), for the keys-per-lane instantiations of the three LP workloads
-(collab EPL 13, ppa EPL 19, dblp EPL 7) and for 32- and 64-bit sort keys.  Feeding the dump back as SUBG_RNG_TRACE
+(collab EPL 13, ppa EPL 19, dblp EPL 8 (bitonic sort, 4 walks per lane)) and for 32- and 64-bit sort keys.  Feeding the dump back as SUBG_RNG_TRACE
 closes the loop inside the library."""
 import ctypes as C
 
