@@ -373,7 +373,7 @@ def run_ours(args):
 
     # ---- the no-replication alternative: linked shards (remote rows read over NVLink at join time) ------------------
     linked = None
-    if c.world > 1 and W["kind"] == "lp" and not args.quick and not args.no_linked:
+    if c.world > 1 and W["kind"] == "lp" and not args.quick and args.linked:
         try:
             linked = bench_linked(c)
         except Exception as ex:  # noqa: BLE001
@@ -961,7 +961,9 @@ def main():
     ap.add_argument("--quick", action="store_true", help="kernel iteration: the sampling pass only (no e2e, SpJoin, CPU baseline)")
     ap.add_argument("--no-replicas", action="store_true", help="N > 1: skip the secondary independent-replicas number")
     ap.add_argument("--no-exchange-compare", action="store_true", help="N > 1: skip the NCCL-staged exchange comparison")
-    ap.add_argument("--no-linked", action="store_true", help="N > 1: skip the linked-shards (no replication) comparison")
+    ap.add_argument("--linked", action="store_true", help="N > 1: also time the linked-shards pass (no replication, remote rows read "
+                    "over NVLink at join time) and SpJoin on it; measured at 2 GPUs (profiles/r3m_bench_ppa_2gpu.json), opt-in so that "
+                    "an unmeasured GPU count never sits between the headline and its JSON line")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
