@@ -420,7 +420,9 @@ constexpr int sampler_min_blocks() {
 // fetch: every kilobyte of SASS that is not executed still competes for the instruction caches).
 // GW: walks a lane advances together.  A lane owns ceil(M / 32) walks; with M <= 128 the slots 4..7 of a group of 8 would
 // never hold a walk but would still run their share of the Philox calls and address arithmetic (dblp / twitter shapes,
-// M = 100: a quarter of the kernel's instructions).  The Philox counters do not depend on GW: same walks either way.
+// M = 100: a quarter of the kernel's instructions).  The Philox counters of the first group do not depend on GW (and GW < 8
+// is only chosen when one group holds all of a lane's walks): same walks either way.  GW = 7 for 128 < M <= 224 (slot 7 idle
+// at M = 200) was measured too: ppa 5.790 -> 5.777 ms, collab 0.963 -> 0.957 ms -- not worth its instantiations.
 template <typename K, int EPL, bool PARITY, bool LEAN, int GW = kGW>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL>()) gset_sample_kernel(const SamplerArgs a) {
     using Acc = std::conditional_t<LEAN, uint32_t, unsigned long long>;   // packed landing counts of one member
@@ -579,10 +581,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, sampler_min_blocks<K, EPL
                     uint2 raw[GW];
 #pragma unroll
                     for (int tt = 0; tt < GW; tt++) raw[tt] = load_row_raw(a, pol, cur[tt]);
-                    uint32_t draw[GW];
+                    constexpr int NC = (GW + 3) / 4;   // Philox calls per hop and lane (GW = 7: the 8th draw is not used)
+                    uint32_t draw[4 * NC];
                     if (!replay) {  // one Philox call = this hop of four walks
 #pragma unroll
-                        for (int c = 0; c < GW / 4; c++) {
+                        for (int c = 0; c < NC; c++) {
                             const uint4 r4 = philox4x32_10(
                                 make_uint4(gi_lo, gi_hi, (uint32_t)(lane + 8 * g + 32 * c) | ((uint32_t)s << 16), 0x57414c4bu),
                                 make_uint2(a.rng_lo, a.rng_hi));
