@@ -21,16 +21,33 @@ _uploaded: "weakref.WeakValueDictionary[int, SpG]" = weakref.WeakValueDictionary
 _upload_keep: dict = {}
 
 
+def _fingerprint(x, device):
+    """What identifies an uploaded scipy matrix besides the object itself: its three buffers and the target device.
+    `utils.encoding(x, ..., 'PPR')` assigns a NEW `x.data` array (utils.py:36), which changes the fingerprint and
+    forces a fresh upload; a write INTO the same buffer cannot be seen from here (invalidate_uploads())."""
+    try:
+        return (x.data.ctypes.data, x.indices.ctypes.data, x.indptr.ctypes.data, int(x.nnz), str(device))
+    except AttributeError:
+        return (None, None, None, -1, str(device))
+
+
+def invalidate_uploads() -> None:
+    """Forget the device copies of scipy matrices passed to gather / pgather / hgather (call after modifying a
+    matrix's buffers in place)."""
+    _upload_keep.clear()
+
+
 def _as_spg(x, device) -> SpG:
     if isinstance(x, SpG):
         return x
     key = id(x)
+    fp = _fingerprint(x, device)
     hit = _upload_keep.get(key)
-    if hit is not None and hit[0]() is x:
+    if hit is not None and hit[0]() is x and hit[2] == fp:
         return hit[1]
     spg = SpG.from_scipy(x, device)
     try:
-        _upload_keep[key] = (weakref.ref(x, lambda _r, k=key: _upload_keep.pop(k, None)), spg)
+        _upload_keep[key] = (weakref.ref(x, lambda _r, k=key: _upload_keep.pop(k, None)), spg, fp)
     except TypeError:
         pass
     return spg

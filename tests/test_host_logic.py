@@ -153,3 +153,31 @@ def test_unmodified_reference_sampler_module_binds_the_shim():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_scipy_upload_cache_follows_the_buffers(monkeypatch):
+    """train._as_spg keeps the device copy of a scipy matrix per object; a matrix whose `.data` is REPLACED
+    (utils.encoding(..., 'PPR') assigns a new array, utils.py:36), or a different target device, is uploaded again;
+    invalidate_uploads() covers writes into the same buffer.  (SpG.from_scipy is stubbed: no GPU here.)"""
+    import scipy.sparse as sp
+    from surel_plus_b200 import train
+    calls = []
+
+    class _Fake:
+        def __init__(self, tag):
+            self.tag = tag
+    monkeypatch.setattr(train.SpG, "from_scipy", classmethod(lambda cls, x, device="cuda": calls.append(device) or _Fake(len(calls))))
+    train.invalidate_uploads()
+    x = sp.random(50, 50, density=0.1, format="csr", random_state=0)
+    a = train._as_spg(x, "cuda:0")
+    assert train._as_spg(x, "cuda:0") is a and len(calls) == 1              # cached by object + buffers
+    x.data = (x.data + 0.1) / (x.data.max() + 0.1)                          # utils.py:36
+    b = train._as_spg(x, "cuda:0")
+    assert b is not a and len(calls) == 2
+    assert train._as_spg(x, "cuda:1") is not b and len(calls) == 3          # the device is part of the key
+    x.data[:] = 0.5                                                         # in place: invisible ...
+    assert len(calls) == 3 and train._as_spg(x, "cuda:1") is not None and len(calls) == 3
+    train.invalidate_uploads()                                              # ... until told
+    train._as_spg(x, "cuda:1")
+    assert len(calls) == 4
+    train.invalidate_uploads()
